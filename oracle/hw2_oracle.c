@@ -1,0 +1,238 @@
+/*
+ * hw2_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C CPU restatement of the reference pairwise aligner
+ * (/root/reference/Local_Global_Alignment/hw2.cpp) used only as the parity
+ * checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.
+ * Nothing under bioinformatics-algorithms_b200/ links, imports or executes it.
+ *
+ * Parity status: PINNED.  tests/test_oracle.py checks this restatement against
+ *   - the reference's shipped golden files (global.txt / local.txt),
+ *   - SURVEY.md Appendix B known-answer vectors,
+ *   - tests/golden/*.json, produced by the UNMODIFIED reference binary
+ *     (oracle/_ref/hw2, built by oracle/Makefile from the reference sources
+ *     where they lie) via tests/golden/make_golden.py,
+ *   - and, when oracle/_ref/hw2 is present, thousands of live 1-pair runs.
+ *
+ * Unlike the reference (which only prints the batch winner) every function
+ * here reports per-pair results so the CUDA path can be checked pair by pair.
+ *
+ * Conventions shared with include/b2align.h:
+ *   ops are produced in TRACEBACK order (alignment end -> start), one byte
+ *   each: 'M' diagonal, 'D' pattern base over '-', 'I' '-' over text base
+ *   (hw2.cpp:164-180, :240-256 -- the reference's own letters).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+typedef struct {
+    int32_t  score;     /* hw2.cpp:186 (global), :225-229 (local)            */
+    uint32_t end_i;     /* cell where the traceback starts (1-based rows)    */
+    uint32_t end_j;
+    uint32_t start_i;   /* cell where the traceback stops                    */
+    uint32_t start_j;
+    int32_t  overlap;   /* overlapLongestExactMatch, hw2.cpp:267-278         */
+    uint32_t n_ops;
+} orc_result;
+
+/* Needleman-Wunsch fill + traceback: hw2.cpp:118-190. Tie order d > l > u. */
+static int orc_global(const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t n,
+                      int match, int mismatch, int gap, orc_result* res, uint8_t* ops)
+{
+    size_t W = (size_t)n + 1;
+    int32_t* dp = (int32_t*)malloc(sizeof(int32_t) * (m + 1) * W);
+    char*    tb = (char*)malloc((size_t)(m + 1) * W);
+    if (!dp || !tb) { free(dp); free(tb); return -1; }
+    memset(tb, ' ', (size_t)(m + 1) * W);
+    /* hw2.cpp:125-136 (size_t * int wraps back to the right int, :126) */
+    for (uint32_t i = 0; i <= m; ++i) { dp[i * W] = (int32_t)((int64_t)i * gap); if (i) tb[i * W] = 'u'; }
+    for (uint32_t j = 0; j <= n; ++j) { dp[j] = (int32_t)((int64_t)j * gap);     if (j) tb[j] = 'l'; }
+    /* hw2.cpp:138-156 */
+    for (uint32_t i = 1; i <= m; ++i) {
+        for (uint32_t j = 1; j <= n; ++j) {
+            int up   = dp[(i - 1) * W + j] + gap;
+            int left = dp[i * W + j - 1] + gap;
+            int v    = dp[(i - 1) * W + j - 1] + (p[i - 1] == t[j - 1] ? match : mismatch);
+            char d = 'd';
+            if (left > v) { v = left; d = 'l'; }
+            if (up > v)   { v = up;   d = 'u'; }
+            dp[i * W + j] = v; tb[i * W + j] = d;
+        }
+    }
+    /* hw2.cpp:158-181 */
+    uint32_t ti = m, tj = n, k = 0;
+    int cur = 0, best = 0;
+    while (ti > 0 || tj > 0) {
+        char d = tb[ti * W + tj];
+        if (ti > 0 && tj > 0 && d == 'd') {
+            ops[k++] = 'M';
+            /* overlapLongestExactMatch hw2.cpp:267-278 (direction-agnostic) */
+            if (p[ti - 1] == t[tj - 1] && p[ti - 1] != '-') { if (++cur > best) best = cur; } else cur = 0;
+            --ti; --tj;
+        } else if (ti > 0 && d == 'u') { ops[k++] = 'D'; cur = 0; --ti; }
+        else if (tj > 0 && d == 'l')   { ops[k++] = 'I'; cur = 0; --tj; }
+        else { free(dp); free(tb); return -2; } /* reference would spin forever */
+    }
+    res->score = dp[(size_t)m * W + n];          /* hw2.cpp:186 */
+    res->end_i = m; res->end_j = n; res->start_i = 0; res->start_j = 0;
+    res->overlap = best; res->n_ops = k;
+    free(dp); free(tb);
+    return 0;
+}
+
+/* Smith-Waterman fill + arg-max + traceback: hw2.cpp:192-265. Tie order 0 > d > u > l. */
+static int orc_local(const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t n,
+                     int match, int mismatch, int gap, orc_result* res, uint8_t* ops)
+{
+    size_t W = (size_t)n + 1;
+    int32_t* dp = (int32_t*)calloc((size_t)(m + 1) * W, sizeof(int32_t));
+    char*    tb = (char*)malloc((size_t)(m + 1) * W);
+    if (!dp || !tb) { free(dp); free(tb); return -1; }
+    memset(tb, ' ', (size_t)(m + 1) * W);
+    int score = 0; uint32_t bi = 0, bj = 0;       /* hw2.cpp:202-203 */
+    for (uint32_t i = 1; i <= m; ++i) {
+        for (uint32_t j = 1; j <= n; ++j) {
+            int diag = dp[(i - 1) * W + j - 1] + (p[i - 1] == t[j - 1] ? match : mismatch);
+            int up   = dp[(i - 1) * W + j] + gap;
+            int left = dp[i * W + j - 1] + gap;
+            int ul = up > left ? up : left;
+            int v  = diag > ul ? diag : ul;
+            if (v < 0) v = 0;                      /* hw2.cpp:211 */
+            dp[i * W + j] = v;
+            char d;                                /* hw2.cpp:214-222 */
+            if (v == 0) d = '0'; else if (v == diag) d = 'd'; else if (v == up) d = 'u'; else d = 'l';
+            tb[i * W + j] = d;
+            if (v > score) { score = v; bi = i; bj = j; } /* hw2.cpp:225-229 */
+        }
+    }
+    uint32_t ti = bi, tj = bj, k = 0;
+    int cur = 0, best = 0;
+    /* hw2.cpp:239-257 */
+    while (ti > 0 && tj > 0 && dp[ti * W + tj] != 0) {
+        char d = tb[ti * W + tj];
+        if (d == 'd') {
+            ops[k++] = 'M';
+            if (p[ti - 1] == t[tj - 1] && p[ti - 1] != '-') { if (++cur > best) best = cur; } else cur = 0;
+            --ti; --tj;
+        } else if (d == 'u') { ops[k++] = 'D'; cur = 0; --ti; }
+        else if (d == 'l')   { ops[k++] = 'I'; cur = 0; --tj; }
+        else { free(dp); free(tb); return -2; }
+    }
+    res->score = score; res->end_i = bi; res->end_j = bj; res->start_i = ti; res->start_j = tj;
+    res->overlap = best; res->n_ops = k;
+    free(dp); free(tb);
+    return 0;
+}
+
+/* mode 0 = global (-g), 1 = local (-l). ops must hold m+n bytes. */
+int orc_align(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t n,
+              int match, int mismatch, int gap, orc_result* res, uint8_t* ops)
+{
+    return mode == 0 ? orc_global(p, m, t, n, match, mismatch, gap, res, ops)
+                     : orc_local(p, m, t, n, match, mismatch, gap, res, ops);
+}
+
+/* Linear-memory score(+end cell) only, for sizes where the full matrices do
+ * not fit: same recurrences (hw2.cpp:138-156 / :205-231), two rows. */
+int orc_score_only(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t n,
+                   int match, int mismatch, int gap, orc_result* res)
+{
+    int32_t* row = (int32_t*)malloc(sizeof(int32_t) * ((size_t)n + 1));
+    if (!row) return -1;
+    int score = 0; uint32_t bi = 0, bj = 0;
+    for (uint32_t j = 0; j <= n; ++j) row[j] = mode == 0 ? (int32_t)((int64_t)j * gap) : 0;
+    for (uint32_t i = 1; i <= m; ++i) {
+        int32_t diagv = row[0];
+        row[0] = mode == 0 ? (int32_t)((int64_t)i * gap) : 0;
+        for (uint32_t j = 1; j <= n; ++j) {
+            int d = diagv + (p[i - 1] == t[j - 1] ? match : mismatch);
+            int u = row[j] + gap, l = row[j - 1] + gap;
+            int v = d; if (l > v) v = l; if (u > v) v = u;
+            if (mode != 0) { if (v < 0) v = 0; if (v > score) { score = v; bi = i; bj = j; } }
+            diagv = row[j]; row[j] = v;
+        }
+    }
+    memset(res, 0, sizeof(*res));
+    if (mode == 0) { res->score = row[n]; res->end_i = m; res->end_j = n; }
+    else { res->score = score; res->end_i = bi; res->end_j = bj; }
+    free(row);
+    return 0;
+}
+
+/* prepareCigarString, hw2.cpp:59-78: RLE of the op list read back to front. */
+size_t orc_cigar(const uint8_t* ops, uint32_t n_ops, char* out, size_t cap)
+{
+    size_t w = 0;
+    if (cap) out[0] = 0;
+    if (n_ops == 0) return 0;
+    uint32_t count = 1; uint8_t cur = ops[n_ops - 1];
+    for (int64_t i = (int64_t)n_ops - 2; i >= -1; --i) {
+        if (i >= 0 && ops[i] == cur) { ++count; continue; }
+        w += (size_t)snprintf(out + (w < cap ? w : cap), w < cap ? cap - w : 0, "%u%c", count, cur);
+        if (i >= 0) { cur = ops[i]; count = 1; }
+    }
+    return w;
+}
+
+/* prepareMDZString, hw2.cpp:80-116, restated on (ops, raw sequences, start cell)
+ * instead of the two aligned strings: column c of the alignment holds pattern
+ * base p[pi] for M/D and text base t[tj] for M/I. */
+size_t orc_mdz(const uint8_t* ops, uint32_t n_ops, const uint8_t* p, const uint8_t* t,
+               uint32_t start_i, uint32_t start_j, char* out, size_t cap)
+{
+    size_t w = 0; int run = 0;
+    uint32_t pi = start_i, tj = start_j;
+    int64_t c = (int64_t)n_ops - 1;                 /* forward order = reversed list (hw2.cpp:81) */
+#define EMIT(...) do { w += (size_t)snprintf(out + (w < cap ? w : cap), w < cap ? cap - w : 0, __VA_ARGS__); } while (0)
+    while (c >= 0) {
+        if (ops[c] == 'M') {
+            if (p[pi] == t[tj]) ++run;              /* hw2.cpp:89-90 */
+            else { EMIT("%d%c", run, t[tj]); run = 0; } /* hw2.cpp:93-95: reference base */
+            ++pi; ++tj; --c;
+        } else if (ops[c] == 'D') {                 /* hw2.cpp:98-108 */
+            EMIT("%d^", run); run = 0;
+            while (c >= 0 && ops[c] == 'D') { EMIT("%c", p[pi]); ++pi; --c; }
+        } else { ++tj; --c; }                       /* hw2.cpp:109-112: I does not break the run */
+    }
+    EMIT("%d", run);                                /* hw2.cpp:114 */
+#undef EMIT
+    return w;
+}
+
+/* hw3.cpp:23-98 score path (3-state affine global, no E<->F transitions), two
+ * rows per state instead of six full matrices. */
+int orc_affine_score(const uint8_t* s1, uint32_t m, const uint8_t* s2, uint32_t n,
+                     int match, int mismatch, int gopen, int gext, int32_t* score)
+{
+    const int32_t NEG = INT32_MIN / 2;             /* hw3.cpp:16 */
+    size_t W = (size_t)n + 1;
+    int32_t* V = (int32_t*)malloc(sizeof(int32_t) * W * 6);
+    if (!V) return -1;
+    int32_t *Vp = V, *Fp = V + W, *Ep = V + 2 * W, *Vc = V + 3 * W, *Fc = V + 4 * W, *Ec = V + 5 * W;
+    Vp[0] = 0; Fp[0] = NEG; Ep[0] = NEG;            /* hw3.cpp:40-41 */
+    for (uint32_t j = 1; j <= n; ++j) { Vp[j] = NEG; Fp[j] = NEG; Ep[j] = gopen + gext * (int32_t)(j - 1); } /* :48-53 */
+    for (uint32_t i = 1; i <= m; ++i) {
+        Vc[0] = NEG; Ec[0] = NEG; Fc[0] = gopen + gext * (int32_t)(i - 1);                                   /* :42-47 */
+        for (uint32_t j = 1; j <= n; ++j) {
+            int s = s1[i - 1] == s2[j - 1] ? match : mismatch;
+            int v = Vp[j - 1] + s;                                         /* :59-68 */
+            if (Fp[j - 1] + s > v) v = Fp[j - 1] + s;
+            if (Ep[j - 1] + s > v) v = Ep[j - 1] + s;
+            int f = Vp[j] + gopen + gext;                                  /* :70-75 */
+            if (Fp[j] + gext > f) f = Fp[j] + gext;
+            int e = Vc[j - 1] + gopen + gext;                              /* :77-82 */
+            if (Ec[j - 1] + gext > e) e = Ec[j - 1] + gext;
+            Vc[j] = v; Fc[j] = f; Ec[j] = e;
+        }
+        int32_t* x;
+        x = Vp; Vp = Vc; Vc = x; x = Fp; Fp = Fc; Fc = x; x = Ep; Ep = Ec; Ec = x;
+    }
+    int best = Vp[n];                                                      /* :86-98 */
+    if (Fp[n] > best) best = Fp[n];
+    if (Ep[n] > best) best = Ep[n];
+    *score = best;
+    free(V);
+    return 0;
+}

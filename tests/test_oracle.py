@@ -1,0 +1,112 @@
+"""Pins oracle/hw2_oracle.c (the CPU restatement) against the reference's own outputs.
+
+  * tests/golden/hw2_kat.json -- produced by the UNMODIFIED reference binary
+    (tests/golden/make_golden.py), including the shipped global.txt/local.txt;
+  * live differential runs against oracle/_ref/hw2 when it is present (build
+    container; it also travels to the GPU box as a prebuilt file).
+"""
+import json
+import os
+import random
+
+import pytest
+
+import oracle_binding as ob
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "hw2_kat.json")))
+MODE = {"g": ob.GLOBAL, "l": ob.LOCAL}
+
+
+def test_golden_single_pairs():
+    for c in KAT["single"]:
+        a = ob.align(MODE[c["mode"]], c["p"].encode("latin-1"), c["t"].encode("latin-1"), *c["s"])
+        assert (a.score, a.cigar, a.mdz) == (c["score"], c["cigar"], c["mdz"]), c
+
+
+def test_golden_multi_pair_selection():
+    for c in KAT["multi"]:
+        out = ob.render_file(MODE[c["mode"]], [x.encode() for x in c["patterns"]], [x.encode() for x in c["texts"]], *c["s"])
+        assert out.decode("latin-1") == c["output"], c
+
+
+def test_shipped_fixture_byte_exact():
+    sh = KAT["shipped"]
+    ps, ts = [x.encode() for x in sh["patterns"]], [x.encode() for x in sh["texts"]]
+    assert ob.render_file(ob.GLOBAL, ps, ts, *sh["s"]).decode() == sh["global_txt"]
+    assert ob.render_file(ob.LOCAL, ps, ts, *sh["s"]).decode() == sh["local_txt"]
+
+
+def test_score_only_matches_full():
+    rng = random.Random(7)
+    for _ in range(200):
+        p = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 60)))
+        t = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 80)))
+        s = rng.choice([(1, -1, -1), (2, -3, -4), (5, -4, -16)])
+        for mode in (ob.GLOBAL, ob.LOCAL):
+            a = ob.align(mode, p, t, *s)
+            assert ob.score_only(mode, p, t, *s) == (a.score, a.end_i, a.end_j)
+
+
+def test_empty_local_alignment():
+    a = ob.align(ob.LOCAL, b"acgt", b"ACGT", 1, -1, -1)
+    assert (a.score, a.cigar, a.mdz, a.n_ops if hasattr(a, "n_ops") else len(a.ops)) == (0, "", "0", 0)
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref/hw2 not built")
+def test_live_differential_vs_reference_binary(tmp_path):
+    """Thousands of cells of fresh random input through the real hw2 and the restatement."""
+    rng = random.Random(20261018)
+    for it in range(150):
+        k = rng.randint(1, 5)
+        alpha = rng.choice([b"ACGT", b"AC", b"A", b"ACGTN", b"ACDEFGHIKLMNPQRSTVWY"])
+        ps = [bytes(rng.choice(alpha) for _ in range(rng.randint(1, 120))) for _ in range(k)]
+        ts = [bytes(rng.choice(alpha) for _ in range(rng.randint(1, 200))) for _ in range(k)]
+        s = rng.choice([(1, -1, -1), (2, -3, -4), (5, -4, -16), (1, -2, 0), (0, 0, 0), (3, 1, -2), (-1, -1, -1)])
+        for flag, mode in (("-g", ob.GLOBAL), ("-l", ob.LOCAL)):
+            want = ob.run_hw2_binary(ob.REF_HW2, flag, ps, ts, *s, tmp_path)
+            assert ob.render_file(mode, ps, ts, *s) == want, (flag, ps, ts, s)
+
+
+@pytest.mark.skipif(not os.path.exists(ob.REF_HW3), reason="oracle/_ref/hw3 not built")
+def test_affine_score_restatement_matches_hw3_centre_choice(tmp_path):
+    """hw3 prints no scores; its centre choice (first line of the PHYLIP body) is the arg-max of the
+    distance-stage sums (hw3.cpp:231-251), so it pins orc_affine_score on whole batches."""
+    import subprocess
+    rng = random.Random(3)
+    for it in range(25):
+        k = rng.randint(3, 6)
+        base = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(20, 60)))
+        seqs = []
+        for _ in range(k):
+            s = bytearray(base)
+            for _ in range(rng.randint(0, 12)):
+                pos = rng.randrange(len(s))
+                r = rng.random()
+                if r < 0.5:
+                    s[pos] = rng.choice(b"ACGT")
+                elif r < 0.75 and len(s) > 5:
+                    del s[pos]
+                else:
+                    s.insert(pos, rng.choice(b"ACGT"))
+            seqs.append(bytes(s))
+        sc = rng.choice([(5, -4, -16, -4), (1, -1, -2, -1), (2, -3, -5, -2)])
+        fin, fout = tmp_path / "in.fa", tmp_path / "out.phy"
+        with open(fin, "wb") as f:
+            for i, s in enumerate(seqs):
+                f.write(b">s%d\n" % i + s + b"\n")
+        subprocess.check_call([ob.REF_HW3, "-i", str(fin), "-o", str(fout), "-s", "%d:%d:%d:%d" % sc],
+                              stdout=subprocess.DEVNULL)
+        lines = open(fout).read().split("\n")
+        centre_name = lines[1].split()[0]
+        sums = [0] * k
+        for i in range(k):
+            for j in range(i + 1, k):
+                v = ob.affine_score(seqs[i], seqs[j], *sc)
+                sums[i] += v
+                sums[j] += v
+        best, idx = None, -1
+        for i, v in enumerate(sums):      # first strict max, hw3.cpp:244-251
+            if best is None or v > best:
+                best, idx = v, i
+        assert centre_name == "s%d" % idx, (seqs, sc, sums, lines[:3])
