@@ -1,0 +1,268 @@
+"""bioinformatics-algorithms_b200 -- B200-native pairwise alignment engine (Python harness side).
+
+Thin ctypes binding over the C ABI in include/b2align.h (libb2align.so, built in-tree by
+`make -C bioinformatics-algorithms_b200`).  The product is the shared library + the `hw2`
+drop-in binary; this module exists for tests, bench.py and scripting.  It mirrors the
+reference's function seam (hw2.cpp:118, :192) with one-pair shims and exposes the batch call
+that replaces the loop hw2.cpp:328-338.
+
+There is no CPU fallback: importing works without a GPU (so symbols can be inspected), but
+creating an Engine raises if the library or a CUDA device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb2align.so")
+HW2_BIN = os.path.join(HERE, "bin", "hw2")
+
+GLOBAL, LOCAL = 0, 1
+WANT_OPS = 1
+
+RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<u4"), ("end_j", "<u4"), ("start_i", "<u4"),
+                         ("start_j", "<u4"), ("overlap", "<i4"), ("n_ops", "<u4"), ("path", "<u4")])
+
+EXPORTS = ["b2a_device_count", "b2a_create", "b2a_destroy", "b2a_last_error", "b2a_host_alloc", "b2a_host_free",
+           "b2a_align_batch", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
+           "b2a_batch_download", "b2a_batch_stats", "b2a_render_cigar", "b2a_render_mdz", "b2a_select_best",
+           "b2a_microbench_int16x2", "b2a_debug_copy_record"]
+
+
+class Params(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("match", C.c_int32), ("mismatch", C.c_int32), ("gap", C.c_int32),
+                ("flags", C.c_uint32)]
+
+
+class B2AError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libb2align.so (raises loudly if the CUDA extension was not built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2AError(f"{LIB_PATH} is missing: build it with `make -C {HERE}` (no CPU fallback exists)")
+        lib = C.CDLL(LIB_PATH)
+        lib.b2a_create.restype = C.c_void_p
+        lib.b2a_create.argtypes = [C.c_int]
+        lib.b2a_destroy.argtypes = [C.c_void_p]
+        lib.b2a_last_error.restype = C.c_char_p
+        lib.b2a_last_error.argtypes = [C.c_void_p]
+        lib.b2a_host_alloc.restype = C.c_void_p
+        lib.b2a_host_alloc.argtypes = [C.c_size_t]
+        lib.b2a_host_free.argtypes = [C.c_void_p]
+        P = C.c_void_p
+        lib.b2a_align_batch.argtypes = [P, C.POINTER(Params), P, P, P, P, C.c_uint64, P]
+        lib.b2a_batch_upload.argtypes = [P, C.POINTER(Params), P, P, P, P, C.c_uint64]
+        lib.b2a_batch_run.argtypes = [P, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        lib.b2a_batch_download.argtypes = [P, P]
+        lib.b2a_batch_stats.argtypes = [P] + [C.POINTER(C.c_uint64)] * 5
+        lib.b2a_fetch_ops.restype = C.c_int64
+        lib.b2a_fetch_ops.argtypes = [P, C.c_uint64, P, C.c_uint64]
+        lib.b2a_copy_ops.restype = C.c_int64
+        lib.b2a_copy_ops.argtypes = [P, P, C.c_uint64, P]
+        lib.b2a_render_cigar.restype = C.c_int64
+        lib.b2a_render_cigar.argtypes = [C.c_char_p, C.c_uint64, P, C.c_uint64]
+        lib.b2a_render_mdz.restype = C.c_int64
+        lib.b2a_render_mdz.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, P, C.c_uint64]
+        lib.b2a_select_best.restype = C.c_int64
+        lib.b2a_select_best.argtypes = [C.c_int32, P, C.c_uint64]
+        lib.b2a_microbench_int16x2.argtypes = [P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+        if hasattr(lib, "b2a_score_batch"):
+            lib.b2a_score_batch.argtypes = [P, C.POINTER(Params), P, P, P, P, C.c_uint64, P]
+        if hasattr(lib, "b2a_affine_score_batch"):
+            lib.b2a_affine_score_batch.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, P, P, P, C.c_uint64, P]
+        _lib = lib
+    return _lib
+
+
+def pack(seqs):
+    """list of bytes -> (uint8 bytes, uint64 offsets[n+1]) in the layout b2a_align_batch takes."""
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if len(seqs):
+        np.cumsum([len(s) for s in seqs], out=off[1:])
+    data = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy() if len(seqs) else np.zeros(0, np.uint8)
+    return data, off
+
+
+def pinned_empty(n, dtype):
+    """numpy array over cudaHostAlloc'ed memory (freed when the array's base object dies)."""
+    lib = load_library()
+    dt = np.dtype(dtype)
+    nbytes = max(int(n) * dt.itemsize, 1)
+    ptr = lib.b2a_host_alloc(nbytes)
+    if not ptr:
+        raise B2AError("b2a_host_alloc failed")
+
+    class _Owner:
+        def __init__(self, p):
+            self.p = p
+
+        def __del__(self):
+            try:
+                lib.b2a_host_free(self.p)
+            except Exception:
+                pass
+    buf = (C.c_uint8 * nbytes).from_address(ptr)
+    buf._owner = _Owner(ptr)
+    return np.frombuffer(buf, dtype=dt, count=int(n))
+
+
+def unpack_ops(words, off, k, n_ops):
+    """2-bit device ops of pair k -> b'MDI...' in traceback order."""
+    w = words[int(off[k]): int(off[k]) + (int(n_ops) + 15) // 16]
+    if n_ops == 0:
+        return b""
+    codes = (np.repeat(w, 16) >> np.tile(np.arange(0, 32, 2, dtype=np.uint32), len(w))) & 3
+    return np.frombuffer(b"MDI?", dtype=np.uint8)[codes[:int(n_ops)]].tobytes()
+
+
+def render_cigar(ops: bytes) -> str:
+    lib = load_library()
+    cap = 24 * (len(ops) + 2)
+    buf = C.create_string_buffer(cap)
+    n = lib.b2a_render_cigar(ops, len(ops), buf, cap)
+    if n < 0:
+        raise B2AError("b2a_render_cigar failed")
+    return buf.raw[:n].decode("latin-1")
+
+
+def render_mdz(ops: bytes, pattern: bytes, text: bytes, start_i: int, start_j: int) -> str:
+    lib = load_library()
+    cap = 24 * (len(ops) + 2)
+    buf = C.create_string_buffer(cap)
+    n = lib.b2a_render_mdz(ops, len(ops), pattern, text, start_i, start_j, buf, cap)
+    if n < 0:
+        raise B2AError("b2a_render_mdz failed")
+    return buf.raw[:n].decode("latin-1")
+
+
+def aligned_strings(ops: bytes, pattern: bytes, text: bytes, start_i: int, start_j: int):
+    """alignedPattern / alignedReference of struct AlignmentResult (hw2.cpp:17-23) from the op list."""
+    ap, ar = bytearray(), bytearray()
+    i, j = start_i, start_j
+    for op in reversed(ops):
+        if op == 0x4D:      # M
+            ap.append(pattern[i]); ar.append(text[j]); i += 1; j += 1
+        elif op == 0x44:    # D
+            ap.append(pattern[i]); ar.append(0x2D); i += 1
+        else:               # I
+            ap.append(0x2D); ar.append(text[j]); j += 1
+    return bytes(ap), bytes(ar)
+
+
+class AlignmentResult:
+    """Mirror of the reference's struct AlignmentResult (hw2.cpp:17-23)."""
+    __slots__ = ("score", "alignedPattern", "alignedReference", "cigar", "mdz", "record", "ops")
+
+
+class Engine:
+    """One context on one GPU (b2a_create / b2a_destroy)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.ctx = self.lib.b2a_create(int(device))
+        if not self.ctx:
+            raise B2AError(f"b2a_create({device}) failed: no usable sm_100 CUDA device (there is no CPU fallback)")
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.b2a_destroy(self.ctx)
+            self.ctx = None
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise B2AError(f"{what} failed (rc={rc}): {self.lib.b2a_last_error(self.ctx).decode()}")
+        return rc
+
+    # -- the batch call that replaces hw2.cpp:328-338 --
+    def align_packed(self, mode, pat, pat_off, txt, txt_off, match, mismatch, gap, want_ops=False, results=None):
+        n = len(pat_off) - 1
+        if results is None:
+            results = np.empty(n, dtype=RESULT_DTYPE)
+        prm = Params(mode, match, mismatch, gap, WANT_OPS if want_ops else 0)
+        self._check(self.lib.b2a_align_batch(self.ctx, C.byref(prm), pat.ctypes.data, pat_off.ctypes.data,
+                                             txt.ctypes.data, txt_off.ctypes.data, n, results.ctypes.data), "b2a_align_batch")
+        return results
+
+    def align_batch(self, mode, patterns, texts, match, mismatch, gap, want_ops=True):
+        """lists of bytes -> (results recarray, list of op byte-strings in traceback order or None)."""
+        assert len(patterns) == len(texts)
+        pat, po = pack(patterns)
+        txt, to = pack(texts)
+        res = self.align_packed(mode, pat, po, txt, to, match, mismatch, gap, want_ops)
+        ops = None
+        if want_ops:
+            words, off = self.copy_ops(len(patterns))
+            ops = [unpack_ops(words, off, k, res["n_ops"][k]) for k in range(len(patterns))]
+        return res, ops
+
+    def copy_ops(self, n_pairs):
+        total = self._check(self.lib.b2a_copy_ops(self.ctx, None, 0, None), "b2a_copy_ops")
+        words = np.empty(max(total, 1), dtype=np.uint32)
+        off = np.empty(n_pairs + 1, dtype=np.uint64)
+        self._check(self.lib.b2a_copy_ops(self.ctx, words.ctypes.data, total, off.ctypes.data), "b2a_copy_ops")
+        return words, off
+
+    def fetch_ops(self, pair, n_ops):
+        buf = C.create_string_buffer(int(n_ops) + 1)
+        n = self._check(self.lib.b2a_fetch_ops(self.ctx, pair, buf, int(n_ops)), "b2a_fetch_ops")
+        return buf.raw[:n]
+
+    # -- device-resident variant, for kernel-only timing --
+    def upload(self, mode, pat, pat_off, txt, txt_off, match, mismatch, gap, want_ops=False):
+        prm = Params(mode, match, mismatch, gap, WANT_OPS if want_ops else 0)
+        self._check(self.lib.b2a_batch_upload(self.ctx, C.byref(prm), pat.ctypes.data, pat_off.ctypes.data,
+                                              txt.ctypes.data, txt_off.ctypes.data, len(pat_off) - 1), "b2a_batch_upload")
+
+    def run(self):
+        f, t = C.c_float(), C.c_float()
+        self._check(self.lib.b2a_batch_run(self.ctx, C.byref(f), C.byref(t)), "b2a_batch_run")
+        return f.value, t.value
+
+    def download(self, n_pairs, results=None):
+        if results is None:
+            results = np.empty(n_pairs, dtype=RESULT_DTYPE)
+        self._check(self.lib.b2a_batch_download(self.ctx, results.ctypes.data), "b2a_batch_download")
+        return results
+
+    def stats(self):
+        v = [C.c_uint64() for _ in range(5)]
+        self.lib.b2a_batch_stats(self.ctx, *[C.byref(x) for x in v])
+        return dict(zip(("launches", "cells", "fill_bytes", "h2d_bytes", "d2h_bytes"), (x.value for x in v)))
+
+    def microbench(self, kind=0):
+        g, mhz = C.c_double(), C.c_float()
+        self._check(self.lib.b2a_microbench_int16x2(self.ctx, kind, C.byref(g), C.byref(mhz)), "b2a_microbench_int16x2")
+        return g.value, mhz.value
+
+    # -- one-pair shims with the reference's own names and argument order (hw2.cpp:118, :192) --
+    def _one(self, mode, pattern, reference, matchScore, mismatchScore, gapPenalty):
+        res, ops = self.align_batch(mode, [pattern], [reference], matchScore, mismatchScore, gapPenalty, True)
+        r = AlignmentResult()
+        r.record, r.ops, r.score = res[0], ops[0], int(res["score"][0])
+        si, sj = int(res["start_i"][0]), int(res["start_j"][0])
+        r.alignedPattern, r.alignedReference = aligned_strings(ops[0], pattern, reference, si, sj)
+        r.cigar = render_cigar(ops[0])
+        r.mdz = render_mdz(ops[0], pattern, reference, si, sj)
+        return r
+
+    def globalAlignmentNeedlemanWunsch(self, patterns, references, matchScore, mismatchScore, gapPenalty):
+        return self._one(GLOBAL, patterns, references, matchScore, mismatchScore, gapPenalty)
+
+    def localAlignmentSmithWaterman(self, patterns, references, matchScore, mismatchScore, gapPenalty):
+        return self._one(LOCAL, patterns, references, matchScore, mismatchScore, gapPenalty)
+
+
+def select_best(mode, results):
+    lib = load_library()
+    res = np.ascontiguousarray(results)
+    return int(lib.b2a_select_best(mode, res.ctypes.data, len(res)))

@@ -1,0 +1,158 @@
+// hw2_main.cpp -- drop-in replacement for the reference CLI (Local_Global_Alignment/hw2.cpp:280-403).
+//
+//   hw2 -g|-l -p <patterns.fasta> -t <texts.fasta> -o <output.txt> -s <match> <mismatch> <gap>
+//
+// Same argv grammar, FASTA semantics, stderr texts, exit codes and output bytes as the reference
+// (SURVEY.md Appendix A); the per-pair alignment work (hw2.cpp:328-357) goes through the C ABI in
+// include/b2align.h to the sm_100a kernels, sharded over every visible GPU (contiguous pair ranges,
+// one host thread + context per device, host-side first-index arg-max).  No CPU alignment path:
+// without a usable GPU the program says so on stderr and exits 1.
+#include <cctype>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "b2align.h"
+
+namespace {
+
+struct FastaBatch {                      // sequences only, concatenated, with offsets (count + 1)
+    std::vector<uint8_t> bytes;
+    std::vector<uint64_t> off{0};
+    size_t count() const { return off.size() - 1; }
+    std::string seq(size_t k) const { return std::string(bytes.begin() + off[k], bytes.begin() + off[k + 1]); }
+};
+
+// hw2.cpp:25-57 semantics: trailing CR/whitespace stripped per line, blank lines skipped, '>' lines
+// flush the current record only if it is non-empty, everything else is appended verbatim.
+bool load_fasta(const std::string& path, FastaBatch& out)
+{
+    std::ifstream in(path.c_str(), std::ios::binary);
+    if (!in) return false;
+    std::string line;
+    bool open_record = false;            // bytes appended since the last flush
+    while (std::getline(in, line)) {
+        size_t e = line.size();
+        while (e > 0 && (line[e - 1] == '\r' || std::isspace((unsigned char)line[e - 1]))) --e;
+        if (e == 0) continue;
+        if (line[0] == '>') {
+            if (open_record) { out.off.push_back(out.bytes.size()); open_record = false; }
+        } else {
+            out.bytes.insert(out.bytes.end(), line.begin(), line.begin() + e);
+            open_record = true;
+        }
+    }
+    if (open_record) out.off.push_back(out.bytes.size());
+    return true;
+}
+
+struct Shard {
+    uint64_t first = 0, count = 0;
+    int rc = 0;
+    std::string err;
+};
+
+} // namespace
+
+int main(int argc, char** argv)
+{
+    if (argc < 9) {
+        std::cerr << "Usage: " << argv[0] << " -g|-l -p <patterns.fasta> -t <texts.fasta> -o <output.txt> -s <match> <mismatch> <gap>" << std::endl;
+        return 1;
+    }
+    bool global = false, local = false;
+    std::string pattern_path, text_path, out_path;
+    int match = 0, mismatch = 0, gap = 0;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (a == "-g") global = true;
+        else if (a == "-l") local = true;
+        else if (a == "-p" && i + 1 < argc) pattern_path = argv[++i];
+        else if (a == "-t" && i + 1 < argc) text_path = argv[++i];
+        else if (a == "-o" && i + 1 < argc) out_path = argv[++i];
+        else if (a == "-s" && i + 3 < argc) { match = std::atoi(argv[++i]); mismatch = std::atoi(argv[++i]); gap = std::atoi(argv[++i]); }
+    }
+
+    FastaBatch pats, txts;
+    if (!load_fasta(pattern_path, pats)) { std::cerr << "Error: Cannot open file " << pattern_path << std::endl; return 1; }
+    if (!load_fasta(text_path, txts))    { std::cerr << "Error: Cannot open file " << text_path << std::endl; return 1; }
+    if (pats.count() != txts.count()) {
+        std::cerr << "Error: Number of patterns and references do not match." << std::endl;
+        return 1;
+    }
+    const uint64_t n_pairs = pats.count();
+    const int mode = global ? B2A_MODE_GLOBAL : B2A_MODE_LOCAL;       // -g wins when both are given (hw2.cpp:331)
+
+    std::vector<b2a_result> results(n_pairs);
+    int64_t best = -1;
+    std::string cigar, mdz;
+    if (n_pairs > 0) {
+        int ndev = b2a_device_count();
+        if (ndev <= 0) { std::cerr << "Error: no usable CUDA device (this build has no CPU alignment path)" << std::endl; return 1; }
+        if ((uint64_t)ndev > n_pairs) ndev = (int)n_pairs;
+        std::vector<Shard> shards(ndev);
+        std::vector<b2a_ctx*> ctxs(ndev, nullptr);
+        std::vector<std::thread> th;
+        for (int d = 0; d < ndev; ++d) {
+            shards[d].first = n_pairs * d / ndev;
+            shards[d].count = n_pairs * (d + 1) / ndev - shards[d].first;
+            th.emplace_back([&, d]() {
+                Shard& s = shards[d];
+                b2a_ctx* ctx = b2a_create(d);
+                ctxs[d] = ctx;
+                if (!ctx) { s.rc = B2A_ERR_CUDA; s.err = "cannot create a context on device " + std::to_string(d); return; }
+                // rebase the shard's offsets so the device only receives its own bytes
+                std::vector<uint64_t> po(s.count + 1), to(s.count + 1);
+                for (uint64_t k = 0; k <= s.count; ++k) { po[k] = pats.off[s.first + k] - pats.off[s.first]; to[k] = txts.off[s.first + k] - txts.off[s.first]; }
+                b2a_params prm{mode, match, mismatch, gap, B2A_WANT_OPS};
+                s.rc = b2a_align_batch(ctx, &prm, pats.bytes.data() + pats.off[s.first], po.data(),
+                                       txts.bytes.data() + txts.off[s.first], to.data(), s.count, results.data() + s.first);
+                if (s.rc != B2A_OK) s.err = b2a_last_error(ctx);
+            });
+        }
+        for (auto& t : th) t.join();
+        for (int d = 0; d < ndev; ++d)
+            if (shards[d].rc != B2A_OK) {
+                std::cerr << "Error: alignment engine failed: " << shards[d].err << std::endl;
+                for (b2a_ctx* c : ctxs) b2a_destroy(c);
+                return 1;
+            }
+        best = b2a_select_best(mode, results.data(), n_pairs);         // ascending index order keeps "first strict max"
+        if (best >= 0) {
+            int d = 0;
+            while (d + 1 < ndev && (uint64_t)best >= shards[d + 1].first) ++d;
+            const b2a_result& r = results[best];
+            std::vector<char> ops(r.n_ops + 1);
+            if (b2a_fetch_ops(ctxs[d], (uint64_t)best - shards[d].first, ops.data(), r.n_ops) < 0) {
+                std::cerr << "Error: alignment engine failed: " << b2a_last_error(ctxs[d]) << std::endl;
+                for (b2a_ctx* c : ctxs) b2a_destroy(c);
+                return 1;
+            }
+            std::vector<char> buf(24ull * (r.n_ops + 2) + 64);
+            b2a_render_cigar(ops.data(), r.n_ops, buf.data(), buf.size());
+            cigar = buf.data();
+            b2a_render_mdz(ops.data(), r.n_ops, pats.bytes.data() + pats.off[best], txts.bytes.data() + txts.off[best],
+                           r.start_i, r.start_j, buf.data(), buf.size());
+            mdz = buf.data();
+        }
+        for (b2a_ctx* c : ctxs) b2a_destroy(c);
+    }
+
+    std::ofstream out(out_path.c_str(), std::ios::binary);
+    if (!out) { std::cerr << "Error: Cannot open output file " << out_path << std::endl; return 1; }
+    if ((global || local) && best >= 0) {
+        out << (global ? "Longest overlap:" : "Highest local alignment score:") << '\n'
+            << "pattern=" << pats.seq(best) << '\n'
+            << "reference=" << txts.seq(best) << '\n'
+            << "Score =" << results[best].score << '\n'
+            << "CIGAR =" << cigar << '\n'
+            << "MD:Z=" << mdz << '\n';
+    }
+    out.close();
+    return 0;
+}

@@ -1,0 +1,192 @@
+// short16_fill.cuh -- inter-pair batched DP fill for short pairs (sm_100a).
+//
+// Replaces the fill loops hw2.cpp:138-156 (NW) and hw2.cpp:205-231 (SW) for every pair of a batch.
+// One warp owns one PAIR-PAIR: two pairs of identical shape whose cells travel in the low/high
+// halves of s16x2 registers.  Lane L owns pattern rows L*R+1 .. L*R+R; the warp sweeps the text
+// as a skewed wavefront (lane L is at column q-L at step q), the row below a lane's band receives
+// its boundary through one __shfl_up_sync per step.  Per packed cell pair the ALU pipe sees
+//     PRMT            substitution score of both pairs from the text's 4-entry score tables
+//     VIADD.16x2      diagonal + score
+//     VIADDMNMX.S16x2 max(left + gap, .)
+//     VIADDMNMX.S16x2(.RELU for SW)  max(up + gap, .)   [+ VIMNMX.S16x2 row maximum for SW]
+// and the FMA pipe one IMAD that folds the new H into the row's delta word (see b2a_format.h
+// encode_word: the word of horizontal deltas is a polynomial in the packed H values, evaluated in
+// 32-bit ring arithmetic, so no masking, shifting or compare instruction is spent on traceback data).
+// Every 3 words a lane stores one 16-byte chunk {w0,w1,w2,anchor}; a warp store is 512 contiguous bytes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "b2a_format.h"
+
+namespace b2a {
+
+struct FillArgs {
+    const uint8_t*  pat;        // concatenated pattern bytes
+    const uint8_t*  txt;        // concatenated text bytes
+    const uint64_t* pat_off;    // per pair, n_pairs+1
+    const uint64_t* txt_off;
+    const PPDesc*   pps;        // pair-pairs of this launch (all with the same R)
+    const uint64_t* code_off;   // per pair-pair: first chunk of its record
+    Chunk*          codes;
+    uint32_t*       rowbest;    // local mode: [n_pp][R][32]
+    uint32_t        n_pp;
+    uint32_t        tbl_cap;    // score-table entries (columns) per warp in dynamic shared memory
+    int32_t         match, mismatch, gap, bias;
+    uint32_t        radix;      // 2^K, passed at run time so the word update stays an IMAD (FMA pipe)
+    uint8_t         sym[4];     // the (<= 4) distinct pattern symbols of the batch
+    int32_t         nsym;
+};
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));   // default mode: selector bit 3 replicates the sign
+    return d;
+}
+__device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xFFFFu) | ((uint32_t)v << 16); }
+
+constexpr int FILL_WARPS = 4;
+
+template <int R, int K, bool LOCAL>
+__global__ void __launch_bounds__(FILL_WARPS * 32)
+short16_fill_kernel(const FillArgs A)
+{
+    constexpr int F = Geo<K>::F, CS = Geo<K>::CS;
+    extern __shared__ uint2 s_tbl_all[];                 // [FILL_WARPS][tbl_cap]: per column (tableA, tableB)
+    __shared__ uint32_t s_tbl4[256];                     // byte -> 4 int8 scores against sym[0..3]
+
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int sc = (c < A.nsym && A.sym[c] == (uint8_t)b) ? A.match : A.mismatch;
+            w |= ((uint32_t)sc & 0xFFu) << (8 * c);
+        }
+        s_tbl4[b] = w;
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t pp = blockIdx.x * FILL_WARPS + warp;
+    if (pp >= A.n_pp) return;
+    uint2* tbl = s_tbl_all + (size_t)warp * A.tbl_cap;
+
+    const PPDesc d = A.pps[pp];
+    const uint32_t m = d.m, n = d.n;
+    const uint8_t* pa = A.pat + A.pat_off[d.a];
+    const uint8_t* pb = A.pat + A.pat_off[d.b];
+    const uint8_t* ta = A.txt + A.txt_off[d.a];
+    const uint8_t* tb = A.txt + A.txt_off[d.b];
+
+    for (uint32_t j = lane; j < n; j += 32) tbl[j] = make_uint2(s_tbl4[ta[j]], s_tbl4[tb[j]]);
+
+    // PRMT selectors of this lane's rows: byte0 = tableA[codeA], byte1 = its sign, byte2 = tableB[codeB], byte3 = its sign
+    uint32_t sel[R], H[R], best[R];
+    const uint32_t g2 = pack2(A.gap);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t i0 = (uint32_t)lane * R + r;     // 0-based row
+        uint32_t ca = 0, cb = 0;
+        if (i0 < m) {
+            const uint8_t xa = pa[i0], xb = pb[i0];
+#pragma unroll
+            for (int c = 1; c < 4; ++c) { if (xa == A.sym[c]) ca = c; if (xb == A.sym[c]) cb = c; }
+        }
+        sel[r] = ca | ((8u | ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
+        H[r] = LOCAL ? 0u : pack2(A.bias + (int)(i0 + 1) * A.gap);      // column-0 border, hw2.cpp:125-130
+        best[r] = 0u;
+    }
+    __syncwarp();
+
+    const uint32_t NC = num_chunks(n, CS);
+    Chunk* rec = A.codes + A.code_off[pp];
+    const uint32_t radix = A.radix;
+    const uint32_t g32 = (uint32_t)A.gap * 65537u;
+    uint32_t geo = 0, bpow = 1;
+#pragma unroll
+    for (int t = 0; t < F; ++t) geo = geo * radix + 1u;
+#pragma unroll
+    for (int t = 0; t < F - 1; ++t) bpow *= radix;
+    const uint32_t negGc = 0u - g32 * geo, negBpow = 0u - bpow, radm1 = radix - 1u;
+    const uint32_t bias32 = LOCAL ? 0u : (uint32_t)A.bias * 65537u;     // row-0 border b0(q) = bias32 + q*g32 (ring-exact)
+
+    uint32_t dgn = LOCAL ? 0u : (lane == 0 ? bias32 : pack2(A.bias + (int)((uint32_t)lane * R) * A.gap));   // H(L*R, 0)
+    const uint2* tcol = tbl - lane - 1;                   // tcol[q] = tables of column j = q - lane (index j-1)
+
+    // one wavefront step for this lane; ACTIVE_CHECK selects the ramp (predicated) flavour
+    auto step = [&](uint32_t q, uint32_t (&S)[R], int f, bool active) {
+        uint32_t up = __shfl_up_sync(0xFFFFFFFFu, H[R - 1], 1);
+        if (lane == 0) up = LOCAL ? 0u : bias32 + q * g32;              // row 0 border H(0, q), hw2.cpp:131-136
+        const uint32_t dg0 = dgn;
+        dgn = up;
+        if (active) {
+            const uint2 tw = tcol[q];
+            uint32_t dg = dg0, u = up;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t s  = prmt(tw.x, tw.y, sel[r]);
+                const uint32_t ds = __vadd2(dg, s);
+                dg = H[r];
+                const uint32_t a = __viaddmax_s16x2(H[r], g2, ds);
+                const uint32_t h = LOCAL ? __viaddmax_s16x2_relu(u, g2, a) : __viaddmax_s16x2(u, g2, a);
+                if (LOCAL) best[r] = __vmaxs2(best[r], h);
+                H[r] = h; u = h;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (f == 0) S[r] = H[r];
+            else if (f < F - 1) S[r] = S[r] * radix + H[r];
+        }
+    };
+
+    for (uint32_t c = 0; c < NC; ++c) {
+        const uint32_t q0 = c * CS;
+        uint32_t w0[R], w1[R];
+        if (q0 >= 32u && q0 + CS - 1 <= n) {
+            // steady state: every lane is inside its row range for the whole chunk
+#pragma unroll
+            for (int wi = 0; wi < 3; ++wi) {
+                uint32_t S[R], pre[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) pre[r] = H[r] * negBpow + negGc;
+#pragma unroll
+                for (int f = 0; f < F; ++f) step(q0 + wi * F + f, S, f, true);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t w = (F > 1 ? S[r] * radm1 : 0u) + H[r] + pre[r];
+                    if (wi == 0) w0[r] = w; else if (wi == 1) w1[r] = w;
+                    else {
+                        const uint4 v = make_uint4(w0[r], w1[r], w, H[r]);
+                        *reinterpret_cast<uint4*>(&rec[((uint32_t)r * NC + c) * 32u + lane]) = v;
+                    }
+                }
+            }
+        } else {
+            // ramp-up / ramp-down chunks: lanes outside 1 <= q - lane <= n keep their H frozen
+#pragma unroll 1
+            for (int wi = 0; wi < 3; ++wi) {
+                uint32_t S[R], pre[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) pre[r] = H[r] * negBpow + negGc;
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+                    const uint32_t q = q0 + wi * F + f;
+                    step(q, S, f, (uint32_t)(q - lane - 1u) < n);
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t w = (F > 1 ? S[r] * radm1 : 0u) + H[r] + pre[r];
+                    uint32_t* cw = reinterpret_cast<uint32_t*>(&rec[((uint32_t)r * NC + c) * 32u + lane]);
+                    cw[wi] = w;
+                    if (wi == 2) cw[3] = H[r];
+                }
+            }
+        }
+    }
+    if (LOCAL) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) A.rowbest[((size_t)pp * R + r) * 32u + lane] = best[r];
+    }
+}
+
+} // namespace b2a

@@ -1,0 +1,139 @@
+/*
+ * b2align.h -- C ABI of the B200-native pairwise alignment engine.
+ *
+ * Drop-in boundary for the hot path of gorkemsolun/Bioinformatics-Algorithms,
+ * Local_Global_Alignment/hw2.cpp.  The reference has no FFI; its seam is the
+ * per-pair function pair
+ *     AlignmentResult* globalAlignmentNeedlemanWunsch(const string&, const string&, int, int, int)   hw2.cpp:118
+ *     AlignmentResult* localAlignmentSmithWaterman   (const string&, const string&, int, int, int)   hw2.cpp:192
+ * called from the serial batch loop hw2.cpp:328-338.  A GPU cannot be fed one
+ * pair at a time, so the boundary is the BATCH: one call replaces the whole
+ * loop hw2.cpp:328-338 plus, per pair, overlapLongestExactMatch (hw2.cpp:267-278).
+ *
+ * Plain C, no exceptions, caller-owned buffers, int status (0 = ok, <0 = error).
+ * One b2a_ctx per host thread / GPU; a ctx is not thread-safe, the library is.
+ * There is NO CPU fallback: every entry point that computes fails with
+ * B2A_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef B2ALIGN_H
+#define B2ALIGN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2A_VERSION 1
+
+/* status codes */
+#define B2A_OK            0
+#define B2A_ERR_ARG      -1   /* bad argument (null pointer, inconsistent offsets, ...)        */
+#define B2A_ERR_CUDA     -2   /* CUDA runtime / no device; b2a_last_error() has the text      */
+#define B2A_ERR_NOMEM    -3   /* host or device allocation failed                             */
+#define B2A_ERR_RANGE    -4   /* scores outside the supported domain */
+#define B2A_ERR_STATE    -5   /* call order violated (e.g. fetch before a batch was run)      */
+
+/* alignment mode: hw2's -g / -l (hw2.cpp:292-295) */
+#define B2A_MODE_GLOBAL   0   /* Needleman-Wunsch, hw2.cpp:118-190, tie order d > l > u      */
+#define B2A_MODE_LOCAL    1   /* Smith-Waterman,   hw2.cpp:192-265, tie order 0 > d > u > l  */
+
+/* b2a_params.flags */
+#define B2A_WANT_OPS      1u  /* keep per-pair traceback ops on the device for b2a_fetch_ops / b2a_copy_ops */
+
+/* op codes, 2 bits each (the reference's own letters, hw2.cpp:164-180 / :240-256) */
+#define B2A_OP_M          0u  /* 'M' diagonal: pattern base over text base            */
+#define B2A_OP_D          1u  /* 'D' up:       pattern base over '-'                   */
+#define B2A_OP_I          2u  /* 'I' left:     '-' over text base                      */
+
+typedef struct b2a_ctx b2a_ctx;
+
+/* hw2's "-s <match> <mismatch> <gap>" (hw2.cpp:302-305): linear gap, raw byte equality (hw2.cpp:142, :208) */
+typedef struct b2a_params {
+    int32_t  mode;       /* B2A_MODE_*            */
+    int32_t  match;
+    int32_t  mismatch;
+    int32_t  gap;
+    uint32_t flags;      /* B2A_WANT_OPS or 0     */
+} b2a_params;
+
+/* One record per pair: everything struct AlignmentResult (hw2.cpp:17-23) carries, in index form.
+ * The aligned strings / CIGAR / MD:Z are rendered from (ops, raw sequences) by b2a_render_*. */
+typedef struct b2a_result {
+    int32_t  score;      /* hw2.cpp:186 dp[m][n] (global) / running max hw2.cpp:225-229 (local)      */
+    uint32_t end_i;      /* traceback start cell, 1-based rows (pattern) ...                         */
+    uint32_t end_j;      /* ... and columns (text): (m,n) global, first row-major arg-max local      */
+    uint32_t start_i;    /* cell where the traceback stopped: (0,0) global; H==0 or an edge local    */
+    uint32_t start_j;
+    int32_t  overlap;    /* overlapLongestExactMatch(alignedPattern, alignedReference), hw2.cpp:267  */
+    uint32_t n_ops;      /* alignment columns = length of the traceback op list                      */
+    uint32_t path;       /* which kernel family served the pair: 1 = short16 (s16x2), 2 = wide32     */
+} b2a_result;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int         b2a_device_count(void);                 /* usable CUDA devices, 0 if none / no driver     */
+b2a_ctx*    b2a_create(int device);                 /* NULL on failure (no CUDA device)               */
+void        b2a_destroy(b2a_ctx* ctx);
+const char* b2a_last_error(const b2a_ctx* ctx);     /* text of the last failure on this ctx           */
+
+/* Pinned host memory for batch inputs/outputs (optional; pageable memory works, staged). */
+void*       b2a_host_alloc(size_t bytes);
+void        b2a_host_free(void* p);
+
+/* ---- the batch call: replaces the loop hw2.cpp:328-338 ------------------------------------ */
+/* Pair k aligns pattern bytes pat[pat_off[k] .. pat_off[k+1]) against text bytes
+ * txt[txt_off[k] .. txt_off[k+1]) (index-wise zip, hw2.cpp:328-335).  All pointers are HOST
+ * pointers; offsets arrays hold n_pairs+1 entries.  results receives n_pairs records.
+ * Host->device copies, both kernels and the device->host copy of the records happen inside. */
+int b2a_align_batch(b2a_ctx* ctx, const b2a_params* prm,
+                    const uint8_t* pat, const uint64_t* pat_off,
+                    const uint8_t* txt, const uint64_t* txt_off,
+                    uint64_t n_pairs, b2a_result* results);
+
+/* After a batch run with B2A_WANT_OPS: traceback ops of one pair as ASCII 'M'/'D'/'I', in
+ * TRACEBACK order (alignment end -> start, exactly the reference's `tracebacks` vector,
+ * hw2.cpp:161).  Returns the op count, or <0.  ops_cap must be >= results[pair].n_ops. */
+int64_t b2a_fetch_ops(b2a_ctx* ctx, uint64_t pair, char* ops, uint64_t ops_cap);
+
+/* All pairs' ops in device format: 2-bit codes, op t of pair k at bits 2*(t%16) of word
+ * ops_words[ops_off[k] + t/16], traceback order.  ops_off (n_pairs+1 entries, may be NULL)
+ * receives the per-pair word offsets.  Returns the total word count (>=0) or <0; call with
+ * ops_words == NULL to query it. */
+int64_t b2a_copy_ops(b2a_ctx* ctx, uint32_t* ops_words, uint64_t cap_words, uint64_t* ops_off);
+
+/* ---- device-resident variant (kernel-only timing; inputs already in HBM) ------------------- */
+int b2a_batch_upload(b2a_ctx* ctx, const b2a_params* prm,
+                     const uint8_t* pat, const uint64_t* pat_off,
+                     const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs);
+int b2a_batch_run(b2a_ctx* ctx, float* fill_ms, float* traceback_ms);   /* CUDA-event times of this run */
+int b2a_batch_download(b2a_ctx* ctx, b2a_result* results);
+/* counters of the last run: kernels launched, algorithmic cells, bytes written by the fill kernel */
+int b2a_batch_stats(const b2a_ctx* ctx, uint64_t* kernel_launches, uint64_t* cells, uint64_t* fill_bytes,
+                    uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
+/* ---- result formatting: prepareCigarString hw2.cpp:59-78, prepareMDZString hw2.cpp:80-116 --- */
+/* ops = ASCII list in traceback order (as returned by b2a_fetch_ops). Return the string
+ * length (excluding NUL) or <0 if cap is too small. */
+int64_t b2a_render_cigar(const char* ops, uint64_t n_ops, char* out, uint64_t cap);
+int64_t b2a_render_mdz(const char* ops, uint64_t n_ops, const uint8_t* pattern, const uint8_t* text,
+                       uint32_t start_i, uint32_t start_j, char* out, uint64_t cap);
+
+/* Batch winner, hw2.cpp:326-357: key = overlap (global) / score (local), strict '>' from
+ * -1000000 so the lowest index wins ties; -1 for an empty batch. */
+int64_t b2a_select_best(int32_t mode, const b2a_result* results, uint64_t n_pairs);
+
+/* ---- measurement helper: sustained issue rate of the packed int16x2 DPX instructions ------- */
+/* Runs the microbenchmark kernel on ctx's device; *gops = 1e9 lane-instructions/s sustained by
+ * kind 0: VIADDMNMX.S16x2 only, 1: the fill kernel's ALU mix, 2: ALU mix + IMAD (both pipes). */
+int b2a_microbench_int16x2(b2a_ctx* ctx, int kind, double* gops, float* sm_mhz);
+
+/* ---- introspection for white-box tests: raw HBM record of the first short16 class --------- */
+/* Copies the delta/anchor chunks (and, in local mode, the per-row maxima) the fill kernel wrote.
+ * Returns the record size in bytes, or <0. */
+int64_t b2a_debug_copy_record(b2a_ctx* ctx, void* chunks, uint64_t chunk_bytes_cap, void* rowbest, uint64_t rowbest_bytes_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2ALIGN_H */

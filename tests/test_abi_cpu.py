@@ -1,0 +1,116 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/b2align.h declares, fails loudly without a GPU, and the host-only formatting/selection
+entry points agree with the oracle.  No compute calls here (no GPU in the build container)."""
+import ctypes as C
+import json
+import os
+import random
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from __graft_entry__ import load_package
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pkg = load_package()
+KAT = json.load(open(os.path.join(ROOT, "tests", "golden", "hw2_kat.json")))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b2align.h")).read()
+    declared = sorted(set(re.findall(r"\b(b2a_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 15
+    lib = pkg.load_library()
+    for name in declared:
+        assert hasattr(lib, name), f"libb2align.so does not export {name}"
+    assert sorted(pkg.EXPORTS) == declared
+
+
+def test_result_record_layout():
+    assert pkg.RESULT_DTYPE.itemsize == 32
+
+
+def test_no_cpu_fallback_without_gpu():
+    lib = pkg.load_library()
+    if lib.b2a_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.B2AError):
+        pkg.Engine(0)
+
+
+def test_render_matches_oracle_and_golden():
+    for c in KAT["single"]:
+        mode = ob.GLOBAL if c["mode"] == "g" else ob.LOCAL
+        p, t = c["p"].encode("latin-1"), c["t"].encode("latin-1")
+        a = ob.align(mode, p, t, *c["s"])
+        assert pkg.render_cigar(a.ops) == c["cigar"]
+        assert pkg.render_mdz(a.ops, p, t, a.start_i, a.start_j) == c["mdz"]
+
+
+def test_render_rejects_small_buffer():
+    lib = pkg.load_library()
+    buf = C.create_string_buffer(2)
+    assert lib.b2a_render_cigar(b"MMMMDDDD", 8, buf, 2) < 0
+
+
+def test_select_best_first_strict_max():
+    rng = random.Random(5)
+    for _ in range(200):
+        n = rng.randint(0, 12)
+        res = np.zeros(n, dtype=pkg.RESULT_DTYPE)
+        res["score"] = [rng.randint(-3, 4) for _ in range(n)]
+        res["overlap"] = [rng.randint(0, 3) for _ in range(n)]
+        for mode, key in ((pkg.GLOBAL, "overlap"), (pkg.LOCAL, "score")):
+            want, best = -1, -1000000
+            for k in range(n):
+                if res[key][k] > best:
+                    best, want = int(res[key][k]), k
+            assert pkg.select_best(mode, res) == want
+
+
+def test_aligned_strings_roundtrip():
+    a = ob.align(ob.GLOBAL, b"ATCAAGCGTCGGCATATGGC", b"ATCAGCGATCATCGGCATAT", 1, -1, -1)
+    ap, ar = pkg.aligned_strings(a.ops, b"ATCAAGCGTCGGCATATGGC", b"ATCAGCGATCATCGGCATAT", 0, 0)
+    assert ap.replace(b"-", b"") == b"ATCAAGCGTCGGCATATGGC" and ar.replace(b"-", b"") == b"ATCAGCGATCATCGGCATAT"
+    assert len(ap) == len(ar) == len(a.ops)
+
+
+# ---- hw2 drop-in CLI: everything that happens before the GPU is touched ----
+def run_cli(args, cwd):
+    return subprocess.run([pkg.HW2_BIN] + args, cwd=cwd, capture_output=True)
+
+
+def test_cli_usage_and_error_paths_match_reference(tmp_path):
+    if not os.path.exists(pkg.HW2_BIN):
+        pytest.skip("bin/hw2 not built")
+    cases = [
+        ["-g"],                                                                  # argc < 9 -> usage
+        ["-g", "-p", "nope.fa", "-t", "nope2.fa", "-o", "o.txt", "-s", "1", "-1", "-1"],     # unopenable pattern file
+        ["-l", "-p", "p.fa", "-t", "t2.fa", "-o", "o.txt", "-s", "1", "-1", "-1"],           # count mismatch
+        ["-l", "-p", "e.fa", "-t", "e.fa", "-o", "o.txt", "-s", "1", "-1", "-1"],            # zero pairs -> empty file
+        ["-g", "-p", "e.fa", "-t", "e.fa", "-o", "nodir/o.txt", "-s", "1", "-1", "-1"],      # unopenable output
+        ["-p", "e.fa", "-t", "e.fa", "-o", "o2.txt", "-s", "1", "-1", "-1", "extra"],        # neither -g nor -l
+    ]
+    (tmp_path / "p.fa").write_bytes(b">a\nACGT\n>b\nAC\n")
+    (tmp_path / "t2.fa").write_bytes(b">a\nACGT\n")
+    (tmp_path / "e.fa").write_bytes(b">only header\n\n")
+    for args in cases:
+        for f in ("o.txt", "o2.txt"):
+            if (tmp_path / f).exists():
+                (tmp_path / f).unlink()
+        mine = run_cli(args, tmp_path)
+        outs = {f: (tmp_path / f).read_bytes() if (tmp_path / f).exists() else None for f in ("o.txt", "o2.txt")}
+        if ob.have_ref():
+            for f in ("o.txt", "o2.txt"):
+                if (tmp_path / f).exists():
+                    (tmp_path / f).unlink()
+            ref = subprocess.run([ob.REF_HW2] + args, cwd=tmp_path, capture_output=True)
+            refouts = {f: (tmp_path / f).read_bytes() if (tmp_path / f).exists() else None for f in ("o.txt", "o2.txt")}
+            assert mine.returncode == ref.returncode, args
+            assert mine.stderr.replace(pkg.HW2_BIN.encode(), b"X") == ref.stderr.replace(ob.REF_HW2.encode(), b"X"), args
+            assert outs == refouts, args
+        else:
+            assert mine.returncode in (0, 1)

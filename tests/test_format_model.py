@@ -1,0 +1,145 @@
+"""CPU tests of the short16 HBM record + the traceback walkers the CUDA kernel runs.
+
+tests/hostmodel.cpp encodes the record from a plain DP matrix (checking the delta-range lemma and
+the ring-arithmetic word encoding on the way) and runs the shared walkers of b2a_format.h; results
+must equal the oracle's (score, coordinates, overlap, op list) exactly.
+"""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import pytest
+
+import oracle_binding as ob
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BUILD = os.path.join(HERE, "_build")
+
+
+class PairResult(C.Structure):
+    _fields_ = [("score", C.c_int32), ("end_i", C.c_uint32), ("end_j", C.c_uint32), ("start_i", C.c_uint32),
+                ("start_j", C.c_uint32), ("overlap", C.c_int32), ("n_ops", C.c_uint32), ("path", C.c_uint32)]
+
+
+def hostmodel():
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, "libhostmodel.so")
+    srcs = [os.path.join(HERE, "hostmodel.cpp"), os.path.join(ROOT, "bioinformatics-algorithms_b200", "csrc", "b2a_format.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-o", so, srcs[0]])
+    lib = C.CDLL(so)
+    lib.hm_record_chunks.restype = C.c_uint64
+    return lib
+
+
+def unpack_ops(words, n_ops):
+    return bytes(b"MDI"[(words[t // 16] >> (2 * (t % 16))) & 3] for t in range(n_ops))
+
+
+def model_pairpair(lib, mode, pa, ta, pb, tb, s):
+    m, n = len(pa), len(ta)
+    assert (len(pb), len(tb)) == (m, n)
+    plan = (C.c_int * 3)()
+    if not lib.hm_plan(mode, m, n, s[0], s[1], s[2], plan):
+        return None
+    K, R, bias = plan[0], plan[1], plan[2]
+    res = (PairResult * 2)()
+    nw = (m + n + 15) // 16 + 1
+    oa, obuf = (C.c_uint32 * nw)(), (C.c_uint32 * nw)()
+    rc = lib.hm_run_pairpair(mode, K, R, pa, pb, m, ta, tb, n, s[0], s[1], s[2], bias, pa[0], res, oa, obuf, None, None)
+    assert rc == 0, f"hostmodel rc={rc} (K={K} R={R} bias={bias})"
+    return [(res[0], unpack_ops(oa, res[0].n_ops)), (res[1], unpack_ops(obuf, res[1].n_ops))], (K, R, bias)
+
+
+def check(lib, mode, pa, ta, pb, tb, s):
+    got = model_pairpair(lib, mode, pa, ta, pb, tb, s)
+    if got is None:
+        return False
+    for (r, ops), (p, t) in zip(got[0], ((pa, ta), (pb, tb))):
+        a = ob.align(mode, p, t, *s)
+        assert (r.score, r.end_i, r.end_j, r.start_i, r.start_j, r.overlap, ops) == \
+               (a.score, a.end_i, a.end_j, a.start_i, a.start_j, a.overlap, a.ops), (mode, p, t, s, got[1], a)
+    return True
+
+
+def rnd(rng, n, alpha=b"ACGT"):
+    return bytes(rng.choice(alpha) for _ in range(n))
+
+
+def mutate(rng, s, psub=0.08, pindel=0.02):
+    out = bytearray()
+    for ch in s:
+        r = rng.random()
+        if r < pindel:
+            continue
+        if r < 2 * pindel:
+            out.append(rng.choice(b"ACGT"))
+        out.append(rng.choice(b"ACGT") if rng.random() < psub else ch)
+    return bytes(out)
+
+
+SCORINGS = [(1, -1, -1), (2, -3, -4), (5, -4, -16), (3, -2, -1), (1, -1, -2), (2, -1, -1), (1, 0, 0), (4, -6, -3), (0, 0, 0)]
+
+
+def test_plan_picks_expected_widths():
+    lib = hostmodel()
+    assert lib.hm_delta_bits(1, -1, -1) == 2
+    assert lib.hm_delta_bits(2, -3, -4) == 4
+    assert lib.hm_delta_bits(5, -4, -16) == 8
+    assert lib.hm_delta_bits(1, -1, 1) == 0      # positive "gap" reward: not representable, wide path
+    plan = (C.c_int * 3)()
+    assert lib.hm_plan(0, 150, 1000, 1, -1, -1, plan) and (plan[0], plan[1]) == (2, 5)
+    assert lib.hm_plan(0, 150, 1000, 5, -4, -16, plan) and plan[0] == 8
+    assert not lib.hm_plan(0, 300, 1000, 1, -1, -1, plan)    # > 256 rows
+    assert not lib.hm_plan(1, 150, 100000, 1, -1, -1, plan)  # too many columns
+
+
+def test_walkers_match_oracle_random_shapes():
+    lib = hostmodel()
+    rng = random.Random(4811)
+    done = 0
+    for it in range(260):
+        m, n = rng.randint(1, 70), rng.randint(1, 120)
+        kind = rng.random()
+        pairs = []
+        for _ in range(2):
+            if kind < 0.3:   # tie stress
+                u1, u2 = rnd(rng, rng.randint(1, 3), b"AC"), rnd(rng, rng.randint(1, 3), b"AC")
+                p, t = (u1 * 200)[:m], (u2 * 200)[:n]
+            elif kind < 0.7:
+                t = rnd(rng, n)
+                src = mutate(rng, t[rng.randint(0, max(0, n - m)):])
+                p = (src + rnd(rng, m))[:m]
+            else:
+                p, t = rnd(rng, m), rnd(rng, n)
+            pairs.append((p, t))
+        s = rng.choice(SCORINGS)
+        for mode in (ob.GLOBAL, ob.LOCAL):
+            done += check(lib, mode, pairs[0][0], pairs[0][1], pairs[1][0], pairs[1][1], s)
+    assert done > 400
+
+
+def test_walkers_match_oracle_config2_shape():
+    lib = hostmodel()
+    rng = random.Random(482)
+    for it in range(6):
+        pairs = []
+        for _ in range(2):
+            t = rnd(rng, 1000)
+            off = rng.randint(0, 850)
+            p = (mutate(rng, t[off:off + 150], 0.05, 0.005) + rnd(rng, 150))[:150]
+            pairs.append((p, t))
+        for s in ((1, -1, -1), (2, -3, -4)):
+            for mode in (ob.GLOBAL, ob.LOCAL):
+                assert check(lib, mode, pairs[0][0], pairs[0][1], pairs[1][0], pairs[1][1], s)
+
+
+def test_walkers_rows_up_to_256_and_homopolymers():
+    lib = hostmodel()
+    for m, n in ((256, 300), (255, 40), (33, 33), (32, 1), (1, 32), (1, 1), (97, 257)):
+        for p, t in ((b"A" * m, b"A" * n), (b"AC" * m, b"CA" * n), (b"A" * m, b"C" * n)):
+            for s in ((1, -1, -1), (2, -3, -4), (1, 0, 0)):
+                for mode in (ob.GLOBAL, ob.LOCAL):
+                    assert check(lib, mode, p[:m], t[:n], p[:m][::-1], t[:n][::-1], s)
