@@ -44,6 +44,24 @@ struct DevBuf {                                   // grow-only device buffer, re
 
 struct ClassRange { int R; uint32_t first, count, max_n; };
 
+// host-side state of the wide32 family for the current batch
+struct WideState {
+    std::vector<WidePair> pairs;
+    std::vector<WideTask> tasks;
+    uint64_t chunks = 0, bound_ints = 0, rowbest_words = 0, prog_words = 0;
+    int K = 32;
+    bool alpha4 = false, store = true;
+    DevBuf<WidePair> d_pairs;
+    DevBuf<WideTask> d_tasks;
+    DevBuf<Chunk> d_codes;
+    DevBuf<int32_t> d_bound, d_final;
+    DevBuf<uint32_t> d_rowbest, d_progress;       // d_progress[prog_words] is the ticket counter
+    void release() {
+        d_pairs.release(); d_tasks.release(); d_codes.release(); d_bound.release(); d_final.release();
+        d_rowbest.release(); d_progress.release();
+    }
+};
+
 } // namespace
 
 struct b2a_ctx {
@@ -83,15 +101,6 @@ int cuda_fail(b2a_ctx* c, cudaError_t e, const char* where) {
     return fail(c, e == cudaErrorMemoryAllocation ? B2A_ERR_NOMEM : B2A_ERR_CUDA,
                 std::string(where) + ": " + cudaGetErrorString(e));
 }
-} // namespace
-// wide32 placeholder: reject loudly until the int32 family lands
-int b2a::WideState::plan(b2a_ctx* c, const std::vector<uint32_t>& prs, const uint64_t*, const uint64_t*, const b2a_params&, bool) {
-    return fail(c, B2A_ERR_RANGE, "pair " + std::to_string(prs.empty() ? 0u : prs[0]) +
-                " needs the wide32 kernel family (pattern > 256 bases, > 4 pattern symbols, or scores outside the s16 record), not built yet");
-}
-int b2a::WideState::fill(b2a_ctx*, cudaStream_t, uint64_t*) { return B2A_OK; }
-int b2a::WideState::traceback(b2a_ctx*, cudaStream_t, uint64_t*) { return B2A_OK; }
-namespace {
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); } while (0)
 
 // 256-bit presence mask of the bytes in [p, p+n)
@@ -168,6 +177,130 @@ cudaError_t launch_tb(int K, bool local, const TbArgs& a, cudaStream_t st) {
 }
 
 inline int chunk_steps(int K) { return 3 * (16 / K); }
+
+// ---------------------------------------------------------------------------------------------
+// wide32 family: host planning and launches
+// ---------------------------------------------------------------------------------------------
+template <int K, bool LOCAL, bool STORE>
+cudaError_t launch_wide_fill_a(bool alpha4, const WideArgs& a, unsigned grid, cudaStream_t st) {
+    if (alpha4) wide32_fill_kernel<K, LOCAL, STORE, true><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
+    else wide32_fill_kernel<K, LOCAL, STORE, false><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+template <int K>
+cudaError_t launch_wide_fill_k(bool local, bool store, bool alpha4, const WideArgs& a, unsigned grid, cudaStream_t st) {
+    if (local) return store ? launch_wide_fill_a<K, true, true>(alpha4, a, grid, st) : launch_wide_fill_a<K, true, false>(alpha4, a, grid, st);
+    return store ? launch_wide_fill_a<K, false, true>(alpha4, a, grid, st) : launch_wide_fill_a<K, false, false>(alpha4, a, grid, st);
+}
+cudaError_t launch_wide_fill(int K, bool local, bool store, bool alpha4, const WideArgs& a, unsigned grid, cudaStream_t st) {
+    switch (K) {
+        case 2:  return launch_wide_fill_k<2>(local, store, alpha4, a, grid, st);
+        case 4:  return launch_wide_fill_k<4>(local, store, alpha4, a, grid, st);
+        case 8:  return launch_wide_fill_k<8>(local, store, alpha4, a, grid, st);
+        case 16: return launch_wide_fill_k<16>(local, store, alpha4, a, grid, st);
+        case 32: return launch_wide_fill_k<32>(local, store, alpha4, a, grid, st);
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_wide_tb(int K, bool local, const WideTbArgs& a, cudaStream_t st) {
+    const unsigned threads = 64, grid = (a.n_wide + threads - 1) / threads;
+    switch (K * 2 + (local ? 1 : 0)) {
+        case 4:  wide32_traceback_kernel<2, false><<<grid, threads, 0, st>>>(a); break;
+        case 5:  wide32_traceback_kernel<2, true><<<grid, threads, 0, st>>>(a); break;
+        case 8:  wide32_traceback_kernel<4, false><<<grid, threads, 0, st>>>(a); break;
+        case 9:  wide32_traceback_kernel<4, true><<<grid, threads, 0, st>>>(a); break;
+        case 16: wide32_traceback_kernel<8, false><<<grid, threads, 0, st>>>(a); break;
+        case 17: wide32_traceback_kernel<8, true><<<grid, threads, 0, st>>>(a); break;
+        case 32: wide32_traceback_kernel<16, false><<<grid, threads, 0, st>>>(a); break;
+        case 33: wide32_traceback_kernel<16, true><<<grid, threads, 0, st>>>(a); break;
+        case 64: wide32_traceback_kernel<32, false><<<grid, threads, 0, st>>>(a); break;
+        case 65: wide32_traceback_kernel<32, true><<<grid, threads, 0, st>>>(a); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+int wide_plan(b2a_ctx* ctx, const uint64_t* pat_off, const uint64_t* txt_off, bool store)
+{
+    WideState& W = ctx->wide;
+    const b2a_params& prm = ctx->prm;
+    W.pairs.clear(); W.tasks.clear();
+    W.chunks = W.bound_ints = W.rowbest_words = W.prog_words = 0;
+    W.K = delta_bits_wide(prm.match, prm.mismatch, prm.gap);
+    W.store = store;
+    W.alpha4 = ctx->nsym <= 4 && prm.match <= 127 && prm.match >= -128 && prm.mismatch <= 127 && prm.mismatch >= -128;
+    const int CS = 2 * (32 / W.K);
+    uint32_t max_bands = 0;
+    for (uint32_t k : ctx->wide_pairs) {
+        WidePair p{};
+        p.pat_off = pat_off[k]; p.txt_off = txt_off[k];
+        p.m = (uint32_t)(pat_off[k + 1] - pat_off[k]); p.n = (uint32_t)(txt_off[k + 1] - txt_off[k]);
+        p.pair = k;
+        p.nbands = (p.m && p.n) ? (p.m + 32u * WIDE_R - 1u) / (32u * WIDE_R) : 0u;
+        p.code_off = W.chunks;
+        if (store) W.chunks += (uint64_t)p.nbands * WIDE_R * num_chunks(p.n, CS) * 32u;
+        p.bound_stride = ((p.n + 64u) + 31u) & ~31u;
+        p.bound_off = W.bound_ints; W.bound_ints += 2ull * p.bound_stride;
+        p.rowbest_off = W.rowbest_words; W.rowbest_words += (uint64_t)p.nbands * 32u * WIDE_R;
+        p.prog_off = W.prog_words; W.prog_words += p.nbands;
+        max_bands = std::max(max_bands, p.nbands);
+        W.pairs.push_back(p);
+    }
+    // ticket order: band-major, so the band a warp depends on always holds an earlier ticket
+    std::vector<uint32_t> order(W.pairs.size());
+    for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return W.pairs[a].nbands > W.pairs[b].nbands; });
+    for (uint32_t b = 0; b < max_bands; ++b)
+        for (uint32_t i : order) { if (W.pairs[i].nbands <= b) break; W.tasks.push_back(WideTask{i, b}); }
+    cudaStream_t st = ctx->stream;
+    CU(W.d_pairs.reserve(W.pairs.size())); CU(W.d_tasks.reserve(W.tasks.size()));
+    CU(W.d_codes.reserve(W.chunks)); CU(W.d_bound.reserve(W.bound_ints)); CU(W.d_final.reserve(W.pairs.size()));
+    CU(W.d_rowbest.reserve(W.rowbest_words)); CU(W.d_progress.reserve(W.prog_words + 1));
+    CU(cudaMemcpyAsync(W.d_pairs.p, W.pairs.data(), W.pairs.size() * sizeof(WidePair), cudaMemcpyHostToDevice, st));
+    if (!W.tasks.empty()) CU(cudaMemcpyAsync(W.d_tasks.p, W.tasks.data(), W.tasks.size() * sizeof(WideTask), cudaMemcpyHostToDevice, st));
+    ctx->h2d += W.pairs.size() * sizeof(WidePair) + W.tasks.size() * sizeof(WideTask);
+    ctx->fill_bytes += W.chunks * sizeof(Chunk);
+    return B2A_OK;
+}
+
+int wide_fill(b2a_ctx* ctx, cudaStream_t st, uint64_t* launches)
+{
+    WideState& W = ctx->wide;
+    if (W.tasks.empty()) return B2A_OK;
+    const b2a_params& prm = ctx->prm;
+    CU(cudaMemsetAsync(W.d_progress.p, 0, (W.prog_words + 1) * 4, st));
+    WideArgs a{};
+    a.pat = ctx->d_pat.p; a.txt = ctx->d_txt.p; a.pairs = W.d_pairs.p; a.tasks = W.d_tasks.p;
+    a.n_tasks = (uint32_t)W.tasks.size(); a.ticket = W.d_progress.p + W.prog_words;
+    a.codes = W.d_codes.p; a.bound = W.d_bound.p; a.rowbest = W.d_rowbest.p; a.progress = W.d_progress.p;
+    a.final_score = W.d_final.p;
+    a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap;
+    a.radix = W.K < 32 ? (1u << W.K) : 0u;
+    for (int s = 0; s < 4; ++s) a.sym[s] = ctx->sym[s];
+    a.nsym = ctx->nsym;
+    const unsigned need = (unsigned)((W.tasks.size() + WIDE_WARPS - 1) / WIDE_WARPS);
+    const unsigned grid = std::min<unsigned>(need, (unsigned)ctx->sm_count * 8u);
+    CU(launch_wide_fill(W.K, prm.mode == B2A_MODE_LOCAL, W.store, W.alpha4, a, grid, st));
+    ++*launches;
+    return B2A_OK;
+}
+
+int wide_traceback(b2a_ctx* ctx, cudaStream_t st, uint64_t* launches, bool score_only)
+{
+    WideState& W = ctx->wide;
+    if (W.pairs.empty()) return B2A_OK;
+    const b2a_params& prm = ctx->prm;
+    WideTbArgs a{};
+    a.pat = ctx->d_pat.p; a.txt = ctx->d_txt.p; a.pairs = W.d_pairs.p; a.n_wide = (uint32_t)W.pairs.size();
+    a.codes = W.d_codes.p; a.rowbest = W.d_rowbest.p; a.final_score = W.d_final.p;
+    a.results = ctx->d_results.p;
+    a.ops = (prm.flags & B2A_WANT_OPS) && !score_only ? ctx->d_ops.p : nullptr;
+    a.ops_off = ctx->d_ops_off.p;
+    a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.score_only = score_only ? 1 : 0;
+    CU(launch_wide_tb(W.K, prm.mode == B2A_MODE_LOCAL, a, st));
+    ++*launches;
+    return B2A_OK;
+}
 
 } // namespace
 
@@ -277,7 +410,7 @@ int b2a_batch_upload(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, co
         cells += m64 * n64;
         const uint64_t key = (m64 << 32) | n64;
         if (key != plan_key) { plan_key = key; plan_ok = short16_plan(prm->mode, m, n, prm->match, prm->mismatch, prm->gap, pl); }
-        if (!plan_ok) { ctx->wide_pairs.push_back((uint32_t)k); continue; }
+        if (!plan_ok || (prm->flags & B2A_SCORE_ONLY)) { ctx->wide_pairs.push_back((uint32_t)k); continue; }
         auto emit = [&](uint32_t a, uint32_t b) { pps[pl.R].push_back(PPDesc{a, b, m, n}); };
         if (have_last && key == last_key) { emit(last_idx, (uint32_t)k); have_last = false; continue; }
         if (have_last) {
@@ -355,9 +488,9 @@ int b2a_batch_upload(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, co
     }
     ctx->fill_bytes = chunks * sizeof(Chunk);
     if (!ctx->wide_pairs.empty()) {
-        int rc = ctx->wide.plan(ctx, ctx->wide_pairs, pat_off, txt_off, *prm, want_ops);
+        int rc = wide_plan(ctx, pat_off, txt_off, !(prm->flags & B2A_SCORE_ONLY));
         if (rc != B2A_OK) return rc;
-    }
+    } else { ctx->wide.pairs.clear(); ctx->wide.tasks.clear(); }
     CU(cudaStreamSynchronize(st));
     ctx->have_batch = true;
     return B2A_OK;
@@ -388,7 +521,7 @@ int b2a_batch_run(b2a_ctx* ctx, float* fill_ms, float* traceback_ms)
         CU(launch_fill(ctx->K, c.R, local, a, st));
         ++launches;
     }
-    if (!ctx->wide_pairs.empty()) { int rc = ctx->wide.fill(ctx, st, &launches); if (rc != B2A_OK) return rc; }
+    if (!ctx->wide_pairs.empty()) { int rc = wide_fill(ctx, st, &launches); if (rc != B2A_OK) return rc; }
     CU(cudaEventRecord(ctx->ev[1], st));
     for (const ClassRange& c : ctx->classes) {
         Short16Plan pl{0, 0, 0};
@@ -403,7 +536,7 @@ int b2a_batch_run(b2a_ctx* ctx, float* fill_ms, float* traceback_ms)
         CU(launch_tb(ctx->K, local, a, st));
         ++launches;
     }
-    if (!ctx->wide_pairs.empty()) { int rc = ctx->wide.traceback(ctx, st, &launches); if (rc != B2A_OK) return rc; }
+    if (!ctx->wide_pairs.empty()) { int rc = wide_traceback(ctx, st, &launches, (prm.flags & B2A_SCORE_ONLY) != 0); if (rc != B2A_OK) return rc; }
     CU(cudaEventRecord(ctx->ev[2], st));
     CU(cudaStreamSynchronize(st));
     float f = 0, t = 0;

@@ -30,7 +30,7 @@ struct TbArgs {
 
 struct DevLoader {
     const Chunk* base;
-    __device__ __forceinline__ Chunk operator()(uint32_t idx) const {
+    __device__ __forceinline__ Chunk operator()(uint64_t idx) const {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + idx));
         return Chunk{v.x, v.y, v.z, v.w};
     }
@@ -53,8 +53,8 @@ short16_traceback_kernel(const TbArgs A)
                d.m, d.n, num_chunks(d.n, Geo<K>::CS), A.R, half, A.match, A.mismatch, A.gap, A.bias};
     OpsSink sink(A.ops ? A.ops + A.ops_off[pair] : nullptr);
     PairResult res;
-    if (LOCAL) walk_local<K>(v, DevLoader{rec}, sink, res);
-    else walk_global<K>(v, DevLoader{rec}, sink, res);
+    if (LOCAL) walk_local<Short16<K>>(v, DevLoader{rec}, sink, res);
+    else walk_global<Short16<K>>(v, DevLoader{rec}, sink, res);
     sink.flush();
     res.path = 1;
     A.results[pair] = res;

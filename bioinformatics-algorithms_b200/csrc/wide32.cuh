@@ -1,17 +1,296 @@
-// wide32.cuh -- int32 kernel family for pairs the s16x2 record cannot hold (placeholder wiring;
-// the kernels land in the next milestone).  Until then such pairs are rejected loudly.
+// wide32.cuh -- int32 kernel family: intra-pair tiled anti-diagonal wavefront for pairs the s16x2
+// record cannot hold (long patterns, general byte alphabets, large scores).
+//
+// Replaces the same reference loops as short16 (hw2.cpp:138-156 / :205-231) for ONE pair spread over
+// many warps: the DP matrix is cut into BANDS of 128 pattern rows (32 lanes x 4 rows); a warp sweeps
+// its band along the text as a skewed wavefront (__shfl_up_sync carries the in-warp diagonal
+// dependency) and exchanges the band's bottom row with the band below through L2/HBM in 32-column
+// blocks guarded by a per-band progress counter (st.release / ld.acquire).  Bands are handed out by
+// a ticket counter in (band, pair) order, so the band a warp waits for was always claimed earlier by
+// a warp that is already running: no cooperative launch is needed and nothing can deadlock.
+// The traceback record is the same delta/anchor chunk format as short16 (b2a_format.h, Wide32<K>),
+// written with the same ring-arithmetic word trick; K = 32 stores raw deltas and covers any scoring.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <vector>
-#include "../../include/b2align.h"
+#include "b2a_format.h"
 
-struct b2a_ctx;
 namespace b2a {
-struct WideState {
-    int plan(b2a_ctx*, const std::vector<uint32_t>&, const uint64_t*, const uint64_t*, const b2a_params&, bool);
-    int fill(b2a_ctx*, cudaStream_t, uint64_t*);
-    int traceback(b2a_ctx*, cudaStream_t, uint64_t*);
-    void release() {}
+
+struct WidePair {
+    uint64_t pat_off, txt_off;      // byte offsets of the pair's sequences
+    uint64_t code_off;              // first chunk of the pair's record
+    uint64_t bound_off;             // int32 index of the pair's 2 boundary rows (each bound_stride long)
+    uint64_t rowbest_off;           // uint32 index, nbands*128 entries
+    uint64_t prog_off;              // uint32 index, nbands entries
+    uint32_t m, n, pair, nbands;
+    uint32_t bound_stride, pad;
 };
+struct WideTask { uint32_t wp, band; };
+
+struct WideArgs {
+    const uint8_t*  pat;
+    const uint8_t*  txt;
+    const WidePair* pairs;
+    const WideTask* tasks;
+    uint32_t        n_tasks;
+    uint32_t*       ticket;
+    Chunk*          codes;
+    int32_t*        bound;
+    uint32_t*       rowbest;
+    uint32_t*       progress;
+    int32_t*        final_score;    // per wide pair: H(m, n) (global mode)
+    int32_t         match, mismatch, gap;
+    uint32_t        radix;
+    uint8_t         sym[4];
+    int32_t         nsym;
+};
+
+constexpr int WIDE_WARPS = 4;
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t prmt32(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// K: delta width; LOCAL: Smith-Waterman; STORE: write the traceback record; ALPHA4: pattern alphabet
+// has <= 4 symbols and scores fit int8, so the substitution score is one PRMT from a 4-entry table.
+template <int K, bool LOCAL, bool STORE, bool ALPHA4>
+__global__ void __launch_bounds__(WIDE_WARPS * 32)
+wide32_fill_kernel(const WideArgs A)
+{
+    using FM = Wide32<K>;
+    constexpr int R = WIDE_R, F = FM::F, CS = FM::CS, CPB = 32 / CS;   // chunks per 32-step block
+    __shared__ uint2 s_ring[WIDE_WARPS][64];       // per 1-based column j (slot j & 63): {text entry, H(top row, j)}
+    __shared__ uint32_t s_tbl4[256];
+    if (ALPHA4) {
+        for (int b = threadIdx.x; b < 256; b += blockDim.x) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int sc = (c < A.nsym && A.sym[c] == (uint8_t)b) ? A.match : A.mismatch;
+                w |= ((uint32_t)sc & 0xFFu) << (8 * c);
+            }
+            s_tbl4[b] = w;
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint2* ring = s_ring[warp];
+    const int gap = A.gap;
+    const uint32_t radix = A.radix, g32 = (uint32_t)gap;
+    uint32_t geo = 0, bpow = 1;
+    if (K < 32) {
+#pragma unroll
+        for (int t = 0; t < F; ++t) geo = geo * radix + 1u;
+#pragma unroll
+        for (int t = 0; t < F - 1; ++t) bpow *= radix;
+    }
+    const uint32_t negGc = 0u - g32 * geo, negBpow = 0u - bpow, radm1 = radix - 1u;
+
+    for (;;) {
+        uint32_t tk = 0;
+        if (lane == 0) tk = atomicAdd(A.ticket, 1u);
+        tk = __shfl_sync(0xFFFFFFFFu, tk, 0);
+        if (tk >= A.n_tasks) break;
+        const WideTask task = A.tasks[tk];
+        const WidePair wp = A.pairs[task.wp];
+        const uint32_t m = wp.m, n = wp.n, band = task.band;
+        const uint8_t* pp = A.pat + wp.pat_off;
+        const uint8_t* tt = A.txt + wp.txt_off;
+        const uint32_t row0 = band * 32u * R + (uint32_t)lane * R;          // 0-based first row of this lane
+        uint32_t pc[R];
+        int32_t H[R], best[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t i0 = row0 + r;
+            if (ALPHA4) {
+                uint32_t c = 0;
+                if (i0 < m) { const uint8_t x = pp[i0];
+#pragma unroll
+                    for (int k = 1; k < 4; ++k) if (x == A.sym[k]) c = k; }
+                pc[r] = c | ((8u | c) << 4) | ((8u | c) << 8) | ((8u | c) << 12);
+            } else pc[r] = i0 < m ? (uint32_t)pp[i0] : 0xFFFFFFFFu;         // junk rows never match
+            H[r] = LOCAL ? 0 : (int32_t)(i0 + 1) * gap;                      // hw2.cpp:125-130
+            best[r] = 0;
+        }
+        const int32_t* bin = A.bound + wp.bound_off + (uint64_t)((band + 1u) & 1u) * wp.bound_stride;
+        int32_t* bout = A.bound + wp.bound_off + (uint64_t)(band & 1u) * wp.bound_stride;
+        const uint32_t* prog_in = A.progress + wp.prog_off + band - 1;
+        uint32_t* prog_out = A.progress + wp.prog_off + band;
+        const bool has_next = band + 1 < wp.nbands;
+        const uint32_t nblk = (n + 32u + 31u) / 32u;
+        const uint32_t NC = num_chunks(n, CS);
+        Chunk* rec = A.codes + wp.code_off;
+        const int32_t top0 = LOCAL ? 0 : (int32_t)(band * 32u * R) * gap;    // H(top row, 0)
+        int32_t dgn = top0;
+        uint32_t have = band == 0 ? 0xFFFFFFFFu : 0u;                        // producer blocks known to be complete
+
+        auto text_entry = [&](uint32_t j) -> uint32_t {                      // ring payload of 1-based column j
+            if (j == 0 || j > n) return ALPHA4 ? 0u : 0xFFFFFF00u;
+            const uint8_t x = tt[j - 1];
+            return ALPHA4 ? s_tbl4[x] : (uint32_t)x;
+        };
+        uint32_t tnext = text_entry((uint32_t)lane);
+
+        for (uint32_t kb = 0; kb < nblk; ++kb) {
+            const uint32_t q0 = kb * 32u;
+            // ---- stage columns q0 .. q0+31 of the text and of the band above into the ring ----
+            int32_t bnd;
+            const uint32_t jcol = q0 + (uint32_t)lane;
+            if (band == 0) bnd = LOCAL ? 0 : (int32_t)jcol * gap;            // hw2.cpp:131-136
+            else {
+                const uint32_t need = kb + 2u < nblk ? kb + 2u : nblk;
+                while (have < need) { have = ld_acquire_u32(prog_in); if (have < need) __nanosleep(64); }
+                bnd = (jcol >= 1 && jcol <= n) ? __ldcg(bin + jcol) : top0;
+            }
+            __syncwarp();
+            ring[jcol & 63u] = make_uint2(tnext, (uint32_t)bnd);
+            __syncwarp();
+            tnext = text_entry(q0 + 32u + (uint32_t)lane);                   // prefetch the next block's text
+            const bool steady = q0 >= 32u && q0 + 31u <= n;
+
+            auto step = [&](uint32_t q, uint32_t (&S)[R], int f, bool active) {
+                int32_t up = __shfl_up_sync(0xFFFFFFFFu, H[R - 1], 1);
+                const uint2 e = ring[(q - (uint32_t)lane) & 63u];   // column q-lane; lane 0 also needs it at q = 0 (H(top,0))
+                if (lane == 0) up = (int32_t)e.y;
+                const int32_t dg0 = dgn;
+                dgn = up;
+                if (active) {
+                    int32_t dg = dg0, u = up;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int32_t s = ALPHA4 ? (int32_t)prmt32(e.x, 0u, pc[r]) : (pc[r] == e.x ? A.match : A.mismatch);
+                        const int32_t ds = dg + s;
+                        dg = H[r];
+                        const int32_t a = __viaddmax_s32(H[r], gap, ds);
+                        const int32_t h = LOCAL ? __viaddmax_s32_relu(u, gap, a) : __viaddmax_s32(u, gap, a);
+                        if (LOCAL) best[r] = max(best[r], h);
+                        H[r] = h; u = h;
+                    }
+                    if (lane == 31 && has_next) __stcg(bout + (q - 31u), H[R - 1]);
+                }
+                if (STORE && K < 32) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (f == 0) S[r] = (uint32_t)H[r];
+                        else if (f < F - 1) S[r] = S[r] * radix + (uint32_t)H[r];
+                    }
+                }
+            };
+
+#pragma unroll 1
+            for (int cb = 0; cb < CPB; ++cb) {
+                uint32_t w0[R];
+#pragma unroll
+                for (int wi = 0; wi < 2; ++wi) {
+                    uint32_t S[R], pre[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) pre[r] = K == 32 ? (0u - (uint32_t)H[r] - g32) : (uint32_t)H[r] * negBpow + negGc;
+                    const uint32_t qw = q0 + (uint32_t)(cb * CS + wi * F);
+                    if (steady) {
+#pragma unroll
+                        for (int f = 0; f < F; ++f) step(qw + f, S, f, true);
+                    } else {
+#pragma unroll
+                        for (int f = 0; f < F; ++f) step(qw + f, S, f, (uint32_t)(qw + f - lane - 1u) < n);
+                    }
+                    if (STORE) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const uint32_t w = (K < 32 && F > 1 ? S[r] * radm1 : 0u) + (uint32_t)H[r] + pre[r];
+                            if (wi == 0) w0[r] = w;
+                            else {
+                                const uint32_t c = kb * CPB + cb;
+                                if (c < NC) {
+                                    const uint4 v = make_uint4(w0[r], w, 0u, (uint32_t)H[r]);
+                                    *reinterpret_cast<uint4*>(&rec[(((uint64_t)band * R + r) * NC + c) * 32u + lane]) = v;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (has_next && lane == 31) st_release_u32(prog_out, kb + 1u);    // lane 31 wrote the row: its release covers it
+        }
+        if (LOCAL) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) A.rowbest[wp.rowbest_off + ((uint64_t)band * R + r) * 32u + lane] = (uint32_t)best[r];
+        } else if (band + 1 == wp.nbands) {
+            const uint32_t ib = (m - 1u) - band * 32u * R;
+            if ((uint32_t)lane == ib / R) {
+                const uint32_t rm = ib % R;
+                int32_t v = H[0];
+#pragma unroll
+                for (int r = 1; r < R; ++r) if (rm == (uint32_t)r) v = H[r];
+                A.final_score[task.wp] = v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- traceback over the wide32 record: one thread per pair ----
+struct WideTbArgs {
+    const uint8_t*  pat;
+    const uint8_t*  txt;
+    const WidePair* pairs;
+    uint32_t        n_wide;
+    const Chunk*    codes;
+    const uint32_t* rowbest;
+    const int32_t*  final_score;
+    PairResult*     results;
+    uint32_t*       ops;
+    const uint64_t* ops_off;
+    int32_t         match, mismatch, gap;
+    int32_t         score_only;
+};
+
+struct WideLoader {
+    const Chunk* base;
+    __device__ __forceinline__ Chunk operator()(uint64_t idx) const {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + idx));
+        return Chunk{v.x, v.y, v.z, v.w};
+    }
+};
+
+template <int K, bool LOCAL>
+__global__ void __launch_bounds__(64)
+wide32_traceback_kernel(const WideTbArgs A)
+{
+    using FM = Wide32<K>;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.n_wide) return;
+    const WidePair wp = A.pairs[t];
+    PairResult res;
+    if (A.score_only) {
+        res = PairResult{0, 0, 0, 0, 0, 0, 0, 2};
+        if (LOCAL) {
+            int M = 0;
+            for (uint64_t k = 0; k < (uint64_t)wp.nbands * 128u; ++k) { const int v = (int)A.rowbest[wp.rowbest_off + k]; if (v > M) M = v; }
+            res.score = M;
+        } else { res.score = (wp.m && wp.n) ? A.final_score[t] : (int32_t)(wp.m + wp.n) * A.gap; res.end_i = wp.m; res.end_j = wp.n; }
+        A.results[wp.pair] = res;
+        return;
+    }
+    const Chunk* rec = A.codes + wp.code_off;
+    PairView v{rec, A.rowbest + wp.rowbest_off, A.pat + wp.pat_off, A.txt + wp.txt_off,
+               wp.m, wp.n, num_chunks(wp.n, FM::CS), WIDE_R, 0, A.match, A.mismatch, A.gap, 0};
+    OpsSink sink(A.ops ? A.ops + A.ops_off[wp.pair] : nullptr);
+    if (LOCAL) walk_local<FM>(v, WideLoader{rec}, sink, res);
+    else walk_global<FM>(v, WideLoader{rec}, sink, res);
+    sink.flush();
+    res.path = 2;
+    A.results[wp.pair] = res;
+}
+
 } // namespace b2a

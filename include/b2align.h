@@ -41,6 +41,8 @@ extern "C" {
 
 /* b2a_params.flags */
 #define B2A_WANT_OPS      1u  /* keep per-pair traceback ops on the device for b2a_fetch_ops / b2a_copy_ops */
+#define B2A_SCORE_ONLY    2u  /* fill only: results carry the score (hw2.cpp:186 / :225-229), no traceback record,
+                                 no coordinates/overlap/ops -- the shape of hw3's distance stage (hw3.cpp:231-241) */
 
 /* op codes, 2 bits each (the reference's own letters, hw2.cpp:164-180 / :240-256) */
 #define B2A_OP_M          0u  /* 'M' diagonal: pattern base over text base            */

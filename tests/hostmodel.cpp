@@ -72,7 +72,7 @@ int encode(int mode, const uint8_t* pa, const uint8_t* pb, uint32_t m, const uin
                         Pv[t] = P(q0 - 1 + t);
                         if (Pv[t] == 0xFFFFFFFFu) return -2;                     // value outside [0, 32767]
                     }
-                    w[wi] = encode_word<K>(Pv, gap);
+                    w[wi] = encode_word<Short16<K>>(Pv, gap);
                     // cross-check the ring-arithmetic word against direct field packing
                     uint32_t direct = 0;
                     for (int t = 0; t < F; ++t) {
@@ -91,7 +91,7 @@ int encode(int mode, const uint8_t* pa, const uint8_t* pb, uint32_t m, const uin
 
 struct HostLoader {
     const Chunk* base;
-    Chunk operator()(uint32_t idx) const { return base[idx]; }
+    Chunk operator()(uint64_t idx) const { return base[idx]; }
 };
 
 template <int K>
@@ -109,11 +109,82 @@ int run(int mode, const uint8_t* pa, const uint8_t* pb, uint32_t m, const uint8_
         PairView v{codes.data(), rowbest.data(), half ? pb : pa, half ? tb : ta, m, n, NC, R, half, match, mismatch, gap, bias};
         OpsSink sink(half ? opsB : opsA);
         std::memset(&res[half], 0, sizeof(PairResult));
-        if (mode == 0) walk_global<K>(v, HostLoader{codes.data()}, sink, res[half]);
-        else walk_local<K>(v, HostLoader{codes.data()}, sink, res[half]);
+        if (mode == 0) walk_global<Short16<K>>(v, HostLoader{codes.data()}, sink, res[half]);
+        else walk_local<Short16<K>>(v, HostLoader{codes.data()}, sink, res[half]);
         sink.flush();
         res[half].path = 1;
     }
+    return 0;
+}
+
+
+// ---- wide32 record model: one pair, bands of 128 rows, int32, Wide32<K> chunks ----
+template <int K>
+int run_wide(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t n, int match, int mismatch, int gap,
+             PairResult* res, uint32_t* ops) {
+    using FM = Wide32<K>;
+    constexpr int F = FM::F, CS = FM::CS, R = WIDE_R;
+    const uint32_t NC = num_chunks(n, CS);
+    const uint32_t nbands = (m + 32u * R - 1u) / (32u * R);
+    const size_t W = (size_t)n + 1;
+    // plain DP, unbiased; rows beyond m never match anything (as in the kernel)
+    const uint32_t rows = nbands * 32u * R;
+    std::vector<int32_t> H((size_t)(rows + 1) * W);
+    for (uint32_t j = 0; j <= n; ++j) H[j] = mode == 0 ? (int)j * gap : 0;
+    for (uint32_t i = 1; i <= rows; ++i) {
+        H[i * W] = mode == 0 ? (int)i * gap : 0;
+        for (uint32_t j = 1; j <= n; ++j) {
+            const bool eq = i <= m && p[i - 1] == t[j - 1];
+            int v = H[(i - 1) * W + j - 1] + (eq ? match : mismatch);
+            const int l = H[i * W + j - 1] + gap, u = H[(i - 1) * W + j] + gap;
+            if (l > v) v = l;
+            if (u > v) v = u;
+            if (mode != 0 && v < 0) v = 0;
+            H[i * W + j] = v;
+        }
+    }
+    std::vector<Chunk> codes((size_t)nbands * R * NC * 32);
+    std::vector<uint32_t> rowbest((size_t)nbands * R * 32);
+    for (uint32_t band = 0; band < nbands; ++band)
+        for (uint32_t L = 0; L < 32; ++L)
+            for (int r = 0; r < R; ++r) {
+                const uint32_t i = band * 32u * R + L * R + (uint32_t)r + 1;
+                auto P = [&](int64_t q) -> uint32_t {
+                    int64_t j = q - (int64_t)L;
+                    if (j < 0) j = 0;
+                    if (j > (int64_t)n) j = n;
+                    return (uint32_t)H[i * W + (size_t)j];
+                };
+                int best = 0;
+                for (uint32_t j = 1; j <= n; ++j) if (H[i * W + j] > best) best = H[i * W + j];
+                rowbest[((size_t)band * R + r) * 32u + L] = (uint32_t)best;
+                for (uint32_t c = 0; c < NC; ++c) {
+                    uint32_t w[2];
+                    for (int wi = 0; wi < 2; ++wi) {
+                        const int64_t q0 = (int64_t)c * CS + (int64_t)wi * F;
+                        uint32_t Pv[F + 1];
+                        for (int tt = 0; tt <= F; ++tt) Pv[tt] = P(q0 - 1 + tt);
+                        w[wi] = encode_word<FM>(Pv, gap);
+                        if (K < 32) {
+                            uint32_t direct = 0;
+                            for (int tt = 0; tt < F; ++tt) {
+                                const int64_t d = (int64_t)(int32_t)Pv[tt + 1] - (int32_t)Pv[tt] - gap;
+                                if (d < 0 || d > (int64_t)FM::MASK) return -3;
+                                direct |= (uint32_t)d << ((K & 31) * (F - 1 - tt));
+                            }
+                            if (direct != w[wi]) return -4;
+                        }
+                    }
+                    codes[(((size_t)band * R + r) * NC + c) * 32u + L] = Chunk{w[0], w[1], 0u, P((int64_t)c * CS + CS - 1)};
+                }
+            }
+    PairView v{codes.data(), rowbest.data(), p, t, m, n, NC, R, 0, match, mismatch, gap, 0};
+    OpsSink sink(ops);
+    std::memset(res, 0, sizeof(PairResult));
+    if (mode == 0) walk_global<FM>(v, HostLoader{codes.data()}, sink, *res);
+    else walk_local<FM>(v, HostLoader{codes.data()}, sink, *res);
+    sink.flush();
+    res->path = 2;
     return 0;
 }
 
@@ -128,6 +199,21 @@ uint64_t hm_record_chunks(int K, int R, uint32_t n) {
 }
 
 int hm_delta_bits(int match, int mismatch, int gap) { return delta_bits(match, mismatch, gap); }
+int hm_delta_bits_wide(int match, int mismatch, int gap) { return delta_bits_wide(match, mismatch, gap); }
+
+// Model one pair through the wide32 record (K <= 0: choose like the library does).
+int hm_run_wide(int mode, int K, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t n, int match, int mismatch, int gap,
+                PairResult* res, uint32_t* ops) {
+    if (K <= 0) K = delta_bits_wide(match, mismatch, gap);
+    switch (K) {
+        case 2:  return run_wide<2>(mode, p, m, t, n, match, mismatch, gap, res, ops);
+        case 4:  return run_wide<4>(mode, p, m, t, n, match, mismatch, gap, res, ops);
+        case 8:  return run_wide<8>(mode, p, m, t, n, match, mismatch, gap, res, ops);
+        case 16: return run_wide<16>(mode, p, m, t, n, match, mismatch, gap, res, ops);
+        case 32: return run_wide<32>(mode, p, m, t, n, match, mismatch, gap, res, ops);
+    }
+    return -1;
+}
 
 // out[0..2] = K, R, bias; returns 1 if the short16 record can hold the pair-class
 int hm_plan(int mode, uint32_t m, uint32_t n, int match, int mismatch, int gap, int* out) {

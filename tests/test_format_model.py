@@ -143,3 +143,54 @@ def test_walkers_rows_up_to_256_and_homopolymers():
             for s in ((1, -1, -1), (2, -3, -4), (1, 0, 0)):
                 for mode in (ob.GLOBAL, ob.LOCAL):
                     assert check(lib, mode, p[:m], t[:n], p[:m][::-1], t[:n][::-1], s)
+
+
+# ---------------- wide32 record (int32, bands of 128 rows, K in {2,4,8,16,32}) ----------------
+def check_wide(lib, mode, p, t, s, K=0):
+    res = PairResult()
+    nw = (len(p) + len(t) + 15) // 16 + 1
+    ops = (C.c_uint32 * nw)()
+    rc = lib.hm_run_wide(mode, K, p, len(p), t, len(t), s[0], s[1], s[2], C.byref(res), ops)
+    assert rc == 0, f"hostmodel wide rc={rc}"
+    a = ob.align(mode, p, t, *s)
+    assert (res.score, res.end_i, res.end_j, res.start_i, res.start_j, res.overlap, unpack_ops(ops, res.n_ops)) == \
+           (a.score, a.end_i, a.end_j, a.start_i, a.start_j, a.overlap, a.ops), (mode, p, t, s, K, a)
+
+
+WIDE_SCORINGS = SCORINGS + [(100, -100, -200), (1, -1, 1), (-1, -2, -1), (-3, -3, -3), (7, 9, -2), (300, -200, -5000)]
+
+
+def test_wide_delta_bits():
+    lib = hostmodel()
+    assert lib.hm_delta_bits_wide(1, -1, -1) == 2
+    assert lib.hm_delta_bits_wide(5, -4, -16) == 8
+    assert lib.hm_delta_bits_wide(100, -100, -200) == 16
+    assert lib.hm_delta_bits_wide(300, -200, -50000) == 32
+    assert lib.hm_delta_bits_wide(1, -1, 1) == 32       # lemma does not apply: raw deltas
+    assert lib.hm_delta_bits_wide(-1, -2, -1) == 32
+
+
+def test_wide_walkers_match_oracle():
+    lib = hostmodel()
+    rng = random.Random(777)
+    for it in range(160):
+        m, n = rng.randint(1, 300), rng.randint(1, 200)
+        alpha = rng.choice([b"ACGT", b"AC", b"ACDEFGHIKLMNPQRSTVWYacgt"])
+        if rng.random() < 0.5:
+            t = rnd(rng, n, alpha)
+            p = (mutate(rng, t[rng.randint(0, max(0, n - 1)):]) + rnd(rng, m, alpha))[:m]
+        else:
+            p, t = rnd(rng, m, alpha), rnd(rng, n, alpha)
+        s = rng.choice(WIDE_SCORINGS)
+        for mode in (ob.GLOBAL, ob.LOCAL):
+            check_wide(lib, mode, p, t, s)
+
+
+def test_wide_every_k_on_the_same_input():
+    lib = hostmodel()
+    rng = random.Random(5)
+    t = rnd(rng, 333)
+    p = mutate(rng, t[40:300])
+    for K in (2, 4, 8, 16, 32):
+        for mode in (ob.GLOBAL, ob.LOCAL):
+            check_wide(lib, mode, p, t, (1, -1, -1), K)

@@ -192,3 +192,93 @@ def test_full_size_batch_properties(eng):
             a = ob.align(mode, P[k].tobytes(), T[k].tobytes(), 1, -1, -1)
             assert (int(res["score"][k]), int(res["overlap"][k]), pkg.unpack_ops(words, off, k, res["n_ops"][k])) == \
                    (a.score, a.overlap, a.ops)
+
+
+# ---------------- wide32 family (int32 banded wavefront) ----------------
+def rnd(rng, n, alpha=b"ACGT"):
+    return bytes(rng.choice(alpha) for _ in range(n))
+
+
+def mutate(rng, s, psub=0.08, pindel=0.02, alpha=b"ACGT"):
+    out = bytearray()
+    for ch in s:
+        r = rng.random()
+        if r < pindel:
+            continue
+        if r < 2 * pindel:
+            out.append(rng.choice(alpha))
+        out.append(rng.choice(alpha) if rng.random() < psub else ch)
+    return bytes(out)
+
+
+def test_wide_long_patterns_vs_oracle(eng):
+    """patterns > 256 rows: several 128-row bands chained through the boundary rows + progress counters"""
+    rng = random.Random(31)
+    ps, ts = [], []
+    for m, n in ((257, 300), (700, 900), (1300, 1100), (129, 5), (128, 4000), (3000, 2500), (5, 3000)):
+        t = rnd(rng, n)
+        p = (mutate(rng, t) + rnd(rng, m))[:m]
+        ps.append(p); ts.append(t)
+    for s in ((1, -1, -1), (2, -3, -4), (5, -4, -16)):
+        for mode in (pkg.GLOBAL, pkg.LOCAL):
+            check_batch(eng, mode, ps, ts, s, expect_path=2)
+
+
+def test_wide_general_alphabet_and_odd_scores_vs_oracle(eng):
+    rng = random.Random(32)
+    prot = b"ACDEFGHIKLMNPQRSTVWYacgt-"
+    ps, ts = [], []
+    for _ in range(40):
+        m, n = rng.randint(1, 400), rng.randint(1, 400)
+        t = rnd(rng, n, prot)
+        ps.append((mutate(rng, t, alpha=prot) + rnd(rng, m, prot))[:m]); ts.append(t)
+    for s in ((1, -1, -1), (100, -100, -200), (1, -1, 1), (-1, -2, -1), (7, 9, -2), (300, -200, -5000), (0, 0, 0)):
+        for mode in (pkg.GLOBAL, pkg.LOCAL):
+            check_batch(eng, mode, ps, ts, s, expect_path=2)
+
+
+def test_mixed_batch_short_and_wide(eng):
+    rng = random.Random(33)
+    ps, ts = [], []
+    for k in range(50):
+        m = rng.choice([20, 150, 150, 256, 257, 600])
+        n = rng.choice([20, 1000, 333])
+        t = rnd(rng, n)
+        ps.append((mutate(rng, t) + rnd(rng, m))[:m]); ts.append(t)
+    for mode in (pkg.GLOBAL, pkg.LOCAL):
+        res, _ = check_batch(eng, mode, ps, ts, (1, -1, -1))
+        assert set(int(x) for x in res["path"]) == {1, 2}
+
+
+def test_wide_tandem_repeats_10k(eng):
+    """tie stress at a size the full-matrix oracle still finishes in seconds (shape of input1610000.fasta)"""
+    ps = [(b"ACGTA" * 2100)[:10010], (b"ACGTACG" * 1500)[:10000]]
+    ts = [(b"ACGTA" * 2000)[:10000], (b"ACGTA" * 2100)[:10020]]
+    for mode in (pkg.GLOBAL, pkg.LOCAL):
+        check_batch(eng, mode, ps, ts, (1, -1, -1), expect_path=2)
+
+
+def test_score_only_flag(eng):
+    rng = random.Random(34)
+    ps, ts = [], []
+    for m, n in ((150, 1000), (700, 900), (33, 40), (2000, 1500)):
+        t = rnd(rng, n)
+        ps.append((mutate(rng, t) + rnd(rng, m))[:m]); ts.append(t)
+    pat, po = pkg.pack(ps)
+    txt, to = pkg.pack(ts)
+    for mode in (pkg.GLOBAL, pkg.LOCAL):
+        res = np.empty(len(ps), dtype=pkg.RESULT_DTYPE)
+        prm = pkg.Params(mode, 1, -1, -1, 2)
+        rc = eng.lib.b2a_align_batch(eng.ctx, C.byref(prm), pat.ctypes.data, po.ctypes.data, txt.ctypes.data, to.ctypes.data,
+                                     len(ps), res.ctypes.data)
+        assert rc == 0, eng.lib.b2a_last_error(eng.ctx)
+        for k in range(len(ps)):
+            assert int(res["score"][k]) == ob.score_only(mode, ps[k], ts[k], 1, -1, -1)[0]
+
+
+def test_empty_and_degenerate_inputs(eng):
+    res, ops = eng.align_batch(pkg.GLOBAL, [], [], 1, -1, -1)
+    assert len(res) == 0
+    # zero-length sequences cannot come out of readFasta (hw2.cpp:44-54 drops empty records) but the ABI accepts them
+    for mode in (pkg.GLOBAL, pkg.LOCAL):
+        check_batch(eng, mode, [b"", b"ACGT", b""], [b"ACGT", b"", b""], (1, -1, -1))
