@@ -79,6 +79,7 @@ struct b2a_ctx {
     int K = 0;
     uint8_t sym[4] = {0, 0, 0, 0};
     int nsym = 0;
+    bool alpha4 = false;                          // pattern alphabet of the batch has <= 4 symbols
     std::vector<ClassRange> classes;
     std::vector<uint32_t> wide_pairs;             // pairs served by the wide32 family
     std::vector<uint64_t> h_pat_off, h_txt_off, h_ops_off;
@@ -228,7 +229,7 @@ int wide_plan(b2a_ctx* ctx, const uint64_t* pat_off, const uint64_t* txt_off, bo
     W.chunks = W.bound_ints = W.rowbest_words = W.prog_words = 0;
     W.K = delta_bits_wide(prm.match, prm.mismatch, prm.gap);
     W.store = store;
-    W.alpha4 = ctx->nsym <= 4 && prm.match <= 127 && prm.match >= -128 && prm.mismatch <= 127 && prm.mismatch >= -128;
+    W.alpha4 = ctx->alpha4 && prm.match <= 127 && prm.match >= -128 && prm.mismatch <= 127 && prm.mismatch >= -128;
     const int CS = 2 * (32 / W.K);
     uint32_t max_bands = 0;
     for (uint32_t k : ctx->wide_pairs) {
@@ -461,6 +462,7 @@ int b2a_batch_upload(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, co
     bool short_ok = true;
     for (int b = 0; b < 256 && short_ok; ++b)
         if (mask[b >> 5] & (1u << (b & 31))) { if (ctx->nsym == 4) short_ok = false; else ctx->sym[ctx->nsym++] = (uint8_t)b; }
+    ctx->alpha4 = short_ok;
     if (!short_ok && !all.empty()) {
         // more than 4 distinct pattern symbols: the PRMT tables cannot hold them -> wide family for everything
         for (const PPDesc& d : all) { ctx->wide_pairs.push_back(d.a); if (d.b != d.a) ctx->wide_pairs.push_back(d.b); }

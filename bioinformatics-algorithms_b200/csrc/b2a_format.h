@@ -243,6 +243,7 @@ B2A_HD void walk_global(const PairView& v, Loader ld, Sink& sink, PairResult& re
 template <class FM, class Loader>
 B2A_HD void find_local_end(const PairView& v, Loader ld, int& M, uint32_t& bi, uint32_t& bj) {
     M = 0; bi = 0; bj = 0;
+    if (v.n == 0) return;                                           // no cells: the fill kernels wrote nothing
     const uint32_t rpb = 32u * (uint32_t)v.R;
     for (uint32_t i = 1; i <= v.m; ++i) {
         const uint32_t band = (i - 1u) / rpb, ib = (i - 1u) - band * rpb;

@@ -276,7 +276,12 @@ wide32_traceback_kernel(const WideTbArgs A)
         res = PairResult{0, 0, 0, 0, 0, 0, 0, 2};
         if (LOCAL) {
             int M = 0;
-            for (uint64_t k = 0; k < (uint64_t)wp.nbands * 128u; ++k) { const int v = (int)A.rowbest[wp.rowbest_off + k]; if (v > M) M = v; }
+            for (uint32_t k = 0; k < wp.nbands * 32u * WIDE_R; ++k) {       // k = (band*R + r)*32 + L; rows beyond m are junk
+                const uint32_t L = k & 31u, br = k >> 5, r = br % WIDE_R, band = br / WIDE_R;
+                if (band * 32u * WIDE_R + L * WIDE_R + r >= wp.m) continue;
+                const int v = (int)A.rowbest[wp.rowbest_off + k];
+                if (v > M) M = v;
+            }
             res.score = M;
         } else { res.score = (wp.m && wp.n) ? A.final_score[t] : (int32_t)(wp.m + wp.n) * A.gap; res.end_i = wp.m; res.end_j = wp.n; }
         A.results[wp.pair] = res;
