@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -79,6 +80,7 @@ struct b2a_ctx {
     int K = 0;
     uint8_t sym[4] = {0, 0, 0, 0};
     int nsym = 0;
+    int tb_opt = 0;                               // walker tuning bits (B2A_TB_OPT overrides, for experiments)
     bool alpha4 = false;                          // pattern alphabet of the batch has <= 4 symbols
     std::vector<ClassRange> classes;
     std::vector<uint32_t> wide_pairs;             // pairs served by the wide32 family
@@ -298,6 +300,7 @@ int wide_traceback(b2a_ctx* ctx, cudaStream_t st, uint64_t* launches, bool score
     a.ops = (prm.flags & B2A_WANT_OPS) && !score_only ? ctx->d_ops.p : nullptr;
     a.ops_off = ctx->d_ops_off.p;
     a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.score_only = score_only ? 1 : 0;
+    a.opt = ctx->tb_opt;
     CU(launch_wide_tb(W.K, prm.mode == B2A_MODE_LOCAL, a, st));
     ++*launches;
     return B2A_OK;
@@ -326,6 +329,7 @@ b2a_ctx* b2a_create(int device) {
         delete ctx; cudaGetLastError(); return nullptr;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = std::getenv("B2A_TB_OPT")) ctx->tb_opt = std::atoi(e);
     for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { b2a_destroy(ctx); return nullptr; }
     return ctx;
 }
@@ -535,6 +539,7 @@ int b2a_batch_run(b2a_ctx* ctx, float* fill_ms, float* traceback_ms)
         a.results = ctx->d_results.p; a.ops = want_ops ? ctx->d_ops.p : nullptr; a.ops_off = ctx->d_ops_off.p;
         a.n_pp = c.count; a.R = c.R;
         a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.bias = pl.bias;
+        a.opt = ctx->tb_opt;
         CU(launch_tb(ctx->K, local, a, st));
         ++launches;
     }

@@ -135,6 +135,8 @@ struct PairView {
     uint32_t m, n, NC;
     int R, half;               // half: short16 only, 0 = low 16 bits, 1 = high
     int match, mismatch, gap, bias;
+    int opt;                   // walker tuning bits: 1 = batch runs of 'l' moves, 2 = L2-prefetch rows ahead
+    int rmagic;                // short16: ceil(65536 / R)
 };
 
 template <class FM> B2A_HD uint32_t word_of(const Chunk& ch, int wi, int half) {
@@ -167,74 +169,142 @@ B2A_HD void decode_step(const Chunk& ch, int half, int gap, int rem, int& H, int
     H = anchor_of<FM>(ch, half) - (FM::CS - 1 - rem) * gap - sum;
 }
 
-// Two-entry cache of chunks in registers: the walk alternates between the current row and the row above.
-template <class Loader>
-struct ChunkCache {
-    Loader ld;
-    uint64_t i0, i1;
-    Chunk c0, c1;
-    B2A_HD explicit ChunkCache(Loader l) : ld(l), i0(~0ull), i1(~0ull) { c0 = Chunk{0, 0, 0, 0}; c1 = c0; }
-    B2A_HD Chunk get(uint64_t idx) {
-        if (idx == i0) return c0;
-        if (idx == i1) return c1;
-        c1 = c0; i1 = i0;
-        c0 = ld(idx); i0 = idx;
-        return c0;
+// (row i, chunk c) -> chunk index, and the lane L that owns the row.  No runtime divisions: the wide32
+// family has R = 4 (shifts); short16 has a single band and R <= 8, where x / R == (x * rmagic) >> 16
+// exactly for x < 256 (rmagic = 65536 / R rounded up; checked exhaustively in tests).
+template <class FM>
+B2A_HD uint32_t row_slot(const PairView& v, uint32_t i, uint32_t& L) {     // band*R + r, and the owning lane
+    const uint32_t x = i - 1u;
+    if (FM::WBITS == 32) { L = (x >> 2) & 31u; return (x >> 7) * 4u + (x & 3u); }
+    L = (x * (uint32_t)v.rmagic) >> 16;
+    return x - L * (uint32_t)v.R;
+}
+template <class FM>
+B2A_HD uint64_t chunk_index(const PairView& v, uint32_t i, uint32_t c, uint32_t& L) {
+    const uint32_t slot = row_slot<FM>(v, i, L);
+    return ((uint64_t)slot * v.NC + c) * 32u + L;
+}
+B2A_HD int short16_rmagic(int R) { return (65536 + R - 1) / R; }
+
+B2A_HD int popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+// sum of the K-bit fields of a 64-bit field string
+template <int K> B2A_HD int field_sum64(uint64_t x) {
+    if (K == 2) return popc64(x & 0x5555555555555555ull) + 2 * popc64(x & 0xAAAAAAAAAAAAAAAAull);
+    if (K == 32) return (int)((uint32_t)x + (uint32_t)(x >> 32));
+    return field_sum<K>((uint32_t)x) + field_sum<K>((uint32_t)(x >> 32));
+}
+// the chunk's delta words as one field string: step rem of the chunk sits at bit K*(CS-1-rem)
+template <class FM> B2A_HD uint64_t chunk_string(const Chunk& ch, int half) {
+    if (FM::WBITS == 32) return ((uint64_t)ch.w0 << 32) | ch.w1;
+    const int sh = half * 16;
+    return ((uint64_t)((ch.w0 >> sh) & 0xFFFFu) << 32) | ((uint64_t)((ch.w1 >> sh) & 0xFFFFu) << 16) | ((ch.w2 >> sh) & 0xFFFFu);
+}
+
+// A cursor on one DP row of the record: knows the exact H at its column and can step LEFT for the
+// price of one field extraction (H(i,j-1) = H(i,j) - D(i,j) - gap); a chunk is (re)loaded only when
+// the column crosses a chunk boundary.  Seeking (a new row) costs one chunk load + one popcount sum
+// from the chunk's anchor.  Row 0 is a virtual cursor: H = bias + j*gap (global) / 0 (local), no loads.
+template <class FM, class Loader, bool LOCAL>
+struct RowCursor {
+    static constexpr int BITS = FM::K * FM::CS;      // 48 (short16) or 64 (wide32)
+    uint64_t X;         // field string of the current chunk
+    uint64_t cidx;      // index of the current chunk (chunks of a row are 32 apart); 0 on the border row
+    int H, off, c;      // off = bit offset of the current field
+    int dborder;        // D of the virtual row 0 (0 global, -gap local), unused otherwise
+    bool border;
+    B2A_HD void seek(const PairView& v, const Loader& ld, uint32_t i, uint32_t j) {
+        if (i == 0) { border = true; H = LOCAL ? 0 : v.bias + (int)j * v.gap; X = 0; off = 0; c = 0; cidx = 0; dborder = LOCAL ? -v.gap : 0; return; }
+        border = false; dborder = 0;
+        uint32_t L;
+        const uint64_t base = chunk_index<FM>(v, i, 0, L);
+        const uint32_t q = j + L;
+        c = (int)(q / (uint32_t)FM::CS);
+        const int rem = (int)(q - (uint32_t)c * (uint32_t)FM::CS);
+        cidx = base + (uint64_t)c * 32u;
+        const Chunk ch = ld(cidx);
+        X = chunk_string<FM>(ch, v.half);
+        off = FM::K * (FM::CS - 1 - rem);
+        const uint64_t low = off ? (X & (~0ull >> (64 - off))) : 0ull;
+        H = anchor_of<FM>(ch, v.half) - (FM::CS - 1 - rem) * v.gap - field_sum64<FM::K>(low);
+    }
+    B2A_HD int D() const {
+        if (border) return dborder;
+        return FM::K == 32 ? (int)(uint32_t)(X >> off) : (int)((uint32_t)(X >> off) & FM::MASK);
+    }
+    // move to column j-1 (caller guarantees j >= 1)
+    B2A_HD void left(const PairView& v, const Loader& ld) {
+        H -= D() + v.gap;
+        off += FM::K;
+        if (off == BITS) {
+            off = 0;
+            if (!border && c > 0) { --c; cidx -= 32u; X = chunk_string<FM>(ld(cidx), v.half); }
+            // c == 0: step q = 0, nothing further left is ever read
+            else if (!border) off = BITS - FM::K;
+        }
     }
 };
 
-B2A_HD uint64_t chunk_index(const PairView& v, uint32_t i, uint32_t c, uint32_t& L) {
-    const uint32_t rpb = 32u * (uint32_t)v.R;
-    const uint32_t band = (i - 1u) / rpb, ib = (i - 1u) - band * rpb;
-    L = ib / (uint32_t)v.R;
-    const uint32_t r = ib - L * (uint32_t)v.R;
-    return (((uint64_t)band * (uint32_t)v.R + r) * v.NC + c) * 32u + L;
-}
-
+// The walk is a chain of dependent chunk loads (one per row change).  The path is mostly diagonal, so the
+// chunks of the next few rows up are predictable: ask for them PF rows ahead (L2 prefetch, no register cost).
+constexpr uint32_t WALK_PF = 6;
 template <class FM, class Loader>
-B2A_HD void cell(const PairView& v, ChunkCache<Loader>& cc, uint32_t i, uint32_t j, int& H, int& D) {
-    const uint32_t rpb = 32u * (uint32_t)v.R;
-    const uint32_t L = (((i - 1u) % rpb)) / (uint32_t)v.R;
-    const uint32_t q = j + L, c = q / (uint32_t)FM::CS, rem = q - c * (uint32_t)FM::CS;
-    uint32_t L2;
-    const Chunk ch = cc.get(chunk_index(v, i, c, L2));
-    decode_step<FM>(ch, v.half, v.gap, (int)rem, H, D);
+B2A_HD void prefetch_row(const PairView& v, const Loader& ld, uint32_t i, uint32_t j) {
+    if (i == 0) return;
+    uint32_t L;
+    const uint64_t base = chunk_index<FM>(v, i, 0, L);
+    ld.prefetch(base + (uint64_t)((j + L) / (uint32_t)FM::CS) * 32u);
 }
 
 // ---- Needleman-Wunsch traceback, hw2.cpp:158-181 on reconstructed H; directions per hw2.cpp:145-153 ----
 template <class FM, class Loader, class Sink>
 B2A_HD void walk_global(const PairView& v, Loader ld, Sink& sink, PairResult& res) {
-    ChunkCache<Loader> cc(ld);
     uint32_t i = v.m, j = v.n, nops = 0;
-    int cur = 0, best = 0, H, D;
-    if (i == 0 || j == 0) H = v.bias + (int)(i + j) * v.gap;       // border, hw2.cpp:125-136
-    else cell<FM>(v, cc, i, j, H, D);
-    res.score = H - v.bias;                                         // hw2.cpp:186
-    while (i > 0 || j > 0) {
-        uint32_t op;
-        if (i == 0) op = OP_I;                                      // row 0 holds 'l' (hw2.cpp:134)
-        else if (j == 0) op = OP_D;                                 // column 0 holds 'u' (hw2.cpp:128)
-        else {
-            cell<FM>(v, cc, i, j, H, D);
-            const int Hl = H - D - v.gap;                           // H(i, j-1); frozen lanes make this the border at j == 1
-            int Hu, Hd;
-            if (i == 1) { Hu = v.bias + (int)j * v.gap; Hd = v.bias + (int)(j - 1) * v.gap; }
-            else { int Du; cell<FM>(v, cc, i - 1, j, Hu, Du); Hd = Hu - Du - v.gap; }
-            const bool eq = v.p[i - 1] == v.t[j - 1];
-            int val = Hd + (eq ? v.match : v.mismatch);             // hw2.cpp:142
-            op = OP_M;                                              // hw2.cpp:145
-            if (Hl + v.gap > val) { val = Hl + v.gap; op = OP_I; }  // hw2.cpp:146-149 'l'
-            if (Hu + v.gap > val) { op = OP_D; }                    // hw2.cpp:150-153 'u'
+    int cur = 0, best = 0;
+    RowCursor<FM, Loader, false> rc, ru;                             // rows i and i-1 at column j
+    rc.seek(v, ld, (i && j) ? i : 0, j);
+    if (i == 0 || j == 0) rc.H = v.bias + (int)(i + j) * v.gap;      // border, hw2.cpp:125-136
+    res.score = rc.H - v.bias;                                       // hw2.cpp:186
+    if (i && j) ru.seek(v, ld, i - 1, j);
+    if (v.opt & 2) for (uint32_t k = 2; k < 2 + WALK_PF && k <= i; ++k) prefetch_row<FM>(v, ld, i - k, j > k ? j - k + 1 : 1);
+    while (i > 0 && j > 0) {
+        const int Hl = rc.H - rc.D() - v.gap;                       // H(i, j-1); frozen lanes make this the border at j == 1
+        const int Hu = ru.H, Hd = Hu - ru.D() - v.gap;              // H(i-1, j), H(i-1, j-1)
+        const uint8_t pc = v.p[i - 1];
+        const bool eq = pc == v.t[j - 1];
+        int val = Hd + (eq ? v.match : v.mismatch);                  // hw2.cpp:142
+        uint32_t op = OP_M;                                          // hw2.cpp:145
+        if (Hl + v.gap > val) { val = Hl + v.gap; op = OP_I; }       // hw2.cpp:146-149 'l'
+        if (Hu + v.gap > val) { op = OP_D; }                         // hw2.cpp:150-153 'u'
+        if (op == OP_I && (v.opt & 1)) {
+            // a run of 'l' moves stays inside the two chunks in registers: no memory traffic until a chunk edge
+            cur = 0;
+            for (;;) {
+                rc.left(v, ld); ru.left(v, ld);
+                --j; sink.put(OP_I); ++nops;
+                if (j == 0 || rc.off == 0 || ru.off == 0) break;
+                const int hl = rc.H - rc.D(), hd = ru.H - ru.D() - v.gap + (pc == v.t[j - 1] ? v.match : v.mismatch);
+                if (!(hl > hd && !(ru.H + v.gap > hl))) break;       // next cell is not 'l' (same tests as above)
+            }
+            continue;
         }
-        if (op == OP_M) {
-            const uint8_t pc = v.p[i - 1];
-            if (pc == v.t[j - 1] && pc != (uint8_t)'-') { if (++cur > best) best = cur; } else cur = 0;   // hw2.cpp:267-278
-            --i; --j;
-        } else if (op == OP_D) { cur = 0; --i; }
-        else { cur = 0; --j; }
+        if (op == OP_M && eq && pc != (uint8_t)'-') { if (++cur > best) best = cur; } else cur = 0;   // hw2.cpp:267-278
+        if (op != OP_D) { rc.left(v, ld); ru.left(v, ld); --j; }     // 'M' and 'I' both move one column left
+        if (op != OP_I) {                                            // 'M' and 'D' both move one row up
+            rc = ru; --i;
+            if (i > 0) ru.seek(v, ld, i - 1, j);
+            if ((v.opt & 2) && i > 1 + WALK_PF) prefetch_row<FM>(v, ld, i - 1 - WALK_PF, j > WALK_PF ? j - WALK_PF : 1);
+        }
         sink.put(op);
         ++nops;
     }
+    for (; i > 0; --i, ++nops) sink.put(OP_D);                       // column 0 holds 'u' (hw2.cpp:128)
+    for (; j > 0; --j, ++nops) sink.put(OP_I);                       // row 0 holds 'l' (hw2.cpp:134)
     res.end_i = v.m; res.end_j = v.n; res.start_i = 0; res.start_j = 0;
     res.overlap = best; res.n_ops = nops;
 }
@@ -244,22 +314,20 @@ template <class FM, class Loader>
 B2A_HD void find_local_end(const PairView& v, Loader ld, int& M, uint32_t& bi, uint32_t& bj) {
     M = 0; bi = 0; bj = 0;
     if (v.n == 0) return;                                           // no cells: the fill kernels wrote nothing
-    const uint32_t rpb = 32u * (uint32_t)v.R;
     for (uint32_t i = 1; i <= v.m; ++i) {
-        const uint32_t band = (i - 1u) / rpb, ib = (i - 1u) - band * rpb;
-        const uint32_t L = ib / (uint32_t)v.R, r = ib - L * (uint32_t)v.R;
-        const int rb = rowbest_of<FM>(v.rowbest[((uint64_t)band * (uint32_t)v.R + r) * 32u + L], v.half);
+        uint32_t L;
+        const uint32_t slot = row_slot<FM>(v, i, L);
+        const int rb = rowbest_of<FM>(v.rowbest[(uint64_t)slot * 32u + L], v.half);
         if (rb > M) { M = rb; bi = i; }
     }
     if (M == 0) { bi = 0; return; }                                 // hw2.cpp:202-203: best cell stays (0,0)
     uint32_t L;
-    chunk_index(v, bi, 0, L);
+    const uint64_t rowbase = chunk_index<FM>(v, bi, 0, L);
     int run = 0;                                                    // H(bi, 0) = 0
     uint32_t q = L + 1u;
     while (q <= L + v.n && bj == 0) {
         const uint32_t c = q / (uint32_t)FM::CS;
-        uint32_t L2;
-        const Chunk ch = ld(chunk_index(v, bi, c, L2));
+        const Chunk ch = ld(rowbase + (uint64_t)c * 32u);
         uint32_t rem = q - c * (uint32_t)FM::CS;
         for (; rem < (uint32_t)FM::CS && q <= L + v.n; ++rem, ++q) {
             const int wi = (int)rem / FM::F, f = (int)rem - wi * FM::F;
@@ -272,28 +340,30 @@ B2A_HD void find_local_end(const PairView& v, Loader ld, int& M, uint32_t& bi, u
 // ---- Smith-Waterman traceback hw2.cpp:239-257 from a known end cell ----
 template <class FM, class Loader, class Sink>
 B2A_HD void walk_local_from(const PairView& v, Loader ld, Sink& sink, PairResult& res, int M, uint32_t bi, uint32_t bj) {
-    ChunkCache<Loader> cc(ld);
     res.score = M; res.overlap = 0; res.n_ops = 0;
     if (M == 0) { res.end_i = res.end_j = res.start_i = res.start_j = 0; return; }
     uint32_t i = bi, j = bj, nops = 0;
-    int cur = 0, best = 0, H = M;
-    while (i > 0 && j > 0 && H != 0) {                               // hw2.cpp:239
-        int Hc, D;
-        cell<FM>(v, cc, i, j, Hc, D);
-        const int Hl = Hc - D - v.gap;
-        int Hu = 0, Hd = 0;
-        if (i > 1) { int Du; cell<FM>(v, cc, i - 1, j, Hu, Du); Hd = Hu - Du - v.gap; }
+    int cur = 0, best = 0;
+    RowCursor<FM, Loader, true> rc, ru;                              // SW borders are 0 (hw2.cpp:193-197)
+    rc.seek(v, ld, i, j);
+    ru.seek(v, ld, i - 1, j);
+    if (v.opt & 2) for (uint32_t k = 2; k < 2 + WALK_PF && k <= i; ++k) prefetch_row<FM>(v, ld, i - k, j > k ? j - k + 1 : 1);
+    while (i > 0 && j > 0 && rc.H != 0) {                            // hw2.cpp:239
+        const int H = rc.H, Hl = H - rc.D() - v.gap;
+        const int Hu = ru.H, Hd = Hu - ru.D() - v.gap;
         const uint8_t pc = v.p[i - 1];
         const bool eq = pc == v.t[j - 1];
         uint32_t op;                                                 // hw2.cpp:214-222 (H != 0 here)
         if (H == Hd + (eq ? v.match : v.mismatch)) op = OP_M;
         else if (H == Hu + v.gap) op = OP_D;
         else op = OP_I;
-        if (op == OP_M) {
-            if (eq && pc != (uint8_t)'-') { if (++cur > best) best = cur; } else cur = 0;
-            --i; --j; H = Hd;
-        } else if (op == OP_D) { cur = 0; --i; H = Hu; }
-        else { cur = 0; --j; H = Hl; }
+        if (op == OP_M && eq && pc != (uint8_t)'-') { if (++cur > best) best = cur; } else cur = 0;
+        if (op != OP_D) { rc.left(v, ld); ru.left(v, ld); --j; }
+        if (op != OP_I) {
+            rc = ru; --i;
+            if (i > 0) ru.seek(v, ld, i - 1, j);
+            if ((v.opt & 2) && i > 1 + WALK_PF) prefetch_row<FM>(v, ld, i - 1 - WALK_PF, j > WALK_PF ? j - WALK_PF : 1);
+        }
         sink.put(op);
         ++nops;
     }

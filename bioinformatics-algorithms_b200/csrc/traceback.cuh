@@ -26,6 +26,7 @@ struct TbArgs {
     uint32_t        n_pp;
     int32_t         R;
     int32_t         match, mismatch, gap, bias;
+    int32_t         opt;
 };
 
 struct DevLoader {
@@ -33,6 +34,9 @@ struct DevLoader {
     __device__ __forceinline__ Chunk operator()(uint64_t idx) const {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + idx));
         return Chunk{v.x, v.y, v.z, v.w};
+    }
+    __device__ __forceinline__ void prefetch(uint64_t idx) const {
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(base + idx));
     }
 };
 
@@ -50,7 +54,7 @@ short16_traceback_kernel(const TbArgs A)
     const Chunk* rec = A.codes + A.code_off[pp];
     PairView v{rec, LOCAL ? A.rowbest + (size_t)pp * A.R * 32u : nullptr,
                A.pat + A.pat_off[pair], A.txt + A.txt_off[pair],
-               d.m, d.n, num_chunks(d.n, Geo<K>::CS), A.R, half, A.match, A.mismatch, A.gap, A.bias};
+               d.m, d.n, num_chunks(d.n, Geo<K>::CS), A.R, half, A.match, A.mismatch, A.gap, A.bias, A.opt, short16_rmagic(A.R)};
     OpsSink sink(A.ops ? A.ops + A.ops_off[pair] : nullptr);
     PairResult res;
     if (LOCAL) walk_local<Short16<K>>(v, DevLoader{rec}, sink, res);

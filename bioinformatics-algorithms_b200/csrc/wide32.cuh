@@ -253,6 +253,7 @@ struct WideTbArgs {
     const uint64_t* ops_off;
     int32_t         match, mismatch, gap;
     int32_t         score_only;
+    int32_t         opt;
 };
 
 struct WideLoader {
@@ -260,6 +261,9 @@ struct WideLoader {
     __device__ __forceinline__ Chunk operator()(uint64_t idx) const {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + idx));
         return Chunk{v.x, v.y, v.z, v.w};
+    }
+    __device__ __forceinline__ void prefetch(uint64_t idx) const {
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(base + idx));
     }
 };
 
@@ -289,7 +293,7 @@ wide32_traceback_kernel(const WideTbArgs A)
     }
     const Chunk* rec = A.codes + wp.code_off;
     PairView v{rec, A.rowbest + wp.rowbest_off, A.pat + wp.pat_off, A.txt + wp.txt_off,
-               wp.m, wp.n, num_chunks(wp.n, FM::CS), WIDE_R, 0, A.match, A.mismatch, A.gap, 0};
+               wp.m, wp.n, num_chunks(wp.n, FM::CS), WIDE_R, 0, A.match, A.mismatch, A.gap, 0, A.opt, 0};
     OpsSink sink(A.ops ? A.ops + A.ops_off[wp.pair] : nullptr);
     if (LOCAL) walk_local<FM>(v, WideLoader{rec}, sink, res);
     else walk_global<FM>(v, WideLoader{rec}, sink, res);

@@ -13,6 +13,8 @@
 #include "../bioinformatics-algorithms_b200/csrc/b2a_format.h"
 
 using namespace b2a;
+static int g_opt = 3;
+extern "C" void hm_set_opt(int o) { g_opt = o; }
 
 namespace {
 
@@ -92,6 +94,7 @@ int encode(int mode, const uint8_t* pa, const uint8_t* pb, uint32_t m, const uin
 struct HostLoader {
     const Chunk* base;
     Chunk operator()(uint64_t idx) const { return base[idx]; }
+    void prefetch(uint64_t) const {}
 };
 
 template <int K>
@@ -106,7 +109,7 @@ int run(int mode, const uint8_t* pa, const uint8_t* pb, uint32_t m, const uint8_
     if (codes_out) std::memcpy(codes_out, codes.data(), codes.size() * sizeof(Chunk));
     if (rowbest_out) std::memcpy(rowbest_out, rowbest.data(), rowbest.size() * sizeof(uint32_t));
     for (int half = 0; half < 2; ++half) {
-        PairView v{codes.data(), rowbest.data(), half ? pb : pa, half ? tb : ta, m, n, NC, R, half, match, mismatch, gap, bias};
+        PairView v{codes.data(), rowbest.data(), half ? pb : pa, half ? tb : ta, m, n, NC, R, half, match, mismatch, gap, bias, g_opt, short16_rmagic(R)};
         OpsSink sink(half ? opsB : opsA);
         std::memset(&res[half], 0, sizeof(PairResult));
         if (mode == 0) walk_global<Short16<K>>(v, HostLoader{codes.data()}, sink, res[half]);
@@ -178,7 +181,7 @@ int run_wide(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t 
                     codes[(((size_t)band * R + r) * NC + c) * 32u + L] = Chunk{w[0], w[1], 0u, P((int64_t)c * CS + CS - 1)};
                 }
             }
-    PairView v{codes.data(), rowbest.data(), p, t, m, n, NC, R, 0, match, mismatch, gap, 0};
+    PairView v{codes.data(), rowbest.data(), p, t, m, n, NC, R, 0, match, mismatch, gap, 0, g_opt, 0};
     OpsSink sink(ops);
     std::memset(res, 0, sizeof(PairResult));
     if (mode == 0) walk_global<FM>(v, HostLoader{codes.data()}, sink, *res);
@@ -198,6 +201,13 @@ uint64_t hm_record_chunks(int K, int R, uint32_t n) {
     return (uint64_t)R * num_chunks(n, CS) * 32u;
 }
 
+// exhaustive check of the multiply-shift row -> lane division used by the short16 walkers
+int hm_check_rmagic() {
+    for (int R = 1; R <= SHORT16_MAX_R; ++R)
+        for (uint32_t x = 0; x < 32u * R; ++x)
+            if (((x * (uint32_t)short16_rmagic(R)) >> 16) != x / (uint32_t)R) return 0;
+    return 1;
+}
 int hm_delta_bits(int match, int mismatch, int gap) { return delta_bits(match, mismatch, gap); }
 int hm_delta_bits_wide(int match, int mismatch, int gap) { return delta_bits_wide(match, mismatch, gap); }
 

@@ -85,6 +85,7 @@ SCORINGS = [(1, -1, -1), (2, -3, -4), (5, -4, -16), (3, -2, -1), (1, -1, -2), (2
 
 def test_plan_picks_expected_widths():
     lib = hostmodel()
+    assert lib.hm_check_rmagic() == 1
     assert lib.hm_delta_bits(1, -1, -1) == 2
     assert lib.hm_delta_bits(2, -3, -4) == 4
     assert lib.hm_delta_bits(5, -4, -16) == 8
