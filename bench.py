@@ -197,16 +197,17 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank); sampler.start()
     launches0 = sum(eng[mode].stats()["launches"] for mode in eng)
-    fill_ms = {0: 0.0, 1: 0.0}; tb_ms = {0: 0.0, 1: 0.0}
+    fill_ms = {0: 0.0, 1: 0.0}; tb_ms = {0: 0.0, 1: 0.0}; tot_ms = {0: 0.0, 1: 0.0}
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for mode in eng:
-            f, t = eng[mode].run()
-            fill_ms[mode] += f; tb_ms[mode] += t
+            eng[mode].run()
+            f, t, tot = eng[mode].times()       # CUDA events on the launching streams: per kernel, and first start -> last end
+            fill_ms[mode] += f; tb_ms[mode] += t; tot_ms[mode] += tot
     barrier()
     wall_dev = time.perf_counter() - t0
     clocks = sampler.summary()
-    dev_s = (sum(fill_ms.values()) + sum(tb_ms.values())) * 1e-3
+    dev_s = sum(tot_ms.values()) * 1e-3
     dev_s = max_over_ranks(dev_s)
     wall_dev = max_over_ranks(wall_dev)
     launches = sum(eng[mode].stats()["launches"] for mode in eng) - launches0
@@ -269,7 +270,8 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s * 1e3 / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
                 "config": {"workload": workload_name, "pairs_per_gpu": n_pairs, "l2": "inputs+record (>50 GB/mode) far larger than L2",
-                           "timing": "library CUDA events on the launching stream (fill+traceback), max over ranks",
+                           "timing": "library CUDA events on the launching streams (first kernel start -> last kernel end per mode), max over ranks",
+                           "e2e_pipeline": "b2a_align_batch cuts the batch into segments (16k pairs doubling to 128k); the H2D copy of segment k+1 overlaps the kernels of segment k",
                            "wall_ms_per_step_device_arm": wall_dev * 1e3 / args.steps},
                 "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3 / args.steps},

@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(HERE, "libb2align.so")
 HW2_BIN = os.path.join(HERE, "bin", "hw2")
 
 GLOBAL, LOCAL = 0, 1
+OPT_LANES, OPT_SEG_PAIRS, OPT_SEG_BYTES, OPT_TB, OPT_SEG_FIRST = 1, 2, 3, 4, 5
 WANT_OPS = 1
 
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<u4"), ("end_j", "<u4"), ("start_i", "<u4"),
@@ -26,7 +27,7 @@ RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<u4"), ("end_j", "<u4"), (
 
 EXPORTS = ["b2a_device_count", "b2a_create", "b2a_destroy", "b2a_last_error", "b2a_host_alloc", "b2a_host_free",
            "b2a_align_batch", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
-           "b2a_batch_download", "b2a_batch_stats", "b2a_render_cigar", "b2a_render_mdz", "b2a_select_best",
+           "b2a_batch_download", "b2a_batch_times", "b2a_set_option", "b2a_batch_stats", "b2a_render_cigar", "b2a_render_mdz", "b2a_select_best",
            "b2a_microbench_int16x2", "b2a_debug_copy_record"]
 
 
@@ -62,6 +63,8 @@ def load_library():
         lib.b2a_batch_upload.argtypes = [P, C.POINTER(Params), P, P, P, P, C.c_uint64]
         lib.b2a_batch_run.argtypes = [P, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         lib.b2a_batch_download.argtypes = [P, P]
+        lib.b2a_batch_times.argtypes = [P] + [C.POINTER(C.c_float)] * 3
+        lib.b2a_set_option.argtypes = [P, C.c_int, C.c_int64]
         lib.b2a_batch_stats.argtypes = [P] + [C.POINTER(C.c_uint64)] * 5
         lib.b2a_fetch_ops.restype = C.c_int64
         lib.b2a_fetch_ops.argtypes = [P, C.c_uint64, P, C.c_uint64]
@@ -227,6 +230,15 @@ class Engine:
         f, t = C.c_float(), C.c_float()
         self._check(self.lib.b2a_batch_run(self.ctx, C.byref(f), C.byref(t)), "b2a_batch_run")
         return f.value, t.value
+
+    def times(self):
+        """(fill_ms, traceback_ms, total_ms) of the last run()"""
+        v = [C.c_float() for _ in range(3)]
+        self.lib.b2a_batch_times(self.ctx, *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)
+
+    def set_option(self, option, value):
+        self._check(self.lib.b2a_set_option(self.ctx, int(option), int(value)), "b2a_set_option")
 
     def download(self, n_pairs, results=None):
         if results is None:

@@ -1,12 +1,19 @@
 // b2a_api.cu -- C ABI (include/b2align.h) over the sm_100a kernels.
 //
-// Host side of the batch boundary that replaces the loop hw2.cpp:328-338: validates the batch,
-// discovers the pattern alphabet on the device, groups pairs of identical shape into pair-pairs
-// (the two 16-bit halves of the s16x2 kernels), sizes the HBM record, launches fill + traceback
-// per rows-per-lane class and returns one record per pair.  No CPU alignment code lives here:
-// if CUDA is unavailable every compute entry point fails with B2A_ERR_CUDA.
+// Host side of the batch boundary that replaces the loop hw2.cpp:328-338.  A batch is cut into
+// SEGMENTS of consecutive pairs.  Per segment the host (1) queues the host->device copy of the
+// segment's sequence bytes, (2) plans it while the copy is in flight: pairs of identical shape are
+// zipped into pair-pairs (the two 16-bit halves of the s16x2 kernels) and grouped by rows-per-lane,
+// (3) queues the fill + traceback kernels on one of two compute lanes.  Nothing in that loop waits
+// for the device: the pattern alphabet of a segment is discovered by a device kernel and stays on
+// the device (AlphaInfo), the DP record of a lane is reused by every second segment, so the copy of
+// segment k+1 overlaps the kernels of segment k and the record footprint is two segments, not the
+// batch.  Pairs the s16x2 record cannot hold (long patterns, wide scores, > 4 pattern symbols) are
+// collected and served afterwards by the wide32 family.
+// No CPU alignment code lives here: if CUDA is unavailable every compute entry point fails.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,8 +49,37 @@ struct DevBuf {                                   // grow-only device buffer, re
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+template <class T>
+struct HostBuf {                                  // grow-only pinned host buffer (sources of async copies)
+    T* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
 
-struct ClassRange { int R; uint32_t first, count, max_n; };
+struct ClassRange { int R; uint32_t first, count, max_n; };   // first: pair-pair index inside its segment
+
+struct Segment {
+    uint64_t first = 0, count = 0;                // pairs [first, first + count)
+    uint64_t pp_first = 0, n_pp = 0;              // slice of the batch-wide pair-pair arrays
+    uint64_t chunks = 0, rowbest_words = 0;       // record size of the segment
+    uint64_t n_wide = 0;                          // pairs of the segment planned for wide32
+    std::vector<ClassRange> classes;
+    int lane = 0;
+    bool flagged = false;                         // > 4 pattern symbols: the whole segment goes to wide32
+};
+
+struct Lane {                                     // one DP record, reused by every n_lanes-th segment
+    DevBuf<Chunk> codes;
+    DevBuf<uint32_t> rowbest;
+    cudaEvent_t tb_done = nullptr;                // last traceback that read this record
+};
 
 // host-side state of the wide32 family for the current batch
 struct WideState {
@@ -63,37 +99,51 @@ struct WideState {
     }
 };
 
+constexpr int MAX_LANES = 2;
+constexpr uint64_t SEG_MIN_PAIRS = 2048;          // a segment is never closed below this many pairs
+
 } // namespace
 
 struct b2a_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int n_lanes = 1;
+    int exp_bits = 0;                             // B2A_EXP: experiment toggles
+    bool trace = false;                           // B2A_TRACE=1: per-segment timeline of b2a_align_batch on stderr
+    uint64_t seg_budget_bytes = 8ull << 30;       // record bytes per segment (B2A_SEG_MB overrides)
+    uint64_t seg_max_pairs = 1ull << 17;          // pairs per segment of b2a_align_batch (B2A_SEG_PAIRS overrides)
+    uint64_t seg_first_pairs = 1ull << 14;        // its first segment (then doubling): the kernels start after a short copy
+    uint64_t seg_resident_pairs = 1ull << 20;     // pairs per segment of b2a_batch_upload / b2a_batch_run
+    // s_fill runs the fill kernels back to back; s_tb (higher priority) runs the tracebacks, so the
+    // latency-bound walk of segment k fills the issue slots the ALU-bound fill of segment k+1 leaves idle
+    cudaStream_t s_copy = nullptr, s_down = nullptr, s_fill = nullptr, s_tb = nullptr;
+    Lane lanes[MAX_LANES];
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ev_pool;             // per segment: ready, fill start, fill end, traceback end
     std::string err;
 
     // batch state
     bool have_batch = false, ran = false;
     b2a_params prm{};
     uint64_t n_pairs = 0;
-    Short16Plan plan{0, 0, 0};
     int K = 0;
-    uint8_t sym[4] = {0, 0, 0, 0};
-    int nsym = 0;
     int tb_opt = 0;                               // walker tuning bits (B2A_TB_OPT overrides, for experiments)
-    bool alpha4 = false;                          // pattern alphabet of the batch has <= 4 symbols
-    std::vector<ClassRange> classes;
+    std::vector<Segment> segs;
     std::vector<uint32_t> wide_pairs;             // pairs served by the wide32 family
-    std::vector<uint64_t> h_pat_off, h_txt_off, h_ops_off;
-    uint64_t total_ops_words = 0;
+    uint64_t total_ops_words = 0, n_pp_total = 0;
     uint64_t cells = 0, fill_bytes = 0, launches = 0, h2d = 0, d2h = 0;
+    float last_fill_ms = 0, last_tb_ms = 0, last_total_ms = 0;
 
     DevBuf<uint8_t> d_pat, d_txt;
     DevBuf<uint64_t> d_pat_off, d_txt_off, d_code_off, d_ops_off;
     DevBuf<PPDesc> d_pps;
-    DevBuf<Chunk> d_codes;
-    DevBuf<uint32_t> d_rowbest, d_ops, d_mask;
+    DevBuf<uint32_t> d_ops;
+    DevBuf<AlphaInfo> d_alpha;                    // one per segment + one for the whole batch (wide32)
     DevBuf<PairResult> d_results;
+    HostBuf<PPDesc> h_pps;
+    HostBuf<uint64_t> h_code_off, h_ops_off;
+    HostBuf<AlphaInfo> h_alpha;
+    size_t alpha_slots = 0;
     WideState wide;
 };
 
@@ -106,8 +156,8 @@ int cuda_fail(b2a_ctx* c, cudaError_t e, const char* where) {
 }
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); } while (0)
 
-// 256-bit presence mask of the bytes in [p, p+n)
-__global__ void alphabet_kernel(const uint8_t* __restrict__ p, uint64_t n, uint32_t* __restrict__ mask) {
+// 256-bit presence mask of the bytes in [p, p+n), OR-ed into info->mask
+__global__ void alphabet_kernel(const uint8_t* __restrict__ p, uint64_t n, AlphaInfo* __restrict__ info) {
     __shared__ uint32_t s[8];
     if (threadIdx.x < 8) s[threadIdx.x] = 0;
     __syncthreads();
@@ -124,7 +174,23 @@ __global__ void alphabet_kernel(const uint8_t* __restrict__ p, uint64_t n, uint3
         if ((threadIdx.x & 31) == 0 && v) atomicOr(&s[k], v);
     }
     __syncthreads();
-    if (threadIdx.x < 8 && s[threadIdx.x]) atomicOr(&mask[threadIdx.x], s[threadIdx.x]);
+    if (threadIdx.x < 8 && s[threadIdx.x]) atomicOr(&info->mask[threadIdx.x], s[threadIdx.x]);
+}
+// mask -> the (<= 4) symbols the PRMT score tables are built for
+__global__ void alphabet_finish_kernel(AlphaInfo* __restrict__ info) {
+    if (threadIdx.x != 0) return;
+    int ns = 0, many = 0;
+    uint8_t sym[4] = {0, 0, 0, 0};
+    for (int b = 0; b < 256; ++b)
+        if (info->mask[b >> 5] & (1u << (b & 31))) { if (ns == 4) { many = 1; break; } sym[ns++] = (uint8_t)b; }
+    for (int c = 0; c < 4; ++c) info->sym[c] = sym[c];
+    info->nsym = ns; info->too_many = many;
+}
+void alpha_from_mask(AlphaInfo& a) {
+    a.nsym = 0; a.too_many = 0;
+    for (int c = 0; c < 4; ++c) a.sym[c] = 0;
+    for (int b = 0; b < 256; ++b)
+        if (a.mask[b >> 5] & (1u << (b & 31))) { if (a.nsym == 4) { a.too_many = 1; break; } a.sym[a.nsym++] = (uint8_t)b; }
 }
 
 template <int R, int K>
@@ -166,7 +232,7 @@ cudaError_t launch_fill(int K, int R, bool local, const FillArgs& a, cudaStream_
     return cudaErrorInvalidValue;
 }
 cudaError_t launch_tb(int K, bool local, const TbArgs& a, cudaStream_t st) {
-    const unsigned threads = 128, grid = (2u * a.n_pp + threads - 1) / threads;
+    const unsigned threads = TB_THREADS, grid = (2u * a.n_pp + threads - 1) / threads;
     switch (K * 2 + (local ? 1 : 0)) {
         case 4:  short16_traceback_kernel<2, false><<<grid, threads, 0, st>>>(a); break;
         case 5:  short16_traceback_kernel<2, true><<<grid, threads, 0, st>>>(a); break;
@@ -223,7 +289,7 @@ cudaError_t launch_wide_tb(int K, bool local, const WideTbArgs& a, cudaStream_t 
     return cudaGetLastError();
 }
 
-int wide_plan(b2a_ctx* ctx, const uint64_t* pat_off, const uint64_t* txt_off, bool store)
+int wide_plan(b2a_ctx* ctx, const uint64_t* pat_off, const uint64_t* txt_off, bool store, bool alpha4, cudaStream_t st)
 {
     WideState& W = ctx->wide;
     const b2a_params& prm = ctx->prm;
@@ -231,7 +297,7 @@ int wide_plan(b2a_ctx* ctx, const uint64_t* pat_off, const uint64_t* txt_off, bo
     W.chunks = W.bound_ints = W.rowbest_words = W.prog_words = 0;
     W.K = delta_bits_wide(prm.match, prm.mismatch, prm.gap);
     W.store = store;
-    W.alpha4 = ctx->alpha4 && prm.match <= 127 && prm.match >= -128 && prm.mismatch <= 127 && prm.mismatch >= -128;
+    W.alpha4 = alpha4 && prm.match <= 127 && prm.match >= -128 && prm.mismatch <= 127 && prm.mismatch >= -128;
     const int CS = 2 * (32 / W.K);
     uint32_t max_bands = 0;
     for (uint32_t k : ctx->wide_pairs) {
@@ -255,11 +321,11 @@ int wide_plan(b2a_ctx* ctx, const uint64_t* pat_off, const uint64_t* txt_off, bo
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return W.pairs[a].nbands > W.pairs[b].nbands; });
     for (uint32_t b = 0; b < max_bands; ++b)
         for (uint32_t i : order) { if (W.pairs[i].nbands <= b) break; W.tasks.push_back(WideTask{i, b}); }
-    cudaStream_t st = ctx->stream;
     CU(W.d_pairs.reserve(W.pairs.size())); CU(W.d_tasks.reserve(W.tasks.size()));
     CU(W.d_codes.reserve(W.chunks)); CU(W.d_bound.reserve(W.bound_ints)); CU(W.d_final.reserve(W.pairs.size()));
     CU(W.d_rowbest.reserve(W.rowbest_words)); CU(W.d_progress.reserve(W.prog_words + 1));
-    CU(cudaMemcpyAsync(W.d_pairs.p, W.pairs.data(), W.pairs.size() * sizeof(WidePair), cudaMemcpyHostToDevice, st));
+    // the vectors outlive the copies: every caller synchronises `st` before the next batch touches them
+    if (!W.pairs.empty()) CU(cudaMemcpyAsync(W.d_pairs.p, W.pairs.data(), W.pairs.size() * sizeof(WidePair), cudaMemcpyHostToDevice, st));
     if (!W.tasks.empty()) CU(cudaMemcpyAsync(W.d_tasks.p, W.tasks.data(), W.tasks.size() * sizeof(WideTask), cudaMemcpyHostToDevice, st));
     ctx->h2d += W.pairs.size() * sizeof(WidePair) + W.tasks.size() * sizeof(WideTask);
     ctx->fill_bytes += W.chunks * sizeof(Chunk);
@@ -279,8 +345,7 @@ int wide_fill(b2a_ctx* ctx, cudaStream_t st, uint64_t* launches)
     a.final_score = W.d_final.p;
     a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap;
     a.radix = W.K < 32 ? (1u << W.K) : 0u;
-    for (int s = 0; s < 4; ++s) a.sym[s] = ctx->sym[s];
-    a.nsym = ctx->nsym;
+    a.alpha = ctx->d_alpha.p + (ctx->alpha_slots - 1);
     const unsigned need = (unsigned)((W.tasks.size() + WIDE_WARPS - 1) / WIDE_WARPS);
     const unsigned grid = std::min<unsigned>(need, (unsigned)ctx->sm_count * 8u);
     CU(launch_wide_fill(W.K, prm.mode == B2A_MODE_LOCAL, W.store, W.alpha4, a, grid, st));
@@ -306,6 +371,351 @@ int wide_traceback(b2a_ctx* ctx, cudaStream_t st, uint64_t* launches, bool score
     return B2A_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// short16 family: segments
+// ---------------------------------------------------------------------------------------------
+cudaEvent_t* seg_events(b2a_ctx* ctx, size_t si) {          // 4 events per segment, created on demand
+    while (ctx->ev_pool.size() < 4 * (si + 1)) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_pool.data() + 4 * si;
+}
+
+// fill + traceback kernels of one segment on its lane
+int launch_segment(b2a_ctx* ctx, size_t si, uint64_t* launches)
+{
+    Segment& sg = ctx->segs[si];
+    if (sg.classes.empty() || sg.flagged) return B2A_OK;
+    const b2a_params& prm = ctx->prm;
+    const bool local = prm.mode == B2A_MODE_LOCAL, want_ops = (prm.flags & B2A_WANT_OPS) != 0;
+    Lane& ln = ctx->lanes[sg.lane];
+    cudaStream_t st = ctx->s_fill;
+    cudaEvent_t* ev = seg_events(ctx, si);
+    if (!ev) return fail(ctx, B2A_ERR_CUDA, "cudaEventCreate failed");
+    if (sg.chunks > ln.codes.cap || sg.rowbest_words > ln.rowbest.cap) {
+        CU(cudaStreamSynchronize(ctx->s_fill)); CU(cudaStreamSynchronize(ctx->s_tb));   // the lane's record is about to be reallocated
+        CU(ln.codes.reserve(sg.chunks));
+        if (local) CU(ln.rowbest.reserve(sg.rowbest_words));
+    }
+    CU(cudaStreamWaitEvent(st, ev[0], 0));                   // inputs + plan of this segment are on the device
+    CU(cudaStreamWaitEvent(st, ln.tb_done, 0));              // the previous user of this lane's record has been walked
+    CU(cudaEventRecord(ev[1], st));
+    const AlphaInfo* alpha = ctx->d_alpha.p + si;
+    for (const ClassRange& c : sg.classes) {
+        Short16Plan pl{0, 0, 0};
+        short16_plan(prm.mode, (uint32_t)c.R * 32u, c.max_n, prm.match, prm.mismatch, prm.gap, pl);   // bias for the class' largest shape
+        FillArgs a{};
+        a.pat = ctx->d_pat.p; a.txt = ctx->d_txt.p; a.pat_off = ctx->d_pat_off.p; a.txt_off = ctx->d_txt_off.p;
+        a.pps = ctx->d_pps.p + sg.pp_first + c.first; a.code_off = ctx->d_code_off.p + sg.pp_first + c.first; a.codes = ln.codes.p;
+        a.rowbest = local ? ln.rowbest.p + (size_t)c.first * c.R * 32 : nullptr;
+        a.n_pp = c.count; a.tbl_cap = (c.max_n + 3u) & ~3u;
+        a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.bias = pl.bias;
+        a.radix = 1u << ctx->K;
+        a.alpha = alpha;
+        CU(launch_fill(ctx->K, c.R, local, a, st));
+        ++*launches;
+    }
+    CU(cudaEventRecord(ev[2], st));
+    st = ctx->s_tb;
+    CU(cudaStreamWaitEvent(st, ev[2], 0));
+    for (const ClassRange& c : sg.classes) {
+        Short16Plan pl{0, 0, 0};
+        short16_plan(prm.mode, (uint32_t)c.R * 32u, c.max_n, prm.match, prm.mismatch, prm.gap, pl);
+        TbArgs a{};
+        a.pat = ctx->d_pat.p; a.txt = ctx->d_txt.p; a.pat_off = ctx->d_pat_off.p; a.txt_off = ctx->d_txt_off.p;
+        a.pps = ctx->d_pps.p + sg.pp_first + c.first; a.code_off = ctx->d_code_off.p + sg.pp_first + c.first; a.codes = ln.codes.p;
+        a.rowbest = local ? ln.rowbest.p + (size_t)c.first * c.R * 32 : nullptr;
+        a.results = ctx->d_results.p; a.ops = want_ops ? ctx->d_ops.p : nullptr; a.ops_off = ctx->d_ops_off.p;
+        a.n_pp = c.count; a.R = c.R;
+        a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.bias = pl.bias;
+        a.opt = ctx->tb_opt;
+        a.alpha = alpha;
+        CU(launch_tb(ctx->K, local, a, st));
+        ++*launches;
+    }
+    CU(cudaEventRecord(ev[3], st));
+    CU(cudaEventRecord(ln.tb_done, st));
+    return B2A_OK;
+}
+
+// s_fill waits for every traceback queued so far (the wide32 phase and the end-of-run event follow on s_fill)
+int join_tracebacks(b2a_ctx* ctx) {
+    for (int l = 0; l < MAX_LANES; ++l) CU(cudaStreamWaitEvent(ctx->s_fill, ctx->lanes[l].tb_done, 0));
+    return B2A_OK;
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// Cuts the batch into segments, queues the copies, plans, and (pipelined == true) launches every
+// segment as soon as it is planned and returns the result records.  With pipelined == false the
+// batch ends up resident and planned; b2a_batch_run launches it.
+int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const uint64_t* pat_off,
+                  const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs, bool pipelined, b2a_result* results)
+{
+    if (!ctx) return B2A_ERR_ARG;
+    if (!prm || !pat_off || !txt_off || (prm->mode != B2A_MODE_GLOBAL && prm->mode != B2A_MODE_LOCAL))
+        return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: null argument or bad mode");
+    if (n_pairs > 0x7FFFFFF0ull) return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: too many pairs");
+    if (pipelined && !results && n_pairs) return fail(ctx, B2A_ERR_ARG, "b2a_align_batch: null results");
+    CU(cudaSetDevice(ctx->device));
+    // a previous batch may still own the pinned plan arrays / device buffers
+    CU(cudaStreamSynchronize(ctx->s_copy)); CU(cudaStreamSynchronize(ctx->s_down));
+    CU(cudaStreamSynchronize(ctx->s_fill)); CU(cudaStreamSynchronize(ctx->s_tb));
+    ctx->have_batch = false; ctx->ran = false;
+    ctx->prm = *prm; ctx->n_pairs = n_pairs;
+    ctx->segs.clear(); ctx->wide_pairs.clear();
+    ctx->cells = ctx->fill_bytes = ctx->launches = ctx->h2d = ctx->d2h = 0;
+    ctx->n_pp_total = 0;
+    const uint64_t pat_bytes = n_pairs ? pat_off[n_pairs] : 0, txt_bytes = n_pairs ? txt_off[n_pairs] : 0;
+    if ((pat_bytes && !pat) || (txt_bytes && !txt)) return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: null sequence buffer");
+    // Appendix A.8: (m+n)*max|score| must stay inside int32 (beyond that the reference itself is undefined)
+    const int64_t smag = std::max<int64_t>({std::llabs((long long)prm->match), std::llabs((long long)prm->mismatch),
+                                            std::llabs((long long)prm->gap)});
+    const bool local = prm->mode == B2A_MODE_LOCAL, want_ops = (prm->flags & B2A_WANT_OPS) != 0;
+    const bool score_only = (prm->flags & B2A_SCORE_ONLY) != 0;
+    ctx->K = delta_bits(prm->match, prm->mismatch, prm->gap);
+    const int CS = ctx->K ? chunk_steps(ctx->K) : 24;
+
+    // ---- batch-wide buffers (grow-only) ----
+    const uint64_t ops_bound = (pat_bytes + txt_bytes) / 16 + 2 * n_pairs + 2;     // >= sum((m+n+15)/16 + 1)
+    ctx->alpha_slots = (size_t)(n_pairs / SEG_MIN_PAIRS + 3);        // >= segments + 1
+    CU(ctx->d_pat.reserve(pat_bytes + 16)); CU(ctx->d_txt.reserve(txt_bytes + 16));
+    CU(ctx->d_pat_off.reserve(n_pairs + 1)); CU(ctx->d_txt_off.reserve(n_pairs + 1));
+    CU(ctx->d_pps.reserve(n_pairs)); CU(ctx->d_code_off.reserve(n_pairs));
+    CU(ctx->h_pps.reserve(n_pairs)); CU(ctx->h_code_off.reserve(n_pairs)); CU(ctx->h_ops_off.reserve(n_pairs + 1));
+    CU(ctx->d_results.reserve(n_pairs));
+    CU(ctx->d_alpha.reserve(ctx->alpha_slots)); CU(ctx->h_alpha.reserve(ctx->alpha_slots));
+    if (want_ops) { CU(ctx->d_ops.reserve(ops_bound)); CU(ctx->d_ops_off.reserve(n_pairs + 1)); }
+    CU(cudaMemsetAsync(ctx->d_alpha.p, 0, ctx->alpha_slots * sizeof(AlphaInfo), ctx->s_copy));
+    const bool async_down = pipelined && results && is_pinned(results) && !(ctx->exp_bits & 1);
+    uint64_t launches = 0;
+    using clk = std::chrono::steady_clock;
+    const clk::time_point t_begin = clk::now();
+    auto ms_since = [&](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+    std::vector<double> tr_host;                                         // per segment: host ms at pass-1 end, plan end, launch end
+    if (ctx->trace) CU(cudaEventRecord(ctx->ev_begin, ctx->s_copy));
+
+    std::vector<PPDesc> pps[SHORT16_MAX_R + 1];
+    std::unordered_map<uint64_t, uint32_t> pending;
+    uint64_t opsw = 0, cells = 0;
+    uint64_t first = 0;
+    while (first < n_pairs) {
+        // ---- pass 1: validate, find the end of the segment, per-pair op offsets ----
+        uint64_t k = first, seg_bytes = 0;
+        const size_t si_next = ctx->segs.size();
+        const uint64_t lim_pairs = !pipelined ? ctx->seg_resident_pairs
+                                 : std::min<uint64_t>(ctx->seg_max_pairs, si_next < 20 ? ctx->seg_first_pairs << si_next : ctx->seg_max_pairs);
+        const uint64_t lim_bytes = pipelined ? ctx->seg_budget_bytes : ~0ull;
+        uint64_t plan_key = ~0ull; bool plan_ok = false; Short16Plan pl{0, 0, 0}; uint64_t pair_bytes = 0;
+        for (; k < n_pairs; ++k) {
+            if (pat_off[k + 1] < pat_off[k] || txt_off[k + 1] < txt_off[k])
+                return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: offsets must be non-decreasing");
+            const uint64_t m64 = pat_off[k + 1] - pat_off[k], n64 = txt_off[k + 1] - txt_off[k];
+            if ((m64 + n64 + 2) * (uint64_t)smag >= 0x7FFFFFFFull || m64 + n64 >= 0x7FFFFFF0ull)
+                return fail(ctx, B2A_ERR_RANGE, "b2a_batch_upload: (m+n)*max|score| exceeds int32 (SURVEY.md A.8)");
+            ctx->h_ops_off.p[k] = opsw;
+            opsw += (m64 + n64 + 15) / 16 + 1;
+            cells += m64 * n64;
+            const uint64_t key = (m64 << 32) | n64;
+            if (key != plan_key) {
+                plan_key = key;
+                plan_ok = !score_only && short16_plan(prm->mode, (uint32_t)m64, (uint32_t)n64, prm->match, prm->mismatch, prm->gap, pl);
+                pair_bytes = plan_ok ? (uint64_t)pl.R * num_chunks((uint32_t)n64, CS) * 32u * sizeof(Chunk) / 2 : 0;
+            }
+            seg_bytes += pair_bytes;
+            const uint64_t cnt = k + 1 - first;
+            if (cnt >= SEG_MIN_PAIRS && !(cnt & 1) && (seg_bytes >= lim_bytes || cnt >= lim_pairs)) { ++k; break; }
+        }
+        if (ctx->trace) tr_host.push_back(ms_since(t_begin));
+        const size_t si = ctx->segs.size();
+        ctx->segs.emplace_back();
+        Segment& sg = ctx->segs.back();
+        sg.first = first; sg.count = k - first; sg.lane = (int)(si % (size_t)ctx->n_lanes);
+        sg.pp_first = ctx->n_pp_total;
+        if (si + 2 > ctx->alpha_slots) return fail(ctx, B2A_ERR_STATE, "internal: segment count exceeds its bound");
+
+        // ---- queue the copies of this segment's inputs ----
+        cudaStream_t sc = ctx->s_copy;
+        const uint64_t pb0 = pat_off[first], pb1 = pat_off[k], tb0 = txt_off[first], tb1 = txt_off[k];
+        if (pb1 > pb0) CU(cudaMemcpyAsync(ctx->d_pat.p + pb0, pat + pb0, pb1 - pb0, cudaMemcpyHostToDevice, sc));
+        if (tb1 > tb0) CU(cudaMemcpyAsync(ctx->d_txt.p + tb0, txt + tb0, tb1 - tb0, cudaMemcpyHostToDevice, sc));
+        CU(cudaMemcpyAsync(ctx->d_pat_off.p + first, pat_off + first, (sg.count + 1) * 8, cudaMemcpyHostToDevice, sc));
+        CU(cudaMemcpyAsync(ctx->d_txt_off.p + first, txt_off + first, (sg.count + 1) * 8, cudaMemcpyHostToDevice, sc));
+        ctx->h2d += (pb1 - pb0) + (tb1 - tb0) + 2 * (sg.count + 1) * 8;
+
+        // ---- pass 2 (overlaps the copies): zip pairs of identical shape into pair-pairs, group by R ----
+        for (auto& v : pps) v.clear();
+        pending.clear();
+        bool have_last = false; uint64_t last_key = 0; uint32_t last_idx = 0;
+        plan_key = ~0ull; plan_ok = false;
+        for (uint64_t q = first; q < k; ++q) {
+            const uint64_t m64 = pat_off[q + 1] - pat_off[q], n64 = txt_off[q + 1] - txt_off[q];
+            const uint32_t m = (uint32_t)m64, n = (uint32_t)n64;
+            const uint64_t key = (m64 << 32) | n64;
+            if (key != plan_key) { plan_key = key; plan_ok = !score_only && short16_plan(prm->mode, m, n, prm->match, prm->mismatch, prm->gap, pl); }
+            if (!plan_ok) { ctx->wide_pairs.push_back((uint32_t)q); ++sg.n_wide; continue; }
+            if (have_last && key == last_key) { pps[pl.R].push_back(PPDesc{last_idx, (uint32_t)q, m, n}); have_last = false; continue; }
+            if (have_last) {                                             // the previous pair found no neighbour: park it
+                auto it = pending.find(last_key);
+                const uint32_t lm = (uint32_t)(last_key >> 32), ln = (uint32_t)last_key;
+                if (it != pending.end()) { pps[(lm + 31) / 32].push_back(PPDesc{it->second, last_idx, lm, ln}); pending.erase(it); }
+                else pending[last_key] = last_idx;
+                have_last = false;
+            }
+            auto it = pending.find(key);
+            if (it != pending.end()) { pps[pl.R].push_back(PPDesc{it->second, (uint32_t)q, m, n}); pending.erase(it); }
+            else { have_last = true; last_key = key; last_idx = (uint32_t)q; }
+        }
+        if (have_last) {
+            auto it = pending.find(last_key);
+            const uint32_t lm = (uint32_t)(last_key >> 32), ln = (uint32_t)last_key;
+            if (it != pending.end()) { pps[(lm + 31) / 32].push_back(PPDesc{it->second, last_idx, lm, ln}); pending.erase(it); }
+            else pending[last_key] = last_idx;
+        }
+        for (auto& kv : pending) {                                       // unpaired leftovers: both halves carry the same pair
+            const uint32_t lm = (uint32_t)(kv.first >> 32), ln = (uint32_t)kv.first;
+            pps[(lm + 31) / 32].push_back(PPDesc{kv.second, kv.second, lm, ln});
+        }
+        PPDesc* hp = ctx->h_pps.p + sg.pp_first;
+        uint64_t* hc = ctx->h_code_off.p + sg.pp_first;
+        uint64_t npp = 0, chunks = 0, rb = 0;
+        for (int R = 1; R <= SHORT16_MAX_R; ++R) {
+            if (pps[R].empty()) continue;
+            ClassRange cr{R, (uint32_t)npp, (uint32_t)pps[R].size(), 0};
+            for (const PPDesc& d : pps[R]) {
+                hp[npp] = d; hc[npp] = chunks; ++npp;
+                chunks += (uint64_t)R * num_chunks(d.n, CS) * 32u;
+                cr.max_n = std::max(cr.max_n, d.n);
+            }
+            rb = std::max<uint64_t>(rb, (uint64_t)(cr.first + cr.count) * R * 32u);
+            sg.classes.push_back(cr);
+        }
+        sg.n_pp = npp; sg.chunks = chunks; sg.rowbest_words = local ? rb : 0;
+        ctx->n_pp_total += npp;
+        ctx->fill_bytes += chunks * sizeof(Chunk);
+        if (npp) {
+            CU(cudaMemcpyAsync(ctx->d_pps.p + sg.pp_first, hp, npp * sizeof(PPDesc), cudaMemcpyHostToDevice, sc));
+            CU(cudaMemcpyAsync(ctx->d_code_off.p + sg.pp_first, hc, npp * 8, cudaMemcpyHostToDevice, sc));
+            ctx->h2d += npp * (sizeof(PPDesc) + 8);
+        }
+        if (want_ops) {
+            ctx->h_ops_off.p[k] = opsw;                                  // rewritten by the next segment with the same value
+            CU(cudaMemcpyAsync(ctx->d_ops_off.p + first, ctx->h_ops_off.p + first, (sg.count + 1) * 8, cudaMemcpyHostToDevice, sc));
+            ctx->h2d += (sg.count + 1) * 8;
+        }
+        // pattern alphabet of the segment, on the device, in copy-stream order right behind the bytes
+        cudaEvent_t* ev = seg_events(ctx, si);
+        if (!ev) return fail(ctx, B2A_ERR_CUDA, "cudaEventCreate failed");
+        CU(cudaEventRecord(ev[0], sc));
+        // Pattern alphabet of the segment, found on the device.  NOT on the copy stream: a kernel there
+        // queues behind the running traceback and stalls every later copy (measured: +25 % end to end).
+        CU(cudaStreamWaitEvent(ctx->s_fill, ev[0], 0));
+        if (pb1 > pb0) {
+            const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count * 4u, (pb1 - pb0 + 4095) / 4096);
+            alphabet_kernel<<<grid, 256, 0, ctx->s_fill>>>(ctx->d_pat.p + pb0, pb1 - pb0, ctx->d_alpha.p + si);
+            CU(cudaGetLastError());
+            ++launches;
+        }
+        alphabet_finish_kernel<<<1, 32, 0, ctx->s_fill>>>(ctx->d_alpha.p + si);
+        CU(cudaGetLastError());
+        ++launches;
+        if (ctx->trace) tr_host.push_back(ms_since(t_begin));
+
+        if (pipelined) {
+            int rc = launch_segment(ctx, si, &launches);
+            if (rc != B2A_OK) return rc;
+            if (async_down && !sg.classes.empty()) {
+                CU(cudaStreamWaitEvent(ctx->s_down, ev[3], 0));
+                CU(cudaMemcpyAsync(results + first, ctx->d_results.p + first, sg.count * sizeof(b2a_result), cudaMemcpyDeviceToHost, ctx->s_down));
+                ctx->d2h += sg.count * sizeof(b2a_result);
+            }
+        }
+        if (ctx->trace) tr_host.push_back(ms_since(t_begin));
+        first = k;
+    }
+    ctx->h_ops_off.p[n_pairs] = opsw;
+    ctx->total_ops_words = opsw;
+    ctx->cells = cells;
+
+    // ---- everything is queued: wait for the segments, collect the alphabets, decide what wide32 has to serve ----
+    cudaStream_t s0 = ctx->s_fill;
+    { int rc = join_tracebacks(ctx); if (rc != B2A_OK) return rc; }
+    CU(cudaMemcpyAsync(ctx->h_alpha.p, ctx->d_alpha.p, ctx->alpha_slots * sizeof(AlphaInfo), cudaMemcpyDeviceToHost, s0));
+    CU(cudaStreamSynchronize(s0));
+    AlphaInfo batch_alpha{};
+    bool any_flagged = false;
+    for (size_t si = 0; si < ctx->segs.size(); ++si) {
+        const AlphaInfo& a = ctx->h_alpha.p[si];
+        for (int w = 0; w < 8; ++w) batch_alpha.mask[w] |= a.mask[w];
+        Segment& sg = ctx->segs[si];
+        if (a.too_many && !sg.classes.empty()) {
+            sg.flagged = true; any_flagged = true;
+            for (uint64_t q = 0; q < sg.n_pp; ++q) {
+                const PPDesc& d = ctx->h_pps.p[sg.pp_first + q];
+                ctx->wide_pairs.push_back(d.a); if (d.b != d.a) ctx->wide_pairs.push_back(d.b);
+            }
+            ctx->fill_bytes -= sg.chunks * sizeof(Chunk);
+        }
+    }
+    if (any_flagged) std::sort(ctx->wide_pairs.begin(), ctx->wide_pairs.end());
+    alpha_from_mask(batch_alpha);
+    ctx->h_alpha.p[ctx->alpha_slots - 1] = batch_alpha;
+    if (!ctx->wide_pairs.empty()) {
+        CU(cudaMemcpyAsync(ctx->d_alpha.p + (ctx->alpha_slots - 1), ctx->h_alpha.p + (ctx->alpha_slots - 1), sizeof(AlphaInfo), cudaMemcpyHostToDevice, s0));
+        int rc = wide_plan(ctx, pat_off, txt_off, !score_only, !batch_alpha.too_many, s0);
+        if (rc != B2A_OK) return rc;
+    } else { ctx->wide.pairs.clear(); ctx->wide.tasks.clear(); }
+
+    if (!pipelined) {
+        // resident mode: size the lanes' records now so that b2a_batch_run never allocates
+        for (const Segment& sg : ctx->segs) {
+            if (sg.flagged) continue;
+            Lane& ln = ctx->lanes[sg.lane];
+            CU(ln.codes.reserve(sg.chunks));
+            if (local) CU(ln.rowbest.reserve(sg.rowbest_words));
+        }
+        CU(cudaStreamSynchronize(s0));
+        ctx->launches = launches;
+        ctx->have_batch = true;
+        return B2A_OK;
+    }
+
+    // ---- pipelined mode: the wide32 phase (if any) runs behind the segments, then the records come back ----
+    if (!ctx->wide_pairs.empty()) {
+        int rc = wide_fill(ctx, s0, &launches);
+        if (rc != B2A_OK) return rc;
+        rc = wide_traceback(ctx, s0, &launches, score_only);
+        if (rc != B2A_OK) return rc;
+    }
+    CU(cudaStreamSynchronize(s0));
+    if (n_pairs && (!async_down || !ctx->wide_pairs.empty())) {
+        CU(cudaMemcpyAsync(results, ctx->d_results.p, n_pairs * sizeof(b2a_result), cudaMemcpyDeviceToHost, ctx->s_down));
+        ctx->d2h = n_pairs * sizeof(b2a_result);
+    }
+    CU(cudaStreamSynchronize(ctx->s_down));
+    if (ctx->trace) {
+        std::fprintf(stderr, "[b2a trace] %llu pairs, %zu segments, host total %.2f ms\n", (unsigned long long)n_pairs, ctx->segs.size(), ms_since(t_begin));
+        for (size_t si = 0; si < ctx->segs.size(); ++si) {
+            const Segment& sg = ctx->segs[si];
+            cudaEvent_t* ev = ctx->ev_pool.data() + 4 * si;
+            float g[4] = {0, 0, 0, 0};
+            for (int e = 0; e < 4; ++e) if (e == 0 || !(sg.classes.empty() || sg.flagged)) cudaEventElapsedTime(&g[e], ctx->ev_begin, ev[e]);
+            std::fprintf(stderr, "[b2a trace] seg %2zu pairs %7llu | host: scanned %6.2f planned %6.2f launched %6.2f | device: inputs %6.2f fill %6.2f..%6.2f tb ..%6.2f\n",
+                         si, (unsigned long long)sg.count, tr_host[3 * si], tr_host[3 * si + 1], tr_host[3 * si + 2], g[0], g[1], g[2], g[3]);
+        }
+        cudaGetLastError();
+    }
+    ctx->launches = launches;
+    ctx->have_batch = true; ctx->ran = true;
+    return B2A_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -324,26 +734,53 @@ b2a_ctx* b2a_create(int device) {
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
-        prop.major < 10 ||                                   // kernels are sm_100a only: no fallback
-        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        prop.major < 10) {                                   // kernels are sm_100a only: no fallback
         delete ctx; cudaGetLastError(); return nullptr;
     }
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = std::getenv("B2A_TB_OPT")) ctx->tb_opt = std::atoi(e);
-    for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { b2a_destroy(ctx); return nullptr; }
+    if (const char* e = std::getenv("B2A_EXP")) ctx->exp_bits = std::atoi(e);
+    if (const char* e = std::getenv("B2A_TRACE")) ctx->trace = std::atoi(e) != 0;
+    if (const char* e = std::getenv("B2A_LANES")) ctx->n_lanes = std::max(1, std::min(MAX_LANES, std::atoi(e)));
+    if (const char* e = std::getenv("B2A_SEG_MB")) ctx->seg_budget_bytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;
+    if (const char* e = std::getenv("B2A_SEG_PAIRS")) ctx->seg_max_pairs = ctx->seg_resident_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, std::strtoull(e, nullptr, 10));
+    if (const char* e = std::getenv("B2A_SEG_FIRST")) ctx->seg_first_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, std::strtoull(e, nullptr, 10));
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // numerically lower = higher priority
+    bool ok = cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_down, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&ctx->s_fill, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&ctx->s_tb, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
+    for (int l = 0; l < MAX_LANES && ok; ++l)
+        ok = cudaEventCreateWithFlags(&ctx->lanes[l].tb_done, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { b2a_destroy(ctx); cudaGetLastError(); return nullptr; }
     return ctx;
 }
 
 void b2a_destroy(b2a_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->s_copy) cudaStreamSynchronize(ctx->s_copy);
+    if (ctx->s_down) cudaStreamSynchronize(ctx->s_down);
+    if (ctx->s_fill) cudaStreamSynchronize(ctx->s_fill);
+    if (ctx->s_tb) cudaStreamSynchronize(ctx->s_tb);
+    for (auto& ln : ctx->lanes) {
+        ln.codes.release(); ln.rowbest.release();
+        if (ln.tb_done) cudaEventDestroy(ln.tb_done);
+    }
+    if (ctx->s_fill) cudaStreamDestroy(ctx->s_fill);
+    if (ctx->s_tb) cudaStreamDestroy(ctx->s_tb);
     ctx->d_pat.release(); ctx->d_txt.release(); ctx->d_pat_off.release(); ctx->d_txt_off.release();
-    ctx->d_code_off.release(); ctx->d_ops_off.release(); ctx->d_pps.release(); ctx->d_codes.release();
-    ctx->d_rowbest.release(); ctx->d_ops.release(); ctx->d_mask.release(); ctx->d_results.release();
+    ctx->d_code_off.release(); ctx->d_ops_off.release(); ctx->d_pps.release();
+    ctx->d_ops.release(); ctx->d_alpha.release(); ctx->d_results.release();
+    ctx->h_pps.release(); ctx->h_code_off.release(); ctx->h_ops_off.release(); ctx->h_alpha.release();
     ctx->wide.release();
-    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (auto& e : ctx->ev_pool) if (e) cudaEventDestroy(e);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    if (ctx->s_down) cudaStreamDestroy(ctx->s_down);
     delete ctx;
 }
 
@@ -359,147 +796,7 @@ void b2a_host_free(void* p) { if (p) cudaFreeHost(p); }
 int b2a_batch_upload(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const uint64_t* pat_off,
                      const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs)
 {
-    if (!ctx) return B2A_ERR_ARG;
-    if (!prm || !pat_off || !txt_off || (prm->mode != B2A_MODE_GLOBAL && prm->mode != B2A_MODE_LOCAL))
-        return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: null argument or bad mode");
-    if (n_pairs > 0x7FFFFFF0ull) return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: too many pairs");
-    CU(cudaSetDevice(ctx->device));
-    ctx->have_batch = false; ctx->ran = false;
-    ctx->prm = *prm; ctx->n_pairs = n_pairs;
-    ctx->classes.clear(); ctx->wide_pairs.clear();
-    ctx->cells = ctx->fill_bytes = ctx->launches = ctx->h2d = ctx->d2h = 0;
-    const uint64_t pat_bytes = n_pairs ? pat_off[n_pairs] : 0, txt_bytes = n_pairs ? txt_off[n_pairs] : 0;
-    if ((pat_bytes && !pat) || (txt_bytes && !txt)) return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: null sequence buffer");
-    // Appendix A.8: (m+n)*max|score| must stay inside int32 (beyond that the reference itself is undefined)
-    const int64_t smag = std::max<int64_t>({std::llabs((long long)prm->match), std::llabs((long long)prm->mismatch),
-                                            std::llabs((long long)prm->gap)});
-
-    cudaStream_t st = ctx->stream;
-    CU(ctx->d_pat.reserve(pat_bytes + 16)); CU(ctx->d_txt.reserve(txt_bytes + 16));
-    CU(ctx->d_pat_off.reserve(n_pairs + 1)); CU(ctx->d_txt_off.reserve(n_pairs + 1));
-    CU(ctx->d_mask.reserve(8));
-    if (pat_bytes) CU(cudaMemcpyAsync(ctx->d_pat.p, pat, pat_bytes, cudaMemcpyHostToDevice, st));
-    if (txt_bytes) CU(cudaMemcpyAsync(ctx->d_txt.p, txt, txt_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_pat_off.p, pat_off, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_txt_off.p, txt_off, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
-    ctx->h2d += pat_bytes + txt_bytes + 2 * (n_pairs + 1) * 8;
-    // pattern alphabet on the device (the PRMT score tables hold 4 symbols)
-    CU(cudaMemsetAsync(ctx->d_mask.p, 0, 32, st));
-    if (pat_bytes) {
-        alphabet_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->d_pat.p, pat_bytes, ctx->d_mask.p);
-        CU(cudaGetLastError());
-        ctx->launches++;
-    }
-    uint32_t mask[8];
-    CU(cudaMemcpyAsync(mask, ctx->d_mask.p, 32, cudaMemcpyDeviceToHost, st));
-
-    // ---- host planning (overlaps the copies above) ----
-    ctx->h_pat_off.assign(pat_off, pat_off + n_pairs + 1);
-    ctx->h_txt_off.assign(txt_off, txt_off + n_pairs + 1);
-    ctx->h_ops_off.resize(n_pairs + 1);
-    std::vector<PPDesc> pps[SHORT16_MAX_R + 1];
-    std::unordered_map<uint64_t, uint32_t> pending;
-    bool have_last = false; uint64_t last_key = 0; uint32_t last_idx = 0;
-    uint64_t plan_key = ~0ull; bool plan_ok = false; Short16Plan pl{0, 0, 0};
-    uint64_t opsw = 0, cells = 0;
-    const bool want_ops = (prm->flags & B2A_WANT_OPS) != 0;
-    for (uint64_t k = 0; k < n_pairs; ++k) {
-        if (pat_off[k + 1] < pat_off[k] || txt_off[k + 1] < txt_off[k])
-            return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: offsets must be non-decreasing");
-        const uint64_t m64 = pat_off[k + 1] - pat_off[k], n64 = txt_off[k + 1] - txt_off[k];
-        if ((m64 + n64 + 2) * (uint64_t)smag >= 0x7FFFFFFFull || m64 + n64 >= 0x7FFFFFF0ull)
-            return fail(ctx, B2A_ERR_RANGE, "b2a_batch_upload: (m+n)*max|score| exceeds int32 (SURVEY.md A.8)");
-        const uint32_t m = (uint32_t)m64, n = (uint32_t)n64;
-        ctx->h_ops_off[k] = opsw;
-        opsw += (m64 + n64 + 15) / 16 + 1;
-        cells += m64 * n64;
-        const uint64_t key = (m64 << 32) | n64;
-        if (key != plan_key) { plan_key = key; plan_ok = short16_plan(prm->mode, m, n, prm->match, prm->mismatch, prm->gap, pl); }
-        if (!plan_ok || (prm->flags & B2A_SCORE_ONLY)) { ctx->wide_pairs.push_back((uint32_t)k); continue; }
-        auto emit = [&](uint32_t a, uint32_t b) { pps[pl.R].push_back(PPDesc{a, b, m, n}); };
-        if (have_last && key == last_key) { emit(last_idx, (uint32_t)k); have_last = false; continue; }
-        if (have_last) {
-            auto it = pending.find(last_key);
-            if (it != pending.end()) {
-                const uint32_t lm = (uint32_t)(last_key >> 32), ln = (uint32_t)last_key;
-                pps[(lm + 31) / 32].push_back(PPDesc{it->second, last_idx, lm, ln});
-                pending.erase(it);
-            } else pending[last_key] = last_idx;
-            have_last = false;
-        }
-        auto it = pending.find(key);
-        if (it != pending.end()) { emit(it->second, (uint32_t)k); pending.erase(it); }
-        else { have_last = true; last_key = key; last_idx = (uint32_t)k; }
-    }
-    if (have_last) {
-        auto it = pending.find(last_key);
-        const uint32_t lm = (uint32_t)(last_key >> 32), ln = (uint32_t)last_key;
-        if (it != pending.end()) { pps[(lm + 31) / 32].push_back(PPDesc{it->second, last_idx, lm, ln}); pending.erase(it); }
-        else pending[last_key] = last_idx;
-    }
-    for (auto& kv : pending) {                                  // unpaired leftovers: both halves carry the same pair
-        const uint32_t lm = (uint32_t)(kv.first >> 32), ln = (uint32_t)kv.first;
-        pps[(lm + 31) / 32].push_back(PPDesc{kv.second, kv.second, lm, ln});
-    }
-    ctx->h_ops_off[n_pairs] = opsw;
-    ctx->total_ops_words = opsw;
-    ctx->cells = cells;
-    ctx->K = delta_bits(prm->match, prm->mismatch, prm->gap);
-    const int CS = ctx->K ? chunk_steps(ctx->K) : 24;
-
-    std::vector<PPDesc> all;
-    std::vector<uint64_t> code_off;
-    uint64_t chunks = 0;
-    for (int R = 1; R <= SHORT16_MAX_R; ++R) {
-        if (pps[R].empty()) continue;
-        ClassRange cr{R, (uint32_t)all.size(), (uint32_t)pps[R].size(), 0};
-        for (const PPDesc& d : pps[R]) {
-            all.push_back(d);
-            code_off.push_back(chunks);
-            chunks += (uint64_t)R * num_chunks(d.n, CS) * 32u;
-            cr.max_n = std::max(cr.max_n, d.n);
-        }
-        ctx->classes.push_back(cr);
-    }
-    CU(cudaStreamSynchronize(st));                               // alphabet mask is on the host now
-    ctx->nsym = 0;
-    bool short_ok = true;
-    for (int b = 0; b < 256 && short_ok; ++b)
-        if (mask[b >> 5] & (1u << (b & 31))) { if (ctx->nsym == 4) short_ok = false; else ctx->sym[ctx->nsym++] = (uint8_t)b; }
-    ctx->alpha4 = short_ok;
-    if (!short_ok && !all.empty()) {
-        // more than 4 distinct pattern symbols: the PRMT tables cannot hold them -> wide family for everything
-        for (const PPDesc& d : all) { ctx->wide_pairs.push_back(d.a); if (d.b != d.a) ctx->wide_pairs.push_back(d.b); }
-        std::sort(ctx->wide_pairs.begin(), ctx->wide_pairs.end());
-        all.clear(); code_off.clear(); ctx->classes.clear(); chunks = 0;
-    }
-    const size_t n_pp = all.size();
-    CU(ctx->d_pps.reserve(n_pp)); CU(ctx->d_code_off.reserve(n_pp));
-    CU(ctx->d_codes.reserve(chunks));
-    CU(ctx->d_results.reserve(n_pairs));
-    if (prm->mode == B2A_MODE_LOCAL) {
-        size_t rb = 0;
-        for (const ClassRange& c : ctx->classes) rb = std::max(rb, (size_t)(c.first + c.count) * c.R * 32);
-        CU(ctx->d_rowbest.reserve(rb));
-    }
-    if (want_ops) { CU(ctx->d_ops.reserve(opsw)); CU(ctx->d_ops_off.reserve(n_pairs + 1)); }
-    if (n_pp) {
-        CU(cudaMemcpyAsync(ctx->d_pps.p, all.data(), n_pp * sizeof(PPDesc), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->d_code_off.p, code_off.data(), n_pp * 8, cudaMemcpyHostToDevice, st));
-        ctx->h2d += n_pp * (sizeof(PPDesc) + 8);
-    }
-    if (want_ops) {
-        CU(cudaMemcpyAsync(ctx->d_ops_off.p, ctx->h_ops_off.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
-        ctx->h2d += (n_pairs + 1) * 8;
-    }
-    ctx->fill_bytes = chunks * sizeof(Chunk);
-    if (!ctx->wide_pairs.empty()) {
-        int rc = wide_plan(ctx, pat_off, txt_off, !(prm->flags & B2A_SCORE_ONLY));
-        if (rc != B2A_OK) return rc;
-    } else { ctx->wide.pairs.clear(); ctx->wide.tasks.clear(); }
-    CU(cudaStreamSynchronize(st));
-    ctx->have_batch = true;
-    return B2A_OK;
+    return batch_prepare(ctx, prm, pat, pat_off, txt, txt_off, n_pairs, false, nullptr);
 }
 
 int b2a_batch_run(b2a_ctx* ctx, float* fill_ms, float* traceback_ms)
@@ -507,52 +804,47 @@ int b2a_batch_run(b2a_ctx* ctx, float* fill_ms, float* traceback_ms)
     if (!ctx) return B2A_ERR_ARG;
     if (!ctx->have_batch) return fail(ctx, B2A_ERR_STATE, "b2a_batch_run: no batch uploaded");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
     const b2a_params& prm = ctx->prm;
-    const bool local = prm.mode == B2A_MODE_LOCAL, want_ops = (prm.flags & B2A_WANT_OPS) != 0;
+    const bool score_only = (prm.flags & B2A_SCORE_ONLY) != 0;
     uint64_t launches = 0;
-    CU(cudaEventRecord(ctx->ev[0], st));
-    for (const ClassRange& c : ctx->classes) {
-        Short16Plan pl{0, 0, 0};
-        short16_plan(prm.mode, (uint32_t)c.R * 32u, c.max_n, prm.match, prm.mismatch, prm.gap, pl);   // bias for the class' largest shape
-        FillArgs a{};
-        a.pat = ctx->d_pat.p; a.txt = ctx->d_txt.p; a.pat_off = ctx->d_pat_off.p; a.txt_off = ctx->d_txt_off.p;
-        a.pps = ctx->d_pps.p + c.first; a.code_off = ctx->d_code_off.p + c.first; a.codes = ctx->d_codes.p;
-        a.rowbest = local ? ctx->d_rowbest.p + (size_t)c.first * c.R * 32 : nullptr;
-        a.n_pp = c.count; a.tbl_cap = (c.max_n + 3u) & ~3u;
-        a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.bias = pl.bias;
-        a.radix = 1u << ctx->K;
-        for (int s = 0; s < 4; ++s) a.sym[s] = ctx->sym[s];
-        a.nsym = ctx->nsym;
-        CU(launch_fill(ctx->K, c.R, local, a, st));
-        ++launches;
+    cudaStream_t s0 = ctx->s_fill;
+    CU(cudaEventRecord(ctx->ev_begin, s0));
+    for (size_t si = 0; si < ctx->segs.size(); ++si) {
+        int rc = launch_segment(ctx, si, &launches);
+        if (rc != B2A_OK) return rc;
     }
-    if (!ctx->wide_pairs.empty()) { int rc = wide_fill(ctx, st, &launches); if (rc != B2A_OK) return rc; }
-    CU(cudaEventRecord(ctx->ev[1], st));
-    for (const ClassRange& c : ctx->classes) {
-        Short16Plan pl{0, 0, 0};
-        short16_plan(prm.mode, (uint32_t)c.R * 32u, c.max_n, prm.match, prm.mismatch, prm.gap, pl);
-        TbArgs a{};
-        a.pat = ctx->d_pat.p; a.txt = ctx->d_txt.p; a.pat_off = ctx->d_pat_off.p; a.txt_off = ctx->d_txt_off.p;
-        a.pps = ctx->d_pps.p + c.first; a.code_off = ctx->d_code_off.p + c.first; a.codes = ctx->d_codes.p;
-        a.rowbest = local ? ctx->d_rowbest.p + (size_t)c.first * c.R * 32 : nullptr;
-        a.results = ctx->d_results.p; a.ops = want_ops ? ctx->d_ops.p : nullptr; a.ops_off = ctx->d_ops_off.p;
-        a.n_pp = c.count; a.R = c.R;
-        a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.bias = pl.bias;
-        a.opt = ctx->tb_opt;
-        CU(launch_tb(ctx->K, local, a, st));
-        ++launches;
+    { int rc = join_tracebacks(ctx); if (rc != B2A_OK) return rc; }
+    cudaEvent_t* wev = seg_events(ctx, ctx->segs.size());          // spare slot: wide32 phase
+    if (!wev) return fail(ctx, B2A_ERR_CUDA, "cudaEventCreate failed");
+    CU(cudaEventRecord(wev[1], s0));
+    if (!ctx->wide_pairs.empty()) { int rc = wide_fill(ctx, s0, &launches); if (rc != B2A_OK) return rc; }
+    CU(cudaEventRecord(wev[2], s0));
+    if (!ctx->wide_pairs.empty()) { int rc = wide_traceback(ctx, s0, &launches, score_only); if (rc != B2A_OK) return rc; }
+    CU(cudaEventRecord(wev[3], s0));
+    CU(cudaEventRecord(ctx->ev_end, s0));
+    CU(cudaStreamSynchronize(s0));
+    float f = 0, t = 0, tot = 0, x = 0;
+    for (size_t si = 0; si <= ctx->segs.size(); ++si) {
+        if (si < ctx->segs.size() && (ctx->segs[si].classes.empty() || ctx->segs[si].flagged)) continue;
+        cudaEvent_t* ev = ctx->ev_pool.data() + 4 * si;
+        CU(cudaEventElapsedTime(&x, ev[1], ev[2])); f += x;
+        CU(cudaEventElapsedTime(&x, ev[2], ev[3])); t += x;
     }
-    if (!ctx->wide_pairs.empty()) { int rc = wide_traceback(ctx, st, &launches, (prm.flags & B2A_SCORE_ONLY) != 0); if (rc != B2A_OK) return rc; }
-    CU(cudaEventRecord(ctx->ev[2], st));
-    CU(cudaStreamSynchronize(st));
-    float f = 0, t = 0;
-    CU(cudaEventElapsedTime(&f, ctx->ev[0], ctx->ev[1]));
-    CU(cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2]));
+    CU(cudaEventElapsedTime(&tot, ctx->ev_begin, ctx->ev_end));
     if (fill_ms) *fill_ms = f;
     if (traceback_ms) *traceback_ms = t;
+    ctx->last_fill_ms = f; ctx->last_tb_ms = t; ctx->last_total_ms = tot;
     ctx->launches += launches;
     ctx->ran = true;
+    return B2A_OK;
+}
+
+int b2a_batch_times(const b2a_ctx* ctx, float* fill_ms, float* traceback_ms, float* total_ms)
+{
+    if (!ctx) return B2A_ERR_ARG;
+    if (fill_ms) *fill_ms = ctx->last_fill_ms;
+    if (traceback_ms) *traceback_ms = ctx->last_tb_ms;
+    if (total_ms) *total_ms = ctx->last_total_ms;
     return B2A_OK;
 }
 
@@ -563,8 +855,8 @@ int b2a_batch_download(b2a_ctx* ctx, b2a_result* results)
     if (!results && ctx->n_pairs) return fail(ctx, B2A_ERR_ARG, "b2a_batch_download: null results");
     CU(cudaSetDevice(ctx->device));
     if (ctx->n_pairs) {
-        CU(cudaMemcpyAsync(results, ctx->d_results.p, ctx->n_pairs * sizeof(b2a_result), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpyAsync(results, ctx->d_results.p, ctx->n_pairs * sizeof(b2a_result), cudaMemcpyDeviceToHost, ctx->s_down));
+        CU(cudaStreamSynchronize(ctx->s_down));
         ctx->d2h += ctx->n_pairs * sizeof(b2a_result);
     }
     return B2A_OK;
@@ -573,11 +865,20 @@ int b2a_batch_download(b2a_ctx* ctx, b2a_result* results)
 int b2a_align_batch(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const uint64_t* pat_off,
                     const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs, b2a_result* results)
 {
-    int rc = b2a_batch_upload(ctx, prm, pat, pat_off, txt, txt_off, n_pairs);
-    if (rc != B2A_OK) return rc;
-    rc = b2a_batch_run(ctx, nullptr, nullptr);
-    if (rc != B2A_OK) return rc;
-    return b2a_batch_download(ctx, results);
+    return batch_prepare(ctx, prm, pat, pat_off, txt, txt_off, n_pairs, true, results);
+}
+
+int b2a_set_option(b2a_ctx* ctx, int option, int64_t value)
+{
+    if (!ctx) return B2A_ERR_ARG;
+    switch (option) {
+        case B2A_OPT_LANES:      if (value < 1 || value > MAX_LANES) break; ctx->n_lanes = (int)value; return B2A_OK;
+        case B2A_OPT_SEG_PAIRS:  if (value < 1) break; ctx->seg_max_pairs = ctx->seg_resident_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, (uint64_t)value); return B2A_OK;
+        case B2A_OPT_SEG_FIRST:  if (value < 1) break; ctx->seg_first_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, (uint64_t)value); return B2A_OK;
+        case B2A_OPT_SEG_BYTES:  if (value < 1) break; ctx->seg_budget_bytes = (uint64_t)value; return B2A_OK;
+        case B2A_OPT_TB:         ctx->tb_opt = (int)value; return B2A_OK;
+    }
+    return fail(ctx, B2A_ERR_ARG, "b2a_set_option: unknown option or bad value");
 }
 
 int b2a_batch_stats(const b2a_ctx* ctx, uint64_t* kernel_launches, uint64_t* cells, uint64_t* fill_bytes,
@@ -603,7 +904,7 @@ int64_t b2a_fetch_ops(b2a_ctx* ctx, uint64_t pair, char* ops, uint64_t ops_cap)
     if (r.n_ops > ops_cap) return fail(ctx, B2A_ERR_ARG, "b2a_fetch_ops: buffer too small");
     const uint64_t nw = ((uint64_t)r.n_ops + 15) / 16;
     std::vector<uint32_t> w(nw);
-    if (nw) CU(cudaMemcpy(w.data(), ctx->d_ops.p + ctx->h_ops_off[pair], nw * 4, cudaMemcpyDeviceToHost));
+    if (nw) CU(cudaMemcpy(w.data(), ctx->d_ops.p + ctx->h_ops_off.p[pair], nw * 4, cudaMemcpyDeviceToHost));
     ctx->d2h += sizeof(r) + nw * 4;
     static const char L[4] = {'M', 'D', 'I', '?'};
     for (uint32_t t = 0; t < r.n_ops; ++t) ops[t] = L[(w[t >> 4] >> (2 * (t & 15))) & 3u];
@@ -614,13 +915,13 @@ int64_t b2a_copy_ops(b2a_ctx* ctx, uint32_t* ops_words, uint64_t cap_words, uint
 {
     if (!ctx) return B2A_ERR_ARG;
     if (!ctx->ran || !(ctx->prm.flags & B2A_WANT_OPS)) return fail(ctx, B2A_ERR_STATE, "b2a_copy_ops: run a batch with B2A_WANT_OPS first");
-    if (ops_off) std::memcpy(ops_off, ctx->h_ops_off.data(), (ctx->n_pairs + 1) * 8);
+    if (ops_off) std::memcpy(ops_off, ctx->h_ops_off.p, (ctx->n_pairs + 1) * 8);
     if (!ops_words) return (int64_t)ctx->total_ops_words;
     if (cap_words < ctx->total_ops_words) return fail(ctx, B2A_ERR_ARG, "b2a_copy_ops: buffer too small");
     CU(cudaSetDevice(ctx->device));
     if (ctx->total_ops_words) {
-        CU(cudaMemcpyAsync(ops_words, ctx->d_ops.p, ctx->total_ops_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpyAsync(ops_words, ctx->d_ops.p, ctx->total_ops_words * 4, cudaMemcpyDeviceToHost, ctx->s_down));
+        CU(cudaStreamSynchronize(ctx->s_down));
         ctx->d2h += ctx->total_ops_words * 4;
     }
     return (int64_t)ctx->total_ops_words;
@@ -629,12 +930,15 @@ int64_t b2a_copy_ops(b2a_ctx* ctx, uint32_t* ops_words, uint64_t cap_words, uint
 int64_t b2a_debug_copy_record(b2a_ctx* ctx, void* chunks, uint64_t chunk_cap, void* rowbest, uint64_t rowbest_cap)
 {
     if (!ctx) return B2A_ERR_ARG;
-    if (!ctx->ran || ctx->classes.empty()) return fail(ctx, B2A_ERR_STATE, "b2a_debug_copy_record: no short16 record");
+    if (!ctx->ran || ctx->segs.empty() || ctx->segs[0].classes.empty() || ctx->segs[0].flagged)
+        return fail(ctx, B2A_ERR_STATE, "b2a_debug_copy_record: no short16 record");
     CU(cudaSetDevice(ctx->device));
-    const uint64_t bytes = ctx->fill_bytes;
-    if (chunks) CU(cudaMemcpy(chunks, ctx->d_codes.p, std::min<uint64_t>(bytes, chunk_cap), cudaMemcpyDeviceToHost));
+    const Segment& sg = ctx->segs[0];                       // the first segment's record still sits in its lane
+    const Lane& ln = ctx->lanes[sg.lane];
+    const uint64_t bytes = sg.chunks * sizeof(Chunk);
+    if (chunks) CU(cudaMemcpy(chunks, ln.codes.p, std::min<uint64_t>(bytes, chunk_cap), cudaMemcpyDeviceToHost));
     if (rowbest && ctx->prm.mode == B2A_MODE_LOCAL)
-        CU(cudaMemcpy(rowbest, ctx->d_rowbest.p, std::min<uint64_t>(ctx->d_rowbest.cap * 4, rowbest_cap), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(rowbest, ln.rowbest.p, std::min<uint64_t>(sg.rowbest_words * 4, rowbest_cap), cudaMemcpyDeviceToHost));
     return (int64_t)bytes;
 }
 
@@ -643,7 +947,7 @@ int b2a_microbench_int16x2(b2a_ctx* ctx, int kind, double* gops, float* sm_mhz)
     if (!ctx || !gops) return B2A_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     double g = 0; float mhz = 0;
-    cudaError_t e = run_microbench(kind, ctx->sm_count, ctx->stream, &g, &mhz);
+    cudaError_t e = run_microbench(kind, ctx->sm_count, ctx->s_fill, &g, &mhz);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "microbench");
     *gops = g;
     if (sm_mhz) *sm_mhz = mhz;

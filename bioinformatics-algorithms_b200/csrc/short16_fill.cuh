@@ -20,6 +20,11 @@
 
 namespace b2a {
 
+// Pattern alphabet of a sub-batch, produced on the device (alphabet kernels in b2a_api.cu) so that the
+// host never has to wait for it: the PRMT score tables hold 4 symbols; with more, the s16x2 kernels
+// return at once and raise `too_many` (the host then re-runs the sub-batch through wide32).
+struct AlphaInfo { uint32_t mask[8]; uint8_t sym[4]; int32_t nsym; int32_t too_many; };
+
 struct FillArgs {
     const uint8_t*  pat;        // concatenated pattern bytes
     const uint8_t*  txt;        // concatenated text bytes
@@ -33,8 +38,7 @@ struct FillArgs {
     uint32_t        tbl_cap;    // score-table entries (columns) per warp in dynamic shared memory
     int32_t         match, mismatch, gap, bias;
     uint32_t        radix;      // 2^K, passed at run time so the word update stays an IMAD (FMA pipe)
-    uint8_t         sym[4];     // the (<= 4) distinct pattern symbols of the batch
-    int32_t         nsym;
+    const AlphaInfo* alpha;     // device-resident: the (<= 4) distinct pattern symbols of this sub-batch
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -54,11 +58,16 @@ short16_fill_kernel(const FillArgs A)
     extern __shared__ uint2 s_tbl_all[];                 // [FILL_WARPS][tbl_cap]: per column (tableA, tableB)
     __shared__ uint32_t s_tbl4[256];                     // byte -> 4 int8 scores against sym[0..3]
 
+    if (A.alpha->too_many) return;                       // uniform: the whole grid leaves
+    const int nsym = A.alpha->nsym;
+    uint8_t sym[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sym[c] = A.alpha->sym[c];
     for (int b = threadIdx.x; b < 256; b += blockDim.x) {
         uint32_t w = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int sc = (c < A.nsym && A.sym[c] == (uint8_t)b) ? A.match : A.mismatch;
+            const int sc = (c < nsym && sym[c] == (uint8_t)b) ? A.match : A.mismatch;
             w |= ((uint32_t)sc & 0xFFu) << (8 * c);
         }
         s_tbl4[b] = w;
@@ -89,7 +98,7 @@ short16_fill_kernel(const FillArgs A)
         if (i0 < m) {
             const uint8_t xa = pa[i0], xb = pb[i0];
 #pragma unroll
-            for (int c = 1; c < 4; ++c) { if (xa == A.sym[c]) ca = c; if (xb == A.sym[c]) cb = c; }
+            for (int c = 1; c < 4; ++c) { if (xa == sym[c]) ca = c; if (xb == sym[c]) cb = c; }
         }
         sel[r] = ca | ((8u | ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
         H[r] = LOCAL ? 0u : pack2(A.bias + (int)(i0 + 1) * A.gap);      // column-0 border, hw2.cpp:125-130

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "b2a_format.h"
+#include "short16_fill.cuh"
 
 namespace b2a {
 
@@ -27,6 +28,7 @@ struct TbArgs {
     int32_t         R;
     int32_t         match, mismatch, gap, bias;
     int32_t         opt;
+    const AlphaInfo* alpha;
 };
 
 struct DevLoader {
@@ -40,14 +42,16 @@ struct DevLoader {
     }
 };
 
+constexpr int TB_THREADS = 128;
+
 template <int K, bool LOCAL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(TB_THREADS)
 short16_traceback_kernel(const TbArgs A)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t pp = t >> 1;
     const int half = (int)(t & 1u);
-    if (pp >= A.n_pp) return;
+    if (pp >= A.n_pp || A.alpha->too_many) return;
     const PPDesc d = A.pps[pp];
     if (half && d.b == d.a) return;                       // singleton: the high half is a duplicate
     const uint32_t pair = half ? d.b : d.a;

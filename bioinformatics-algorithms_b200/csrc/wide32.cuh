@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "b2a_format.h"
+#include "short16_fill.cuh"
 
 namespace b2a {
 
@@ -42,8 +43,7 @@ struct WideArgs {
     int32_t*        final_score;    // per wide pair: H(m, n) (global mode)
     int32_t         match, mismatch, gap;
     uint32_t        radix;
-    uint8_t         sym[4];
-    int32_t         nsym;
+    const AlphaInfo* alpha;         // used by the ALPHA4 variant only
 };
 
 constexpr int WIDE_WARPS = 4;
@@ -72,12 +72,16 @@ wide32_fill_kernel(const WideArgs A)
     constexpr int R = WIDE_R, F = FM::F, CS = FM::CS, CPB = 32 / CS;   // chunks per 32-step block
     __shared__ uint2 s_ring[WIDE_WARPS][64];       // per 1-based column j (slot j & 63): {text entry, H(top row, j)}
     __shared__ uint32_t s_tbl4[256];
+    uint8_t sym[4] = {0, 0, 0, 0};
     if (ALPHA4) {
+        const int nsym = A.alpha->nsym;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sym[c] = A.alpha->sym[c];
         for (int b = threadIdx.x; b < 256; b += blockDim.x) {
             uint32_t w = 0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const int sc = (c < A.nsym && A.sym[c] == (uint8_t)b) ? A.match : A.mismatch;
+                const int sc = (c < nsym && sym[c] == (uint8_t)b) ? A.match : A.mismatch;
                 w |= ((uint32_t)sc & 0xFFu) << (8 * c);
             }
             s_tbl4[b] = w;
@@ -117,7 +121,7 @@ wide32_fill_kernel(const WideArgs A)
                 uint32_t c = 0;
                 if (i0 < m) { const uint8_t x = pp[i0];
 #pragma unroll
-                    for (int k = 1; k < 4; ++k) if (x == A.sym[k]) c = k; }
+                    for (int k = 1; k < 4; ++k) if (x == sym[k]) c = k; }
                 pc[r] = c | ((8u | c) << 4) | ((8u | c) << 8) | ((8u | c) << 12);
             } else pc[r] = i0 < m ? (uint32_t)pp[i0] : 0xFFFFFFFFu;         // junk rows never match
             H[r] = LOCAL ? 0 : (int32_t)(i0 + 1) * gap;                      // hw2.cpp:125-130

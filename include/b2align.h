@@ -110,9 +110,23 @@ int b2a_batch_upload(b2a_ctx* ctx, const b2a_params* prm,
                      const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs);
 int b2a_batch_run(b2a_ctx* ctx, float* fill_ms, float* traceback_ms);   /* CUDA-event times of this run */
 int b2a_batch_download(b2a_ctx* ctx, b2a_result* results);
+/* times of the last b2a_batch_run: sums of the per-segment fill / traceback kernel times and the
+ * device time from the first kernel's start to the last kernel's end (with two compute lanes the
+ * kernels of neighbouring segments overlap, so total <= fill + traceback). */
+int b2a_batch_times(const b2a_ctx* ctx, float* fill_ms, float* traceback_ms, float* total_ms);
 /* counters of the last run: kernels launched, algorithmic cells, bytes written by the fill kernel */
 int b2a_batch_stats(const b2a_ctx* ctx, uint64_t* kernel_launches, uint64_t* cells, uint64_t* fill_bytes,
                     uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
+/* ---- tuning knobs (defaults are what bench.py measures) -------------------------------------- */
+/* A batch is cut into segments of consecutive pairs; the copy of segment k+1 overlaps the kernels
+ * of segment k and the DP record of a lane is reused by every second segment. */
+#define B2A_OPT_LANES      1   /* compute lanes (streams + records) the segments alternate over: 1 or 2 */
+#define B2A_OPT_SEG_PAIRS  2   /* max pairs per segment                                                  */
+#define B2A_OPT_SEG_FIRST  5   /* pairs of the first segment of b2a_align_batch (doubling up to the max) */
+#define B2A_OPT_SEG_BYTES  3   /* DP-record bytes per segment                                            */
+#define B2A_OPT_TB         4   /* traceback walker tuning bits (experiments)                             */
+int b2a_set_option(b2a_ctx* ctx, int option, int64_t value);
 
 /* ---- result formatting: prepareCigarString hw2.cpp:59-78, prepareMDZString hw2.cpp:80-116 --- */
 /* ops = ASCII list in traceback order (as returned by b2a_fetch_ops). Return the string
