@@ -26,7 +26,7 @@ RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<u4"), ("end_j", "<u4"), (
                          ("start_j", "<u4"), ("overlap", "<i4"), ("n_ops", "<u4"), ("path", "<u4")])
 
 EXPORTS = ["b2a_device_count", "b2a_create", "b2a_destroy", "b2a_last_error", "b2a_host_alloc", "b2a_host_free",
-           "b2a_align_batch", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
+           "b2a_align_batch", "b2a_affine_score_batch", "b2a_affine_star_scores", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
            "b2a_batch_download", "b2a_batch_times", "b2a_set_option", "b2a_batch_stats", "b2a_render_cigar", "b2a_render_mdz", "b2a_select_best",
            "b2a_microbench_int16x2", "b2a_debug_copy_record"]
 
@@ -77,10 +77,9 @@ def load_library():
         lib.b2a_select_best.restype = C.c_int64
         lib.b2a_select_best.argtypes = [C.c_int32, P, C.c_uint64]
         lib.b2a_microbench_int16x2.argtypes = [P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
-        if hasattr(lib, "b2a_score_batch"):
-            lib.b2a_score_batch.argtypes = [P, C.POINTER(Params), P, P, P, P, C.c_uint64, P]
-        if hasattr(lib, "b2a_affine_score_batch"):
-            lib.b2a_affine_score_batch.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, P, P, P, C.c_uint64, P]
+        lib.b2a_affine_score_batch.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, P, P, P, C.c_uint64, P]
+        lib.b2a_affine_star_scores.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, P, C.c_uint32,
+                                               C.c_uint32, C.c_uint32, P, P, P]
         _lib = lib
     return _lib
 
@@ -245,6 +244,33 @@ class Engine:
             results = np.empty(n_pairs, dtype=RESULT_DTYPE)
         self._check(self.lib.b2a_batch_download(self.ctx, results.ctypes.data), "b2a_batch_download")
         return results
+
+    # -- hw3's distance stage (hw3.cpp:23-98, :231-251): score-only affine global alignment --
+    def affine_scores(self, patterns, texts, match, mismatch, gap_open, gap_extend):
+        """lists of bytes -> int32 scores, pair k = affine_alignment(patterns[k], texts[k], ..., &score)"""
+        assert len(patterns) == len(texts)
+        pat, po = pack(patterns)
+        txt, to = pack(texts)
+        out = np.zeros(len(patterns), dtype=np.int32)
+        self._check(self.lib.b2a_affine_score_batch(self.ctx, match, mismatch, gap_open, gap_extend, pat.ctypes.data,
+                                                    po.ctypes.data, txt.ctypes.data, to.ctypes.data, len(patterns),
+                                                    out.ctypes.data), "b2a_affine_score_batch")
+        return out
+
+    def affine_star_scores(self, seqs, match, mismatch, gap_open, gap_extend, pair_first=0, pair_count=None):
+        """All-vs-all (i < j) scores of one sequence set, the star sums and the centre index (hw3.cpp:231-251)."""
+        data, off = pack(seqs)
+        n = len(seqs)
+        total = n * (n - 1) // 2
+        if pair_count is None:
+            pair_count = total - pair_first
+        ps = np.zeros(max(pair_count, 1), dtype=np.int32)
+        sums = np.zeros(max(n, 1), dtype=np.int32)
+        center = C.c_int64(-1)
+        self._check(self.lib.b2a_affine_star_scores(self.ctx, match, mismatch, gap_open, gap_extend, data.ctypes.data,
+                                                    off.ctypes.data, n, pair_first, pair_count, ps.ctypes.data,
+                                                    sums.ctypes.data, C.byref(center)), "b2a_affine_star_scores")
+        return ps[:pair_count], sums[:n], center.value
 
     def stats(self):
         v = [C.c_uint64() for _ in range(5)]

@@ -1,0 +1,190 @@
+// affine32.cuh -- score-only 3-state affine global alignment (sm_100a): the distance stage of the
+// reference's centre-star MSA, Multiple_Sequence_Alignment/hw3.cpp:23-98 called from hw3.cpp:231-241.
+//
+// The reference recurrences (note: no E<->F transitions, V = "ends in a (mis)match"):
+//     V[i][j] = max(V, F, E)[i-1][j-1] + s(i,j)                         hw3.cpp:57-68
+//     F[i][j] = max(V[i-1][j] + Go + Ge, F[i-1][j] + Ge)                hw3.cpp:70-75
+//     E[i][j] = max(V[i][j-1] + Go + Ge, E[i][j-1] + Ge)                hw3.cpp:77-82
+//     borders V[0][0] = 0, F[i][0] = Go + Ge(i-1), E[0][j] = Go + Ge(j-1), all else NEG = INT_MIN/2   hw3.cpp:40-53
+//     score   = max(V, F, E)[m][n]                                      hw3.cpp:86-98
+// are evaluated in the same int32 arithmetic with the same sentinel, so every cell (also the
+// sentinel-tainted ones) holds exactly the reference's value; only the score is wanted here, so no
+// tie-breaking is involved.
+//
+// Same execution scheme as wide32.cuh: bands of 128 rows (32 lanes x 4 rows), a warp sweeps its band
+// as a skewed wavefront, bands of one pair are chained through boundary rows in L2/HBM guarded by
+// per-band progress counters, bands are claimed from a ticket counter in (band, pair) order inside one
+// launch.  Per cell the lane keeps  Vg = V + Go + Ge,  E  and  M3 = max(V, F, E); F only travels
+// downwards inside the step.  6 integer instructions per cell:
+//     PRMT|SEL (s)   IADD (V = M3diag + s)   VIADDMNMX (F)   VIADDMNMX (E)   IADD (Vg)   VIMNMX3 (M3)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "b2a_format.h"
+#include "wide32.cuh"
+
+namespace b2a {
+
+struct AffineArgs {
+    const uint8_t*  pat;
+    const uint8_t*  txt;
+    const WidePair* pairs;          // bound_off indexes 2 buffers x 3 planes x bound_stride int32
+    const WideTask* tasks;
+    uint32_t        n_tasks;
+    uint32_t*       ticket;
+    int32_t*        bound;
+    uint32_t*       progress;
+    int32_t*        final_score;    // per pair: max(V, F, E)[m][n]
+    int32_t         match, mismatch, gopen, gext;
+    const AlphaInfo* alpha;         // ALPHA4 variant only
+};
+
+constexpr int32_t AFFINE_NEG = INT32_MIN / 2;        // hw3.cpp:16
+
+template <bool ALPHA4>
+__global__ void __launch_bounds__(WIDE_WARPS * 32)
+affine32_score_kernel(const AffineArgs A)
+{
+    constexpr int R = WIDE_R;
+    __shared__ uint4 s_ring[WIDE_WARPS][64];       // per 1-based column j (slot j & 63): {text entry, Vg, F, M3 of the row above the band}
+    __shared__ uint32_t s_tbl4[256];
+    uint8_t sym[4] = {0, 0, 0, 0};
+    if (ALPHA4) {
+        const int nsym = A.alpha->nsym;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sym[c] = A.alpha->sym[c];
+        for (int b = threadIdx.x; b < 256; b += blockDim.x) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int sc = (c < nsym && sym[c] == (uint8_t)b) ? A.match : A.mismatch;
+                w |= ((uint32_t)sc & 0xFFu) << (8 * c);
+            }
+            s_tbl4[b] = w;
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4* ring = s_ring[warp];
+    const int32_t ge = A.gext, go = A.gopen, goe = A.gopen + A.gext, NEG = AFFINE_NEG;
+
+    for (;;) {
+        uint32_t tk = 0;
+        if (lane == 0) tk = atomicAdd(A.ticket, 1u);
+        tk = __shfl_sync(0xFFFFFFFFu, tk, 0);
+        if (tk >= A.n_tasks) break;
+        const WideTask task = A.tasks[tk];
+        const WidePair wp = A.pairs[task.wp];
+        const uint32_t m = wp.m, n = wp.n, band = task.band;
+        const uint8_t* pp = A.pat + wp.pat_off;
+        const uint8_t* tt = A.txt + wp.txt_off;
+        const uint32_t row0 = band * 32u * R + (uint32_t)lane * R;          // 0-based first row of this lane = 1-based row above it
+        uint32_t pc[R];
+        int32_t Vg[R], E[R], M3[R];                                          // state at the lane's current column
+        int32_t Fk;                                                          // F of the lane's last row
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t i0 = row0 + r;                                    // 1-based row i = i0 + 1
+            if (ALPHA4) {
+                uint32_t c = 0;
+                if (i0 < m) { const uint8_t x = pp[i0];
+#pragma unroll
+                    for (int k = 1; k < 4; ++k) if (x == sym[k]) c = k; }
+                pc[r] = c | ((8u | c) << 4) | ((8u | c) << 8) | ((8u | c) << 12);
+            } else pc[r] = i0 < m ? (uint32_t)pp[i0] : 0xFFFFFFFFu;         // junk rows never match
+            Vg[r] = NEG + goe;                                               // V[i][0] = NEG            hw3.cpp:43
+            E[r]  = NEG;                                                     // E[i][0] = NEG            hw3.cpp:46
+            M3[r] = go + ge * (int32_t)i0;                                   // F[i][0] = Go + Ge(i-1)   hw3.cpp:44
+        }
+        Fk = M3[R - 1];
+        const uint64_t plane = wp.bound_stride;
+        const int32_t* bin = A.bound + wp.bound_off + (uint64_t)((band + 1u) & 1u) * 3u * plane;
+        int32_t* bout = A.bound + wp.bound_off + (uint64_t)(band & 1u) * 3u * plane;
+        const uint32_t* prog_in = A.progress + wp.prog_off + band - 1;
+        uint32_t* prog_out = A.progress + wp.prog_off + band;
+        const bool has_next = band + 1 < wp.nbands;
+        const uint32_t nblk = (n + 32u + 31u) / 32u;
+        // max(V, F, E) of the row above the band at column 0: V[0][0] = 0 for the first band, else F[i][0]
+        const int32_t top0 = band == 0 ? 0 : go + ge * (int32_t)(band * 32u * R - 1u);
+        int32_t dgn = row0 == 0 ? 0 : go + ge * (int32_t)(row0 - 1u);       // M3[row above][0]; lane 0 reloads it from the ring at q = 0
+        uint32_t have = band == 0 ? 0xFFFFFFFFu : 0u;
+
+        auto text_entry = [&](uint32_t j) -> uint32_t {
+            if (j == 0 || j > n) return ALPHA4 ? 0u : 0xFFFFFF00u;
+            const uint8_t x = tt[j - 1];
+            return ALPHA4 ? s_tbl4[x] : (uint32_t)x;
+        };
+        uint32_t tnext = text_entry((uint32_t)lane);
+
+        for (uint32_t kb = 0; kb < nblk; ++kb) {
+            const uint32_t q0 = kb * 32u;
+            const uint32_t jcol = q0 + (uint32_t)lane;
+            int32_t bVg, bF, bM;
+            if (band == 0) {                                                 // row 0: V = F = NEG, E[0][j] = Go + Ge(j-1)   hw3.cpp:48-53
+                bVg = NEG + goe; bF = NEG;
+                bM = jcol == 0 ? 0 : go + ge * (int32_t)(jcol - 1u);
+            } else {
+                const uint32_t need = kb + 2u < nblk ? kb + 2u : nblk;
+                while (have < need) { have = ld_acquire_u32(prog_in); if (have < need) __nanosleep(64); }
+                if (jcol >= 1 && jcol <= n) { bVg = __ldcg(bin + jcol); bF = __ldcg(bin + plane + jcol); bM = __ldcg(bin + 2u * plane + jcol); }
+                else { bVg = NEG + goe; bF = NEG; bM = top0; }
+            }
+            __syncwarp();
+            ring[jcol & 63u] = make_uint4(tnext, (uint32_t)bVg, (uint32_t)bF, (uint32_t)bM);
+            __syncwarp();
+            tnext = text_entry(q0 + 32u + (uint32_t)lane);
+            const bool steady = q0 >= 32u && q0 + 31u <= n;
+
+            auto step = [&](uint32_t q, bool active) {
+                int32_t uVg = __shfl_up_sync(0xFFFFFFFFu, Vg[R - 1], 1);
+                int32_t uF  = __shfl_up_sync(0xFFFFFFFFu, Fk, 1);
+                int32_t uM  = __shfl_up_sync(0xFFFFFFFFu, M3[R - 1], 1);
+                const uint4 e = ring[(q - (uint32_t)lane) & 63u];
+                if (lane == 0) { uVg = (int32_t)e.y; uF = (int32_t)e.z; uM = (int32_t)e.w; }
+                const int32_t dg0 = dgn;
+                dgn = uM;
+                if (active) {
+                    int32_t dg = dg0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int32_t s = ALPHA4 ? (int32_t)prmt32(e.x, 0u, pc[r]) : (pc[r] == e.x ? A.match : A.mismatch);
+                        const int32_t v = dg + s;                            // hw3.cpp:59-68
+                        dg = M3[r];
+                        const int32_t f  = __viaddmax_s32(uF, ge, uVg);      // hw3.cpp:70-75
+                        const int32_t ee = __viaddmax_s32(E[r], ge, Vg[r]);  // hw3.cpp:77-82
+                        const int32_t vg = v + goe;
+                        M3[r] = __vimax3_s32(v, f, ee);
+                        Vg[r] = vg; E[r] = ee;
+                        uVg = vg; uF = f;
+                    }
+                    Fk = uF;
+                    if (lane == 31 && has_next) {
+                        const uint32_t j = q - 31u;
+                        __stcg(bout + j, Vg[R - 1]); __stcg(bout + plane + j, Fk); __stcg(bout + 2u * plane + j, M3[R - 1]);
+                    }
+                }
+            };
+            if (steady) {
+#pragma unroll 8
+                for (int f = 0; f < 32; ++f) step(q0 + (uint32_t)f, true);
+            } else {
+#pragma unroll 4
+                for (int f = 0; f < 32; ++f) step(q0 + (uint32_t)f, (uint32_t)(q0 + (uint32_t)f - lane - 1u) < n);
+            }
+            if (has_next && lane == 31) st_release_u32(prog_out, kb + 1u);
+        }
+        if (band + 1 == wp.nbands) {                                         // hw3.cpp:86-98: max(V, F, E)[m][n]
+            const uint32_t ib = (m - 1u) - band * 32u * R;
+            if ((uint32_t)lane == ib / R) {
+                const uint32_t rm = ib % R;
+                int32_t v = M3[0];
+#pragma unroll
+                for (int r = 1; r < R; ++r) if (rm == (uint32_t)r) v = M3[r];
+                A.final_score[task.wp] = v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+} // namespace b2a

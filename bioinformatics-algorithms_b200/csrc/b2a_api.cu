@@ -27,6 +27,7 @@
 #include "short16_fill.cuh"
 #include "traceback.cuh"
 #include "wide32.cuh"
+#include "affine32.cuh"
 #include "microbench.cuh"
 
 using namespace b2a;
@@ -443,6 +444,108 @@ int launch_segment(b2a_ctx* ctx, size_t si, uint64_t* launches)
 // s_fill waits for every traceback queued so far (the wide32 phase and the end-of-run event follow on s_fill)
 int join_tracebacks(b2a_ctx* ctx) {
     for (int l = 0; l < MAX_LANES; ++l) CU(cudaStreamWaitEvent(ctx->s_fill, ctx->lanes[l].tb_done, 0));
+    return B2A_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// affine32: hw3's distance stage (score only).  `specs` index into the device copies of pat / txt.
+// ---------------------------------------------------------------------------------------------
+struct AffSpec { uint64_t pat_off, txt_off; uint32_t m, n; };
+
+int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const uint8_t* pat, uint64_t pat_bytes,
+               const uint8_t* txt, uint64_t txt_bytes, bool same_buffer, const std::vector<AffSpec>& specs, int32_t* scores)
+{
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->s_copy)); CU(cudaStreamSynchronize(ctx->s_down));
+    CU(cudaStreamSynchronize(ctx->s_fill)); CU(cudaStreamSynchronize(ctx->s_tb));
+    ctx->have_batch = false; ctx->ran = false;              // the batch buffers are reused below
+    ctx->cells = ctx->fill_bytes = ctx->launches = ctx->h2d = ctx->d2h = 0;
+    const int64_t smag = std::max<int64_t>({std::llabs((long long)match), std::llabs((long long)mismatch),
+                                            std::llabs((long long)gopen) + std::llabs((long long)gext)});
+    WideState& W = ctx->wide;
+    W.pairs.clear(); W.tasks.clear();
+    W.bound_ints = W.prog_words = 0;
+    uint32_t max_bands = 0;
+    std::vector<uint32_t> slot(specs.size(), 0xFFFFFFFFu);
+    for (size_t k = 0; k < specs.size(); ++k) {
+        const AffSpec& sp = specs[k];
+        // the sentinel arithmetic of hw3.cpp:16 must not wrap: NEG - (m+n)*max|score| has to stay above INT_MIN
+        if (((uint64_t)sp.m + sp.n + 2) * (uint64_t)smag >= (1ull << 30))
+            return fail(ctx, B2A_ERR_RANGE, "b2a_affine: (m+n)*max|score| exceeds 2^30 (hw3's INT_MIN/2 sentinel would wrap)");
+        ctx->cells += (uint64_t)sp.m * sp.n;
+        if (sp.m == 0 || sp.n == 0) continue;                // borders only: answered on the host below
+        WidePair p{};
+        p.pat_off = sp.pat_off; p.txt_off = sp.txt_off; p.m = sp.m; p.n = sp.n; p.pair = (uint32_t)k;
+        p.nbands = (sp.m + 32u * WIDE_R - 1u) / (32u * WIDE_R);
+        p.bound_stride = ((sp.n + 64u) + 31u) & ~31u;
+        p.bound_off = W.bound_ints; W.bound_ints += 6ull * p.bound_stride;     // 2 buffers x {Vg, F, M3}
+        p.prog_off = W.prog_words; W.prog_words += p.nbands;
+        max_bands = std::max(max_bands, p.nbands);
+        slot[k] = (uint32_t)W.pairs.size();
+        W.pairs.push_back(p);
+    }
+    std::vector<uint32_t> order(W.pairs.size());
+    for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return W.pairs[a].nbands > W.pairs[b].nbands; });
+    for (uint32_t b = 0; b < max_bands; ++b)                 // band-major tickets: a band's producer always holds an earlier ticket
+        for (uint32_t i : order) { if (W.pairs[i].nbands <= b) break; W.tasks.push_back(WideTask{i, b}); }
+
+    cudaStream_t st = ctx->s_fill;
+    CU(ctx->d_pat.reserve(pat_bytes + 16));
+    if (!same_buffer) CU(ctx->d_txt.reserve(txt_bytes + 16));
+    CU(ctx->d_alpha.reserve(2)); CU(ctx->h_alpha.reserve(2));
+    CU(W.d_pairs.reserve(W.pairs.size())); CU(W.d_tasks.reserve(W.tasks.size()));
+    CU(W.d_bound.reserve(W.bound_ints)); CU(W.d_final.reserve(W.pairs.size())); CU(W.d_progress.reserve(W.prog_words + 1));
+    if (pat_bytes) CU(cudaMemcpyAsync(ctx->d_pat.p, pat, pat_bytes, cudaMemcpyHostToDevice, st));
+    if (!same_buffer && txt_bytes) CU(cudaMemcpyAsync(ctx->d_txt.p, txt, txt_bytes, cudaMemcpyHostToDevice, st));
+    ctx->h2d += pat_bytes + (same_buffer ? 0 : txt_bytes);
+    CU(cudaMemsetAsync(ctx->d_alpha.p, 0, sizeof(AlphaInfo), st));
+    uint64_t launches = 0;
+    if (pat_bytes) {
+        const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count * 4u, (pat_bytes + 4095) / 4096);
+        alphabet_kernel<<<grid, 256, 0, st>>>(ctx->d_pat.p, pat_bytes, ctx->d_alpha.p);
+        CU(cudaGetLastError()); ++launches;
+    }
+    alphabet_finish_kernel<<<1, 32, 0, st>>>(ctx->d_alpha.p);
+    CU(cudaGetLastError()); ++launches;
+    CU(cudaMemcpyAsync(ctx->h_alpha.p, ctx->d_alpha.p, sizeof(AlphaInfo), cudaMemcpyDeviceToHost, st));
+    if (!W.pairs.empty()) {
+        CU(cudaMemcpyAsync(W.d_pairs.p, W.pairs.data(), W.pairs.size() * sizeof(WidePair), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(W.d_tasks.p, W.tasks.data(), W.tasks.size() * sizeof(WideTask), cudaMemcpyHostToDevice, st));
+        ctx->h2d += W.pairs.size() * sizeof(WidePair) + W.tasks.size() * sizeof(WideTask);
+    }
+    CU(cudaStreamSynchronize(st));
+    const bool alpha4 = !ctx->h_alpha.p[0].too_many && match <= 127 && match >= -128 && mismatch <= 127 && mismatch >= -128;
+    std::vector<int32_t> fin(W.pairs.size());
+    float ms = 0;
+    if (!W.tasks.empty()) {
+        CU(cudaMemsetAsync(W.d_progress.p, 0, (W.prog_words + 1) * 4, st));
+        AffineArgs a{};
+        a.pat = ctx->d_pat.p; a.txt = same_buffer ? ctx->d_pat.p : ctx->d_txt.p; a.pairs = W.d_pairs.p; a.tasks = W.d_tasks.p;
+        a.n_tasks = (uint32_t)W.tasks.size(); a.ticket = W.d_progress.p + W.prog_words;
+        a.bound = W.d_bound.p; a.progress = W.d_progress.p; a.final_score = W.d_final.p;
+        a.match = match; a.mismatch = mismatch; a.gopen = gopen; a.gext = gext; a.alpha = ctx->d_alpha.p;
+        const unsigned need = (unsigned)((W.tasks.size() + WIDE_WARPS - 1) / WIDE_WARPS);
+        const unsigned grid = std::min<unsigned>(need, (unsigned)ctx->sm_count * 8u);
+        CU(cudaEventRecord(ctx->ev_begin, st));
+        if (alpha4) affine32_score_kernel<true><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
+        else affine32_score_kernel<false><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
+        CU(cudaGetLastError()); ++launches;
+        CU(cudaEventRecord(ctx->ev_end, st));
+        CU(cudaMemcpyAsync(fin.data(), W.d_final.p, fin.size() * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+        ctx->d2h += fin.size() * 4;
+    }
+    for (size_t k = 0; k < specs.size(); ++k) {
+        const AffSpec& sp = specs[k];
+        if (slot[k] != 0xFFFFFFFFu) scores[k] = fin[slot[k]];
+        else if (sp.m == 0 && sp.n == 0) scores[k] = 0;                                  // V[0][0]               hw3.cpp:40
+        else if (sp.m == 0) scores[k] = gopen + gext * (int32_t)(sp.n - 1);              // E[0][n]               hw3.cpp:50
+        else scores[k] = gopen + gext * (int32_t)(sp.m - 1);                             // F[m][0]               hw3.cpp:44
+    }
+    ctx->last_fill_ms = ms; ctx->last_tb_ms = 0; ctx->last_total_ms = ms;
+    ctx->launches = launches;
     return B2A_OK;
 }
 
@@ -866,6 +969,66 @@ int b2a_align_batch(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, con
                     const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs, b2a_result* results)
 {
     return batch_prepare(ctx, prm, pat, pat_off, txt, txt_off, n_pairs, true, results);
+}
+
+int b2a_affine_score_batch(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                           const uint8_t* pat, const uint64_t* pat_off, const uint8_t* txt, const uint64_t* txt_off,
+                           uint64_t n_pairs, int32_t* scores)
+{
+    if (!ctx) return B2A_ERR_ARG;
+    if (!pat_off || !txt_off || (!scores && n_pairs)) return fail(ctx, B2A_ERR_ARG, "b2a_affine_score_batch: null argument");
+    if (n_pairs > 0x7FFFFFF0ull) return fail(ctx, B2A_ERR_ARG, "b2a_affine_score_batch: too many pairs");
+    const uint64_t pat_bytes = n_pairs ? pat_off[n_pairs] : 0, txt_bytes = n_pairs ? txt_off[n_pairs] : 0;
+    if ((pat_bytes && !pat) || (txt_bytes && !txt)) return fail(ctx, B2A_ERR_ARG, "b2a_affine_score_batch: null sequence buffer");
+    std::vector<AffSpec> specs(n_pairs);
+    for (uint64_t k = 0; k < n_pairs; ++k) {
+        if (pat_off[k + 1] < pat_off[k] || txt_off[k + 1] < txt_off[k])
+            return fail(ctx, B2A_ERR_ARG, "b2a_affine_score_batch: offsets must be non-decreasing");
+        const uint64_t m = pat_off[k + 1] - pat_off[k], n = txt_off[k + 1] - txt_off[k];
+        if (m + n >= 0x7FFFFFF0ull) return fail(ctx, B2A_ERR_RANGE, "b2a_affine_score_batch: sequence too long");
+        specs[k] = AffSpec{pat_off[k], txt_off[k], (uint32_t)m, (uint32_t)n};
+    }
+    return affine_run(ctx, match, mismatch, gap_open, gap_extend, pat, pat_bytes, txt, txt_bytes, false, specs, scores);
+}
+
+int b2a_affine_star_scores(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                           const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_seqs,
+                           uint32_t pair_first, uint32_t pair_count, int32_t* pair_scores, int32_t* sum_scores, int64_t* center)
+{
+    if (!ctx) return B2A_ERR_ARG;
+    if (!seq_off || (n_seqs && !seqs && seq_off[n_seqs])) return fail(ctx, B2A_ERR_ARG, "b2a_affine_star_scores: null argument");
+    const uint64_t total = (uint64_t)n_seqs * (n_seqs ? n_seqs - 1 : 0) / 2;
+    if (pair_first > total) return fail(ctx, B2A_ERR_ARG, "b2a_affine_star_scores: pair range out of bounds");
+    const uint64_t count = std::min<uint64_t>(pair_count, total - pair_first);
+    std::vector<AffSpec> specs;
+    std::vector<std::pair<uint32_t, uint32_t>> ij;
+    uint64_t idx = 0;
+    for (uint32_t i = 0; i < n_seqs; ++i)                                    // hw3.cpp:233-234: i < j, row-major
+        for (uint32_t j = i + 1; j < n_seqs; ++j, ++idx) {
+            if (idx < pair_first || idx >= pair_first + count) continue;
+            if (seq_off[i + 1] < seq_off[i] || seq_off[j + 1] < seq_off[j]) return fail(ctx, B2A_ERR_ARG, "b2a_affine_star_scores: offsets must be non-decreasing");
+            const uint64_t m = seq_off[i + 1] - seq_off[i], n = seq_off[j + 1] - seq_off[j];
+            if (m + n >= 0x7FFFFFF0ull) return fail(ctx, B2A_ERR_RANGE, "b2a_affine_star_scores: sequence too long");
+            specs.push_back(AffSpec{seq_off[i], seq_off[j], (uint32_t)m, (uint32_t)n});
+            ij.emplace_back(i, j);
+        }
+    std::vector<int32_t> sc(specs.size());
+    int rc = affine_run(ctx, match, mismatch, gap_open, gap_extend, seqs, n_seqs ? seq_off[n_seqs] : 0, nullptr, 0, true, specs, sc.data());
+    if (rc != B2A_OK) return rc;
+    if (pair_scores) std::copy(sc.begin(), sc.end(), pair_scores);
+    if (sum_scores) {                                                        // hw3.cpp:238-239 (partial sums of this pair range)
+        for (uint32_t i = 0; i < n_seqs; ++i) sum_scores[i] = 0;
+        for (size_t k = 0; k < ij.size(); ++k) { sum_scores[ij[k].first] += sc[k]; sum_scores[ij[k].second] += sc[k]; }
+    }
+    if (center) {                                                            // hw3.cpp:243-251: first strict maximum
+        *center = -1;
+        if (sum_scores && n_seqs) {
+            int64_t c = 0;
+            for (uint32_t i = 1; i < n_seqs; ++i) if (sum_scores[i] > sum_scores[c]) c = i;
+            *center = c;
+        }
+    }
+    return B2A_OK;
 }
 
 int b2a_set_option(b2a_ctx* ctx, int option, int64_t value)

@@ -118,6 +118,23 @@ int b2a_batch_times(const b2a_ctx* ctx, float* fill_ms, float* traceback_ms, flo
 int b2a_batch_stats(const b2a_ctx* ctx, uint64_t* kernel_launches, uint64_t* cells, uint64_t* fill_bytes,
                     uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
+/* ---- hw3's distance stage: score-only 3-state affine global alignment ------------------------ */
+/* Replaces affine_alignment(..., &alignmentScore) (Multiple_Sequence_Alignment/hw3.cpp:23-98) as it is
+ * called from the all-vs-all loop hw3.cpp:231-241: V/F/E recurrences with hw3's "-s M:Mm:Go:Ge" scores,
+ * the INT_MIN/2 sentinel (hw3.cpp:16), result max(V,F,E)[m][n].  Pair k aligns pat[k] (string1, rows)
+ * against txt[k] (string2, columns); scores receives n_pairs ints. */
+int b2a_affine_score_batch(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                           const uint8_t* pat, const uint64_t* pat_off, const uint8_t* txt, const uint64_t* txt_off,
+                           uint64_t n_pairs, int32_t* scores);
+/* The loop hw3.cpp:231-251 itself over one sequence set: pairs (i, j), i < j, in the reference's
+ * row-major order; this call serves pairs [pair_first, pair_first + pair_count) of that order (so the
+ * n(n-1)/2 pairs can be sharded over GPUs), writes their scores, the star sums sum_scores[n_seqs]
+ * restricted to the range (add the ranges' sums, hw3.cpp:238-239) and, when the range is everything,
+ * the centre index hw3.cpp:243-251 (first strict maximum).  Any output pointer may be NULL. */
+int b2a_affine_star_scores(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                           const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_seqs,
+                           uint32_t pair_first, uint32_t pair_count, int32_t* pair_scores, int32_t* sum_scores, int64_t* center);
+
 /* ---- tuning knobs (defaults are what bench.py measures) -------------------------------------- */
 /* A batch is cut into segments of consecutive pairs; the copy of segment k+1 overlaps the kernels
  * of segment k and the DP record of a lane is reused by every second segment. */

@@ -283,3 +283,65 @@ def test_empty_and_degenerate_inputs(eng):
     # zero-length sequences cannot come out of readFasta (hw2.cpp:44-54 drops empty records) but the ABI accepts them
     for mode in (pkg.GLOBAL, pkg.LOCAL):
         check_batch(eng, mode, [b"", b"ACGT", b""], [b"ACGT", b"", b""], (1, -1, -1))
+
+
+# ---------------- affine32: hw3's distance stage (hw3.cpp:23-98, :231-251), score only ----------------
+def test_affine_golden_vectors_from_hw3(eng):
+    """tests/golden/hw3_kat.json (made by the unmodified hw3 binary): the score implied by hw3's own alignment."""
+    from test_oracle import HW3_KAT, parse_phy, alignment_score
+    by = {}
+    for c in HW3_KAT["pairs"]:
+        by.setdefault(tuple(c["s"]), []).append(c)
+    for s, cases in by.items():
+        got = eng.affine_scores([c["seqs"][0].encode() for c in cases], [c["seqs"][1].encode() for c in cases], *s)
+        for c, g in zip(cases, got):
+            (_, a1), (_, a2) = parse_phy(c["phy"])
+            assert int(g) == alignment_score(a1, a2, *s), c
+    for c in HW3_KAT["stars"]:
+        _, sums, centre = eng.affine_star_scores([x.encode() for x in c["seqs"]], *c["s"])
+        assert parse_phy(c["phy"])[0][0] == "s%d" % centre, c
+
+
+def test_affine_random_pairs_vs_oracle(eng):
+    rng = random.Random(41)
+    prot = b"ACDEFGHIKLMNPQRSTVWY"
+    for alpha in (b"ACGT", b"AC", prot):
+        ps, ts = [], []
+        for m, n in ((1, 1), (1, 40), (40, 1), (127, 128), (128, 128), (129, 130), (300, 270), (700, 900), (1300, 1100),
+                     (5, 3000), (2500, 60), (0, 5), (5, 0), (0, 0)):
+            t = rnd(rng, n, alpha)
+            ps.append((mutate(rng, t, alpha=alpha) + rnd(rng, m, alpha))[:m]); ts.append(t)
+        for s in ((5, -4, -16, -4), (1, -1, -2, -1), (2, -3, -5, -2), (3, -1, 0, -2), (4, -6, -10, 0), (200, -300, -1000, -50), (0, 0, 0, 0)):
+            got = eng.affine_scores(ps, ts, *s)
+            for k in range(len(ps)):
+                assert int(got[k]) == ob.affine_score(ps[k], ts[k], *s), (alpha, len(ps[k]), len(ts[k]), s)
+
+
+def test_affine_star_scores_and_sharding(eng):
+    """The all-vs-all loop hw3.cpp:231-251: pair order, star sums, centre; pair ranges add up (multi-GPU sharding)."""
+    rng = random.Random(42)
+    base = rnd(rng, 900)
+    seqs = [mutate(rng, base, psub=0.1, pindel=0.02) for _ in range(7)]
+    s = (5, -4, -16, -4)
+    ps, sums, centre = eng.affine_star_scores(seqs, *s)
+    want, wsum = [], [0] * len(seqs)
+    for i in range(len(seqs)):
+        for j in range(i + 1, len(seqs)):
+            v = ob.affine_score(seqs[i], seqs[j], *s)
+            want.append(v); wsum[i] += v; wsum[j] += v
+    assert list(map(int, ps)) == want and list(map(int, sums)) == wsum
+    assert centre == max(range(len(seqs)), key=lambda i: (wsum[i], -i))
+    total = len(want)
+    parts = [eng.affine_star_scores(seqs, *s, pair_first=a, pair_count=b) for a, b in ((0, 8), (8, 5), (13, total - 13))]
+    assert [int(x) for p in parts for x in p[0]] == want
+    assert list(map(int, sum(p[1].astype(np.int64) for p in parts))) == wsum
+
+
+def test_affine_tandem_repeats_10k(eng):
+    """shape of Multiple_Sequence_Alignment/input1610000.fasta: 10 kb tandem repeats, 79 chained bands"""
+    a, b = (b"ACGTA" * 2100)[:10010], (b"ACGTACG" * 1500)[:10000]
+    c = (b"ACGTA" * 2000)[:10000]
+    s = (5, -4, -16, -4)
+    got = eng.affine_scores([a, b, c], [c, a, b], *s)
+    for g, (x, y) in zip(got, ((a, c), (b, a), (c, b))):
+        assert int(g) == ob.affine_score(x, y, *s)

@@ -110,3 +110,58 @@ def test_affine_score_restatement_matches_hw3_centre_choice(tmp_path):
             if best is None or v > best:
                 best, idx = v, i
         assert centre_name == "s%d" % idx, (seqs, sc, sums, lines[:3])
+
+
+# ---------------- hw3 affine score: pinned by alignment-derived scores and centre choices ----------------
+HW3_KAT = json.load(open(os.path.join(HERE, "golden", "hw3_kat.json")))
+
+
+def parse_phy(text):
+    """PHYLIP as hw3 writes it (hw3.cpp:339-357): 10-char name, then the row in space-separated blocks of 10."""
+    lines = text.split("\n")
+    n = int(lines[0].split()[0])
+    return [(ln[:10].strip(), ln[10:].replace(" ", "")) for ln in lines[1:1 + n]]
+
+
+def alignment_score(a1, a2, match, mismatch, gopen, gext):
+    """Score of one alignment under hw3's model (hw3.cpp:40-84): a (mis)match column scores s; a gap run of
+    length L costs Go + Ge*L (opened from V, hw3.cpp:70,77), except a run that starts the alignment, which
+    comes from the borders F[i][0] / E[0][j] = Go + Ge*(L-1) (hw3.cpp:44,50)."""
+    total, k, n = 0, 0, len(a1)
+    while k < n:
+        if a1[k] != "-" and a2[k] != "-":
+            total += match if a1[k] == a2[k] else mismatch
+            k += 1
+            continue
+        row = 0 if a1[k] == "-" else 1
+        e = k
+        while e < n and (a1[e] == "-" if row == 0 else a2[e] == "-") and not (a1[e] == "-" and a2[e] == "-"):
+            e += 1
+        L = e - k
+        total += gopen + gext * (L - 1 if k == 0 else L)
+        k = e
+    return total
+
+
+def test_affine_restatement_equals_score_of_hw3_alignments_golden():
+    for c in HW3_KAT["pairs"]:
+        rows = parse_phy(c["phy"])
+        s1, s2 = c["seqs"]
+        (_, a1), (_, a2) = rows
+        assert a1.replace("-", "") == s1 and a2.replace("-", "") == s2
+        want = alignment_score(a1, a2, *c["s"])
+        assert ob.affine_score(s1.encode(), s2.encode(), *c["s"]) == want, c
+
+
+def test_affine_restatement_reproduces_hw3_centre_golden():
+    for c in HW3_KAT["stars"]:
+        seqs = [s.encode() for s in c["seqs"]]
+        k = len(seqs)
+        sums = [0] * k
+        for i in range(k):
+            for j in range(i + 1, k):
+                v = ob.affine_score(seqs[i], seqs[j], *c["s"])
+                sums[i] += v
+                sums[j] += v
+        idx = max(range(k), key=lambda i: (sums[i], -i))          # first strict max, hw3.cpp:244-251
+        assert parse_phy(c["phy"])[0][0] == "s%d" % idx, c
