@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(HERE, "libb2align.so")
 HW2_BIN = os.path.join(HERE, "bin", "hw2")
 
 GLOBAL, LOCAL = 0, 1
+SCORE_ONLY = 2
 OPT_LANES, OPT_SEG_PAIRS, OPT_SEG_BYTES, OPT_TB, OPT_SEG_FIRST = 1, 2, 3, 4, 5
 WANT_OPS = 1
 
@@ -186,11 +187,12 @@ class Engine:
         return rc
 
     # -- the batch call that replaces hw2.cpp:328-338 --
-    def align_packed(self, mode, pat, pat_off, txt, txt_off, match, mismatch, gap, want_ops=False, results=None):
+    def align_packed(self, mode, pat, pat_off, txt, txt_off, match, mismatch, gap, want_ops=False, results=None,
+                     score_only=False):
         n = len(pat_off) - 1
         if results is None:
             results = np.empty(n, dtype=RESULT_DTYPE)
-        prm = Params(mode, match, mismatch, gap, WANT_OPS if want_ops else 0)
+        prm = Params(mode, match, mismatch, gap, (WANT_OPS if want_ops else 0) | (SCORE_ONLY if score_only else 0))
         self._check(self.lib.b2a_align_batch(self.ctx, C.byref(prm), pat.ctypes.data, pat_off.ctypes.data,
                                              txt.ctypes.data, txt_off.ctypes.data, n, results.ctypes.data), "b2a_align_batch")
         return results
@@ -220,8 +222,8 @@ class Engine:
         return buf.raw[:n]
 
     # -- device-resident variant, for kernel-only timing --
-    def upload(self, mode, pat, pat_off, txt, txt_off, match, mismatch, gap, want_ops=False):
-        prm = Params(mode, match, mismatch, gap, WANT_OPS if want_ops else 0)
+    def upload(self, mode, pat, pat_off, txt, txt_off, match, mismatch, gap, want_ops=False, score_only=False):
+        prm = Params(mode, match, mismatch, gap, (WANT_OPS if want_ops else 0) | (SCORE_ONLY if score_only else 0))
         self._check(self.lib.b2a_batch_upload(self.ctx, C.byref(prm), pat.ctypes.data, pat_off.ctypes.data,
                                               txt.ctypes.data, txt_off.ctypes.data, len(pat_off) - 1), "b2a_batch_upload")
 
