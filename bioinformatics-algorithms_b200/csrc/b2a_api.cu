@@ -273,7 +273,7 @@ cudaError_t launch_wide_fill(int K, bool local, bool store, bool alpha4, const W
     return cudaErrorInvalidValue;
 }
 cudaError_t launch_wide_tb(int K, bool local, const WideTbArgs& a, cudaStream_t st) {
-    const unsigned threads = 64, grid = (a.n_wide + threads - 1) / threads;
+    const unsigned threads = WIDE_TB_WARPS * 32, grid = (a.n_wide + WIDE_TB_WARPS - 1) / WIDE_TB_WARPS;
     switch (K * 2 + (local ? 1 : 0)) {
         case 4:  wide32_traceback_kernel<2, false><<<grid, threads, 0, st>>>(a); break;
         case 5:  wide32_traceback_kernel<2, true><<<grid, threads, 0, st>>>(a); break;

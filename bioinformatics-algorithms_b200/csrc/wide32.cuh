@@ -15,6 +15,7 @@
 #include <stdint.h>
 #include "b2a_format.h"
 #include "short16_fill.cuh"
+#include "walk_warp.cuh"
 
 namespace b2a {
 
@@ -271,12 +272,16 @@ struct WideLoader {
     }
 };
 
+constexpr int WIDE_TB_WARPS = 2;
+
+// One WARP per pair (walk_warp.cuh); score-only batches just gather the scores the fill kernel left.
 template <int K, bool LOCAL>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(WIDE_TB_WARPS * 32)
 wide32_traceback_kernel(const WideTbArgs A)
 {
     using FM = Wide32<K>;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = (int)(threadIdx.x & 31u);
+    const uint32_t t = blockIdx.x * WIDE_TB_WARPS + (threadIdx.x >> 5);
     if (t >= A.n_wide) return;
     const WidePair wp = A.pairs[t];
     PairResult res;
@@ -284,26 +289,42 @@ wide32_traceback_kernel(const WideTbArgs A)
         res = PairResult{0, 0, 0, 0, 0, 0, 0, 2};
         if (LOCAL) {
             int M = 0;
-            for (uint32_t k = 0; k < wp.nbands * 32u * WIDE_R; ++k) {       // k = (band*R + r)*32 + L; rows beyond m are junk
+            for (uint32_t k = (uint32_t)lane; k < wp.nbands * 32u * WIDE_R; k += 32u) {   // k = (band*R + r)*32 + L; rows beyond m are junk
                 const uint32_t L = k & 31u, br = k >> 5, r = br % WIDE_R, band = br / WIDE_R;
                 if (band * 32u * WIDE_R + L * WIDE_R + r >= wp.m) continue;
-                const int v = (int)A.rowbest[wp.rowbest_off + k];
-                if (v > M) M = v;
+                M = max(M, (int)A.rowbest[wp.rowbest_off + k]);
             }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) M = max(M, __shfl_xor_sync(0xFFFFFFFFu, M, o));
             res.score = M;
         } else { res.score = (wp.m && wp.n) ? A.final_score[t] : (int32_t)(wp.m + wp.n) * A.gap; res.end_i = wp.m; res.end_j = wp.n; }
-        A.results[wp.pair] = res;
+        if (lane == 0) A.results[wp.pair] = res;
         return;
     }
     const Chunk* rec = A.codes + wp.code_off;
-    PairView v{rec, A.rowbest + wp.rowbest_off, A.pat + wp.pat_off, A.txt + wp.txt_off,
-               wp.m, wp.n, num_chunks(wp.n, FM::CS), WIDE_R, 0, A.match, A.mismatch, A.gap, 0, A.opt, 0};
-    OpsSink sink(A.ops ? A.ops + A.ops_off[wp.pair] : nullptr);
-    if (LOCAL) walk_local<FM>(v, WideLoader{rec}, sink, res);
-    else walk_global<FM>(v, WideLoader{rec}, sink, res);
+    const PairView v{rec, A.rowbest + wp.rowbest_off, A.pat + wp.pat_off, A.txt + wp.txt_off,
+                     wp.m, wp.n, num_chunks(wp.n, FM::CS), WIDE_R, 0, A.match, A.mismatch, A.gap, 0, A.opt, 0};
+    const WideLoader ld{rec};
+    WarpOpsSink sink(A.ops ? A.ops + A.ops_off[wp.pair] : nullptr, lane == 0);
+    uint32_t i, j, nops = 0;
+    int best = 0;
+    if (LOCAL) {
+        int M; uint32_t bi, bj;
+        warp_find_local_end<FM>(v, ld, M, bi, bj);
+        res.score = M; res.end_i = bi; res.end_j = bj;
+        i = bi; j = bj;
+        if (M != 0) warp_walk<FM, WideLoader, true>(v, ld, sink, i, j, nops, best);
+    } else {
+        i = wp.m; j = wp.n;
+        res.end_i = i; res.end_j = j;
+        res.score = (i && j) ? A.final_score[t] : (int32_t)(i + j) * A.gap;               // hw2.cpp:186 / borders :125-136
+        warp_walk<FM, WideLoader, false>(v, ld, sink, i, j, nops, best);
+        sink.put_run(OP_D, i); nops += i; i = 0;                                           // column 0 holds 'u' (hw2.cpp:128)
+        sink.put_run(OP_I, j); nops += j; j = 0;                                           // row 0 holds 'l'    (hw2.cpp:134)
+    }
     sink.flush();
-    res.path = 2;
-    A.results[wp.pair] = res;
+    res.start_i = i; res.start_j = j; res.overlap = best; res.n_ops = nops; res.path = 2;
+    if (lane == 0) A.results[wp.pair] = res;
 }
 
 } // namespace b2a
