@@ -12,14 +12,15 @@
 // tie-breaking is involved.
 //
 // Same execution scheme as wide32.cuh: bands of 128 rows (32 lanes x 4 rows), a warp sweeps its band
-// as a skewed wavefront, bands of one pair are chained through boundary rows in L2/HBM guarded by
-// per-band progress counters, bands are claimed from a ticket counter in (band, pair) order inside one
-// launch.  Per cell the lane keeps  Vg = V + Go + Ge,  E  and  M3 = max(V, F, E); F only travels
+// as a skewed wavefront, bands of one pair are chained through boundary rows of self-validating
+// tagged 64-bit entries in L2 (three per column: Vg, F, M3), bands are claimed from a ticket counter
+// in (band, pair) order inside one launch.  Per cell the lane keeps  Vg = V + Go + Ge,  E  and  M3 = max(V, F, E); F only travels
 // downwards inside the step.  6 integer instructions per cell:
 //     PRMT|SEL (s)   IADD (V = M3diag + s)   VIADDMNMX (F)   VIADDMNMX (E)   IADD (Vg)   VIMNMX3 (M3)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "b2a_format.h"
 #include "wide32.cuh"
 
@@ -28,17 +29,21 @@ namespace b2a {
 struct AffineArgs {
     const uint8_t*  pat;
     const uint8_t*  txt;
-    const WidePair* pairs;          // bound_off indexes 2 buffers x 3 planes x bound_stride int32
+    const WidePair* pairs;          // bound_off indexes 2 buffers x 3 planes x bound_stride tagged entries
     const WideTask* tasks;
     uint32_t        n_tasks;
     uint32_t*       ticket;
-    int32_t*        bound;
-    uint32_t*       progress;
+    uint64_t*       bound;
     int32_t*        final_score;    // per pair: max(V, F, E)[m][n]
     int32_t         match, mismatch, gopen, gext;
+    uint32_t        epoch_tag;
     const AlphaInfo* alpha;         // ALPHA4 variant only
 };
 
+#ifndef AFFINE_UNROLL
+#define AFFINE_UNROLL 32
+#endif
+constexpr int AFF_UNROLL = AFFINE_UNROLL;
 constexpr int32_t AFFINE_NEG = INT32_MIN / 2;        // hw3.cpp:16
 
 template <bool ALPHA4>
@@ -47,6 +52,7 @@ affine32_score_kernel(const AffineArgs A)
 {
     constexpr int R = WIDE_R;
     __shared__ uint4 s_ring[WIDE_WARPS][64];       // per 1-based column j (slot j & 63): {text entry, Vg, F, M3 of the row above the band}
+    __shared__ uint4 s_out[WIDE_WARPS][32];        // {Vg, F, M3} of the band's bottom row, produced by lane 31 during the current block
     __shared__ uint32_t s_tbl4[256];
     uint8_t sym[4] = {0, 0, 0, 0};
     if (ALPHA4) {
@@ -66,6 +72,7 @@ affine32_score_kernel(const AffineArgs A)
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint4* ring = s_ring[warp];
+    uint4* outb = s_out[warp];
     const int32_t ge = A.gext, go = A.gopen, goe = A.gopen + A.gext, NEG = AFFINE_NEG;
 
     for (;;) {
@@ -98,23 +105,26 @@ affine32_score_kernel(const AffineArgs A)
         }
         Fk = M3[R - 1];
         const uint64_t plane = wp.bound_stride;
-        const int32_t* bin = A.bound + wp.bound_off + (uint64_t)((band + 1u) & 1u) * 3u * plane;
-        int32_t* bout = A.bound + wp.bound_off + (uint64_t)(band & 1u) * 3u * plane;
-        const uint32_t* prog_in = A.progress + wp.prog_off + band - 1;
-        uint32_t* prog_out = A.progress + wp.prog_off + band;
+        const uint64_t* bin = A.bound + wp.bound_off + (uint64_t)((band + 1u) & 1u) * 3u * plane;
+        uint64_t* bout = A.bound + wp.bound_off + (uint64_t)(band & 1u) * 3u * plane;
+        const uint32_t tag_in = A.epoch_tag + band;
+        const uint64_t tag_out = (uint64_t)(A.epoch_tag + band + 1u) << 32;
         const bool has_next = band + 1 < wp.nbands;
         const uint32_t nblk = (n + 32u + 31u) / 32u;
         // max(V, F, E) of the row above the band at column 0: V[0][0] = 0 for the first band, else F[i][0]
         const int32_t top0 = band == 0 ? 0 : go + ge * (int32_t)(band * 32u * R - 1u);
         int32_t dgn = row0 == 0 ? 0 : go + ge * (int32_t)(row0 - 1u);       // M3[row above][0]; lane 0 reloads it from the ring at q = 0
-        uint32_t have = band == 0 ? 0xFFFFFFFFu : 0u;
+        uint64_t nx0 = 0, nx1 = 0, nx2 = 0;                                   // this lane's entries of the next block, loaded a block ahead
+        if (band != 0 && lane >= 1 && (uint32_t)lane <= n) {
+            nx0 = ld_relaxed_u64(bin + lane); nx1 = ld_relaxed_u64(bin + plane + lane); nx2 = ld_relaxed_u64(bin + 2u * plane + lane);
+        }
 
-        auto text_entry = [&](uint32_t j) -> uint32_t {
-            if (j == 0 || j > n) return ALPHA4 ? 0u : 0xFFFFFF00u;
-            const uint8_t x = tt[j - 1];
-            return ALPHA4 ? s_tbl4[x] : (uint32_t)x;
+        auto text_byte = [&](uint32_t j) -> uint32_t { return (j == 0 || j > n) ? 0x100u : (uint32_t)tt[j - 1]; };   // one block ahead
+        auto text_entry = [&](uint32_t x) -> uint32_t {
+            if (x & 0x100u) return ALPHA4 ? 0u : 0xFFFFFF00u;
+            return ALPHA4 ? s_tbl4[x] : x;
         };
-        uint32_t tnext = text_entry((uint32_t)lane);
+        uint32_t tnext = text_byte((uint32_t)lane);
 
         for (uint32_t kb = 0; kb < nblk; ++kb) {
             const uint32_t q0 = kb * 32u;
@@ -124,54 +134,65 @@ affine32_score_kernel(const AffineArgs A)
                 bVg = NEG + goe; bF = NEG;
                 bM = jcol == 0 ? 0 : go + ge * (int32_t)(jcol - 1u);
             } else {
-                const uint32_t need = kb + 2u < nblk ? kb + 2u : nblk;
-                while (have < need) { have = ld_acquire_u32(prog_in); if (have < need) __nanosleep(64); }
-                if (jcol >= 1 && jcol <= n) { bVg = __ldcg(bin + jcol); bF = __ldcg(bin + plane + jcol); bM = __ldcg(bin + 2u * plane + jcol); }
-                else { bVg = NEG + goe; bF = NEG; bM = top0; }
+                const bool need = jcol >= 1 && jcol <= n;
+                bVg = (int32_t)bound_wait(bin + jcol, nx0, tag_in, need);
+                bF  = (int32_t)bound_wait(bin + plane + jcol, nx1, tag_in, need);
+                bM  = (int32_t)bound_wait(bin + 2u * plane + jcol, nx2, tag_in, need);
+                if (!need) { bVg = NEG + goe; bF = NEG; bM = top0; }
+                const uint32_t jn = jcol + 32u;
+                if (jn <= n) { nx0 = ld_relaxed_u64(bin + jn); nx1 = ld_relaxed_u64(bin + plane + jn); nx2 = ld_relaxed_u64(bin + 2u * plane + jn); }
             }
             __syncwarp();
-            ring[jcol & 63u] = make_uint4(tnext, (uint32_t)bVg, (uint32_t)bF, (uint32_t)bM);
+            ring[jcol & 63u] = make_uint4(text_entry(tnext), (uint32_t)bVg, (uint32_t)bF, (uint32_t)bM);
             __syncwarp();
-            tnext = text_entry(q0 + 32u + (uint32_t)lane);
-            const bool steady = q0 >= 32u && q0 + 31u <= n;
+            tnext = text_byte(q0 + 32u + (uint32_t)lane);
 
-            auto step = [&](uint32_t q, bool active) {
+            const bool steady = q0 >= 32u && q0 + 31u <= n;
+            // RAMP flavour freezes the lanes outside 1 <= q - lane <= n with selects, not a branch (see wide32.cuh)
+            auto step = [&](uint32_t q, auto ramp_tag, bool active) {
+                constexpr bool RAMP = decltype(ramp_tag)::value;
                 int32_t uVg = __shfl_up_sync(0xFFFFFFFFu, Vg[R - 1], 1);
                 int32_t uF  = __shfl_up_sync(0xFFFFFFFFu, Fk, 1);
                 int32_t uM  = __shfl_up_sync(0xFFFFFFFFu, M3[R - 1], 1);
                 const uint4 e = ring[(q - (uint32_t)lane) & 63u];
                 if (lane == 0) { uVg = (int32_t)e.y; uF = (int32_t)e.z; uM = (int32_t)e.w; }
-                const int32_t dg0 = dgn;
+                int32_t dg = dgn;
                 dgn = uM;
-                if (active) {
-                    int32_t dg = dg0;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int32_t s = ALPHA4 ? (int32_t)prmt32(e.x, 0u, pc[r]) : (pc[r] == e.x ? A.match : A.mismatch);
-                        const int32_t v = dg + s;                            // hw3.cpp:59-68
-                        dg = M3[r];
-                        const int32_t f  = __viaddmax_s32(uF, ge, uVg);      // hw3.cpp:70-75
-                        const int32_t ee = __viaddmax_s32(E[r], ge, Vg[r]);  // hw3.cpp:77-82
-                        const int32_t vg = v + goe;
-                        M3[r] = __vimax3_s32(v, f, ee);
-                        Vg[r] = vg; E[r] = ee;
-                        uVg = vg; uF = f;
-                    }
-                    Fk = uF;
-                    if (lane == 31 && has_next) {
-                        const uint32_t j = q - 31u;
-                        __stcg(bout + j, Vg[R - 1]); __stcg(bout + plane + j, Fk); __stcg(bout + 2u * plane + j, M3[R - 1]);
-                    }
+                for (int r = 0; r < R; ++r) {
+                    const int32_t s = ALPHA4 ? (int32_t)prmt32(e.x, 0u, pc[r]) : (pc[r] == e.x ? A.match : A.mismatch);
+                    const int32_t v = dg + s;                                // hw3.cpp:59-68
+                    dg = M3[r];
+                    const int32_t f  = __viaddmax_s32(uF, ge, uVg);          // hw3.cpp:70-75
+                    const int32_t ee = __viaddmax_s32(E[r], ge, Vg[r]);      // hw3.cpp:77-82
+                    const int32_t vg = v + goe;
+                    const int32_t m3 = __vimax3_s32(v, f, ee);
+                    if (RAMP) { M3[r] = active ? m3 : M3[r]; Vg[r] = active ? vg : Vg[r]; E[r] = active ? ee : E[r]; }
+                    else { M3[r] = m3; Vg[r] = vg; E[r] = ee; }
+                    uVg = vg; uF = f;
                 }
+                if (RAMP) Fk = active ? uF : Fk; else Fk = uF;
+                if (lane == 31) outb[q & 31u] = make_uint4((uint32_t)Vg[R - 1], (uint32_t)Fk, (uint32_t)M3[R - 1], 0u);
             };
+            // small unroll on purpose: compact code keeps a band's first (cold) blocks cheap, see wide32.cuh
             if (steady) {
-#pragma unroll 8
-                for (int f = 0; f < 32; ++f) step(q0 + (uint32_t)f, true);
+#pragma unroll AFF_UNROLL
+                for (int f = 0; f < 32; ++f) step(q0 + (uint32_t)f, std::false_type{}, true);
             } else {
-#pragma unroll 4
-                for (int f = 0; f < 32; ++f) step(q0 + (uint32_t)f, (uint32_t)(q0 + (uint32_t)f - lane - 1u) < n);
+#pragma unroll AFF_UNROLL
+                for (int f = 0; f < 32; ++f) step(q0 + (uint32_t)f, std::true_type{}, (uint32_t)(q0 + (uint32_t)f - lane - 1u) < n);
             }
-            if (has_next && lane == 31) st_release_u32(prog_out, kb + 1u);
+            if (has_next) {                                                  // publish the block's bottom row, one coalesced store per plane
+                __syncwarp();
+                const uint32_t jc = q0 + (uint32_t)lane - 31u;
+                if (jc - 1u < n) {
+                    const uint4 o = outb[lane];
+                    st_relaxed_u64(bout + jc, tag_out | o.x);
+                    st_relaxed_u64(bout + plane + jc, tag_out | o.y);
+                    st_relaxed_u64(bout + 2u * plane + jc, tag_out | o.z);
+                }
+                __syncwarp();
+            }
         }
         if (band + 1 == wp.nbands) {                                         // hw3.cpp:86-98: max(V, F, E)[m][n]
             const uint32_t ib = (m - 1u) - band * 32u * R;

@@ -86,14 +86,30 @@ struct Lane {                                     // one DP record, reused by ev
 struct WideState {
     std::vector<WidePair> pairs;
     std::vector<WideTask> tasks;
-    uint64_t chunks = 0, bound_ints = 0, rowbest_words = 0, prog_words = 0;
+    uint64_t chunks = 0, bound_words = 0, rowbest_words = 0;
+    uint32_t epoch = 0;                           // boundary-entry tags carry it, so stale entries of earlier launches never validate
     int K = 32;
     bool alpha4 = false, store = true;
     DevBuf<WidePair> d_pairs;
     DevBuf<WideTask> d_tasks;
     DevBuf<Chunk> d_codes;
-    DevBuf<int32_t> d_bound, d_final;
-    DevBuf<uint32_t> d_rowbest, d_progress;       // d_progress[prog_words] is the ticket counter
+    DevBuf<uint64_t> d_bound;                     // tagged boundary entries (wide32.cuh)
+    DevBuf<int32_t> d_final;
+    DevBuf<uint32_t> d_rowbest, d_progress;       // d_progress[0] is the ticket counter
+    // epoch tag of the next launch; the boundary buffer is cleared when it was reallocated or the 12-bit epoch wraps
+    cudaError_t next_epoch(uint64_t need_words, cudaStream_t st, uint32_t* tag) {
+        const size_t cap_before = d_bound.cap;
+        cudaError_t e = d_bound.reserve(need_words);
+        if (e != cudaSuccess) return e;
+        epoch = (epoch + 1u) & 0xFFFu;
+        // a reallocation may hand back the same address with uncleared memory behind the old end
+        if (d_bound.cap != cap_before || epoch == 0u) {
+            epoch = 1u;
+            e = cudaMemsetAsync(d_bound.p, 0, d_bound.cap * sizeof(uint64_t), st);
+        }
+        *tag = epoch << 20;
+        return e;
+    }
     void release() {
         d_pairs.release(); d_tasks.release(); d_codes.release(); d_bound.release(); d_final.release();
         d_rowbest.release(); d_progress.release();
@@ -295,7 +311,7 @@ int wide_plan(b2a_ctx* ctx, const uint64_t* pat_off, const uint64_t* txt_off, bo
     WideState& W = ctx->wide;
     const b2a_params& prm = ctx->prm;
     W.pairs.clear(); W.tasks.clear();
-    W.chunks = W.bound_ints = W.rowbest_words = W.prog_words = 0;
+    W.chunks = W.bound_words = W.rowbest_words = 0;
     W.K = delta_bits_wide(prm.match, prm.mismatch, prm.gap);
     W.store = store;
     W.alpha4 = alpha4 && prm.match <= 127 && prm.match >= -128 && prm.mismatch <= 127 && prm.mismatch >= -128;
@@ -310,9 +326,9 @@ int wide_plan(b2a_ctx* ctx, const uint64_t* pat_off, const uint64_t* txt_off, bo
         p.code_off = W.chunks;
         if (store) W.chunks += (uint64_t)p.nbands * WIDE_R * num_chunks(p.n, CS) * 32u;
         p.bound_stride = ((p.n + 64u) + 31u) & ~31u;
-        p.bound_off = W.bound_ints; W.bound_ints += 2ull * p.bound_stride;
+        p.bound_off = W.bound_words; if (p.nbands > 1u) W.bound_words += 2ull * p.bound_stride;   // single-band pairs exchange nothing
         p.rowbest_off = W.rowbest_words; W.rowbest_words += (uint64_t)p.nbands * 32u * WIDE_R;
-        p.prog_off = W.prog_words; W.prog_words += p.nbands;
+        if (p.nbands >= (1u << 20)) return fail(ctx, B2A_ERR_RANGE, "wide32: pattern too long (band index must fit 20 bits)");
         max_bands = std::max(max_bands, p.nbands);
         W.pairs.push_back(p);
     }
@@ -323,8 +339,8 @@ int wide_plan(b2a_ctx* ctx, const uint64_t* pat_off, const uint64_t* txt_off, bo
     for (uint32_t b = 0; b < max_bands; ++b)
         for (uint32_t i : order) { if (W.pairs[i].nbands <= b) break; W.tasks.push_back(WideTask{i, b}); }
     CU(W.d_pairs.reserve(W.pairs.size())); CU(W.d_tasks.reserve(W.tasks.size()));
-    CU(W.d_codes.reserve(W.chunks)); CU(W.d_bound.reserve(W.bound_ints)); CU(W.d_final.reserve(W.pairs.size()));
-    CU(W.d_rowbest.reserve(W.rowbest_words)); CU(W.d_progress.reserve(W.prog_words + 1));
+    CU(W.d_codes.reserve(W.chunks)); CU(W.d_final.reserve(W.pairs.size()));
+    CU(W.d_rowbest.reserve(W.rowbest_words)); CU(W.d_progress.reserve(1));
     // the vectors outlive the copies: every caller synchronises `st` before the next batch touches them
     if (!W.pairs.empty()) CU(cudaMemcpyAsync(W.d_pairs.p, W.pairs.data(), W.pairs.size() * sizeof(WidePair), cudaMemcpyHostToDevice, st));
     if (!W.tasks.empty()) CU(cudaMemcpyAsync(W.d_tasks.p, W.tasks.data(), W.tasks.size() * sizeof(WideTask), cudaMemcpyHostToDevice, st));
@@ -338,19 +354,34 @@ int wide_fill(b2a_ctx* ctx, cudaStream_t st, uint64_t* launches)
     WideState& W = ctx->wide;
     if (W.tasks.empty()) return B2A_OK;
     const b2a_params& prm = ctx->prm;
-    CU(cudaMemsetAsync(W.d_progress.p, 0, (W.prog_words + 1) * 4, st));
+    CU(cudaMemsetAsync(W.d_progress.p, 0, 4, st));
     WideArgs a{};
+    CU(W.next_epoch(W.bound_words, st, &a.epoch_tag));
     a.pat = ctx->d_pat.p; a.txt = ctx->d_txt.p; a.pairs = W.d_pairs.p; a.tasks = W.d_tasks.p;
-    a.n_tasks = (uint32_t)W.tasks.size(); a.ticket = W.d_progress.p + W.prog_words;
-    a.codes = W.d_codes.p; a.bound = W.d_bound.p; a.rowbest = W.d_rowbest.p; a.progress = W.d_progress.p;
+    a.n_tasks = (uint32_t)W.tasks.size(); a.ticket = W.d_progress.p;
+    a.codes = W.d_codes.p; a.bound = W.d_bound.p; a.rowbest = W.d_rowbest.p;
     a.final_score = W.d_final.p;
     a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap;
     a.radix = W.K < 32 ? (1u << W.K) : 0u;
     a.alpha = ctx->d_alpha.p + (ctx->alpha_slots - 1);
     const unsigned need = (unsigned)((W.tasks.size() + WIDE_WARPS - 1) / WIDE_WARPS);
     const unsigned grid = std::min<unsigned>(need, (unsigned)ctx->sm_count * 8u);
+    static const bool dbg = std::getenv("B2A_WIDE_DEBUG") != nullptr;
+    unsigned long long* d_dbg = nullptr;
+    if (dbg) { CU(cudaMalloc((void**)&d_dbg, W.tasks.size() * 64)); CU(cudaMemsetAsync(d_dbg, 0, W.tasks.size() * 64, st)); a.debug = d_dbg; }
     CU(launch_wide_fill(W.K, prm.mode == B2A_MODE_LOCAL, W.store, W.alpha4, a, grid, st));
     ++*launches;
+    if (dbg) {
+        std::vector<unsigned long long> h(W.tasks.size() * 8);
+        CU(cudaMemcpyAsync(h.data(), d_dbg, h.size() * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        cudaFree(d_dbg);
+        const unsigned long long t0 = h[0];
+        for (size_t k = 0; k < W.tasks.size(); k += std::max<size_t>(1, W.tasks.size() / 40))
+            std::fprintf(stderr, "[wide dbg] band %5u: blk0 waited %8.2f us | ring +%5.2f steps +%5.2f stores +%5.2f | blk1 wait +%5.2f compute +%5.2f | done %9.2f\n",
+                         W.tasks[k].band, (h[8 * k + 1] - t0) * 1e-3, (h[8 * k + 2] - h[8 * k + 1]) * 1e-3, (h[8 * k + 3] - h[8 * k + 2]) * 1e-3,
+                         (h[8 * k + 4] - h[8 * k + 3]) * 1e-3, (h[8 * k + 5] - h[8 * k + 4]) * 1e-3, (h[8 * k + 6] - h[8 * k + 5]) * 1e-3, (h[8 * k + 7] - t0) * 1e-3);
+    }
     return B2A_OK;
 }
 
@@ -464,7 +495,7 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
                                             std::llabs((long long)gopen) + std::llabs((long long)gext)});
     WideState& W = ctx->wide;
     W.pairs.clear(); W.tasks.clear();
-    W.bound_ints = W.prog_words = 0;
+    W.bound_words = 0;
     uint32_t max_bands = 0;
     std::vector<uint32_t> slot(specs.size(), 0xFFFFFFFFu);
     for (size_t k = 0; k < specs.size(); ++k) {
@@ -478,8 +509,8 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
         p.pat_off = sp.pat_off; p.txt_off = sp.txt_off; p.m = sp.m; p.n = sp.n; p.pair = (uint32_t)k;
         p.nbands = (sp.m + 32u * WIDE_R - 1u) / (32u * WIDE_R);
         p.bound_stride = ((sp.n + 64u) + 31u) & ~31u;
-        p.bound_off = W.bound_ints; W.bound_ints += 6ull * p.bound_stride;     // 2 buffers x {Vg, F, M3}
-        p.prog_off = W.prog_words; W.prog_words += p.nbands;
+        if (p.nbands >= (1u << 20)) return fail(ctx, B2A_ERR_RANGE, "b2a_affine: sequence too long (band index must fit 20 bits)");
+        p.bound_off = W.bound_words; if (p.nbands > 1u) W.bound_words += 6ull * p.bound_stride;   // 2 buffers x {Vg, F, M3}
         max_bands = std::max(max_bands, p.nbands);
         slot[k] = (uint32_t)W.pairs.size();
         W.pairs.push_back(p);
@@ -495,7 +526,7 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
     if (!same_buffer) CU(ctx->d_txt.reserve(txt_bytes + 16));
     CU(ctx->d_alpha.reserve(2)); CU(ctx->h_alpha.reserve(2));
     CU(W.d_pairs.reserve(W.pairs.size())); CU(W.d_tasks.reserve(W.tasks.size()));
-    CU(W.d_bound.reserve(W.bound_ints)); CU(W.d_final.reserve(W.pairs.size())); CU(W.d_progress.reserve(W.prog_words + 1));
+    CU(W.d_final.reserve(W.pairs.size())); CU(W.d_progress.reserve(1));
     if (pat_bytes) CU(cudaMemcpyAsync(ctx->d_pat.p, pat, pat_bytes, cudaMemcpyHostToDevice, st));
     if (!same_buffer && txt_bytes) CU(cudaMemcpyAsync(ctx->d_txt.p, txt, txt_bytes, cudaMemcpyHostToDevice, st));
     ctx->h2d += pat_bytes + (same_buffer ? 0 : txt_bytes);
@@ -519,11 +550,12 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
     std::vector<int32_t> fin(W.pairs.size());
     float ms = 0;
     if (!W.tasks.empty()) {
-        CU(cudaMemsetAsync(W.d_progress.p, 0, (W.prog_words + 1) * 4, st));
+        CU(cudaMemsetAsync(W.d_progress.p, 0, 4, st));
         AffineArgs a{};
+        CU(W.next_epoch(W.bound_words, st, &a.epoch_tag));
         a.pat = ctx->d_pat.p; a.txt = same_buffer ? ctx->d_pat.p : ctx->d_txt.p; a.pairs = W.d_pairs.p; a.tasks = W.d_tasks.p;
-        a.n_tasks = (uint32_t)W.tasks.size(); a.ticket = W.d_progress.p + W.prog_words;
-        a.bound = W.d_bound.p; a.progress = W.d_progress.p; a.final_score = W.d_final.p;
+        a.n_tasks = (uint32_t)W.tasks.size(); a.ticket = W.d_progress.p;
+        a.bound = W.d_bound.p; a.final_score = W.d_final.p;
         a.match = match; a.mismatch = mismatch; a.gopen = gopen; a.gext = gext; a.alpha = ctx->d_alpha.p;
         const unsigned need = (unsigned)((W.tasks.size() + WIDE_WARPS - 1) / WIDE_WARPS);
         const unsigned grid = std::min<unsigned>(need, (unsigned)ctx->sm_count * 8u);

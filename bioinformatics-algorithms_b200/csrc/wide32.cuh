@@ -4,15 +4,22 @@
 // Replaces the same reference loops as short16 (hw2.cpp:138-156 / :205-231) for ONE pair spread over
 // many warps: the DP matrix is cut into BANDS of 128 pattern rows (32 lanes x 4 rows); a warp sweeps
 // its band along the text as a skewed wavefront (__shfl_up_sync carries the in-warp diagonal
-// dependency) and exchanges the band's bottom row with the band below through L2/HBM in 32-column
-// blocks guarded by a per-band progress counter (st.release / ld.acquire).  Bands are handed out by
-// a ticket counter in (band, pair) order, so the band a warp waits for was always claimed earlier by
-// a warp that is already running: no cooperative launch is needed and nothing can deadlock.
+// dependency) and hands the band's bottom row to the band below through L2 as SELF-VALIDATING 64-bit
+// entries {H, tag}: value and validity travel in one atomic word, so neither side needs a fence or a
+// separate progress flag (an earlier st.release/ld.acquire counter design spent 60 % of a single long
+// pair's time in membar/long-scoreboard stalls, profiles/r01_ncu_wide32_c4.md).  The consumer loads
+// its column of the next 32-column block one block ahead and only re-polls if the tag is not there yet.
+// tag = epoch * 2^20 + band + 1: the two boundary buffers of a pair alternate between bands, the epoch
+// changes with every launch, the host clears the buffers when the epoch wraps or the buffer moves.
+// Bands are handed out by a ticket counter in (band, pair) order, so the band a warp waits for was
+// always claimed earlier by a warp that is already running: no cooperative launch is needed and
+// nothing can deadlock.
 // The traceback record is the same delta/anchor chunk format as short16 (b2a_format.h, Wide32<K>),
 // written with the same ring-arithmetic word trick; K = 32 stores raw deltas and covers any scoring.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "b2a_format.h"
 #include "short16_fill.cuh"
 #include "walk_warp.cuh"
@@ -22,9 +29,8 @@ namespace b2a {
 struct WidePair {
     uint64_t pat_off, txt_off;      // byte offsets of the pair's sequences
     uint64_t code_off;              // first chunk of the pair's record
-    uint64_t bound_off;             // int32 index of the pair's 2 boundary rows (each bound_stride long)
+    uint64_t bound_off;             // entry index of the pair's 2 boundary rows (each bound_stride long); multi-band pairs only
     uint64_t rowbest_off;           // uint32 index, nbands*128 entries
-    uint64_t prog_off;              // uint32 index, nbands entries
     uint32_t m, n, pair, nbands;
     uint32_t bound_stride, pad;
 };
@@ -38,24 +44,44 @@ struct WideArgs {
     uint32_t        n_tasks;
     uint32_t*       ticket;
     Chunk*          codes;
-    int32_t*        bound;
+    uint64_t*       bound;          // tagged boundary entries: (tag << 32) | (uint32) H
     uint32_t*       rowbest;
-    uint32_t*       progress;
     int32_t*        final_score;    // per wide pair: H(m, n) (global mode)
     int32_t         match, mismatch, gap;
     uint32_t        radix;
+    uint32_t        epoch_tag;      // epoch << 20
+    unsigned long long* debug;      // optional (B2A_WIDE_DEBUG): per task {claimed, first block staged, first block done, band done} in ns
     const AlphaInfo* alpha;         // used by the ALPHA4 variant only
 };
 
 constexpr int WIDE_WARPS = 4;
+#ifndef WIDE_MID_UNROLL
+#define WIDE_MID_UNROLL 32     // unroll of the F-2 middle steps of a delta word (tuned on config 4 / config 5, scripts/bench_long.py)
+#endif
+constexpr int MID_UNROLL = WIDE_MID_UNROLL;
 
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));       // no "memory" clobber: nothing else is ordered by it
     return v;
 }
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v));
+}
+// Waits until this lane's tagged boundary entry (if it `need`s one) carries `tag`; `v` is a copy loaded a block
+// earlier.  WARP-UNIFORM on purpose: every lane leaves the loop in the same iteration (__all_sync).  A per-lane
+// polling loop left the warp split into sub-warps that then executed the whole next block of shuffle-synchronised
+// steps one group after the other (3.5x slower first block of every band, measured with B2A_WIDE_DEBUG stamps).
+// Re-polls back off so that hundreds of waiting bands of one long pair do not flood L2.
+__device__ __forceinline__ uint32_t bound_wait(const uint64_t* p, uint64_t v, uint32_t tag, bool need) {
+    uint32_t ns = 32;
+    for (;;) {
+        const bool ok = !need || (uint32_t)(v >> 32) == tag;
+        if (__all_sync(0xFFFFFFFFu, ok)) break;
+        __nanosleep(ns); ns = min(ns * 2u, 256u);
+        if (!ok) v = ld_relaxed_u64(p);
+    }
+    return (uint32_t)v;
 }
 __device__ __forceinline__ uint32_t prmt32(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
@@ -72,6 +98,7 @@ wide32_fill_kernel(const WideArgs A)
     using FM = Wide32<K>;
     constexpr int R = WIDE_R, F = FM::F, CS = FM::CS, CPB = 32 / CS;   // chunks per 32-step block
     __shared__ uint2 s_ring[WIDE_WARPS][64];       // per 1-based column j (slot j & 63): {text entry, H(top row, j)}
+    __shared__ int32_t s_out[WIDE_WARPS][32];      // bottom-row values lane 31 produced during the current block
     __shared__ uint32_t s_tbl4[256];
     uint8_t sym[4] = {0, 0, 0, 0};
     if (ALPHA4) {
@@ -91,6 +118,7 @@ wide32_fill_kernel(const WideArgs A)
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint2* ring = s_ring[warp];
+    int32_t* outb = s_out[warp];
     const int gap = A.gap;
     const uint32_t radix = A.radix, g32 = (uint32_t)gap;
     uint32_t geo = 0, bpow = 1;
@@ -128,69 +156,95 @@ wide32_fill_kernel(const WideArgs A)
             H[r] = LOCAL ? 0 : (int32_t)(i0 + 1) * gap;                      // hw2.cpp:125-130
             best[r] = 0;
         }
-        const int32_t* bin = A.bound + wp.bound_off + (uint64_t)((band + 1u) & 1u) * wp.bound_stride;
-        int32_t* bout = A.bound + wp.bound_off + (uint64_t)(band & 1u) * wp.bound_stride;
-        const uint32_t* prog_in = A.progress + wp.prog_off + band - 1;
-        uint32_t* prog_out = A.progress + wp.prog_off + band;
+        const uint64_t* bin = A.bound + wp.bound_off + (uint64_t)((band + 1u) & 1u) * wp.bound_stride;
+        uint64_t* bout = A.bound + wp.bound_off + (uint64_t)(band & 1u) * wp.bound_stride;
+        const uint32_t tag_in = A.epoch_tag + band;                          // what the band above writes
+        const uint64_t tag_out = (uint64_t)(A.epoch_tag + band + 1u) << 32;
         const bool has_next = band + 1 < wp.nbands;
         const uint32_t nblk = (n + 32u + 31u) / 32u;
         const uint32_t NC = num_chunks(n, CS);
         Chunk* rec = A.codes + wp.code_off;
         const int32_t top0 = LOCAL ? 0 : (int32_t)(band * 32u * R) * gap;    // H(top row, 0)
         int32_t dgn = top0;
-        uint32_t have = band == 0 ? 0xFFFFFFFFu : 0u;                        // producer blocks known to be complete
+        uint64_t nx = 0;                                                     // this lane's entry of the next block, loaded a block ahead
+        if (band != 0 && lane >= 1 && (uint32_t)lane <= n) nx = ld_relaxed_u64(bin + lane);
 
-        auto text_entry = [&](uint32_t j) -> uint32_t {                      // ring payload of 1-based column j
-            if (j == 0 || j > n) return ALPHA4 ? 0u : 0xFFFFFF00u;
-            const uint8_t x = tt[j - 1];
-            return ALPHA4 ? s_tbl4[x] : (uint32_t)x;
+        // text byte of 1-based column j, fetched one block ahead (0x100 = outside the text); the score-table
+        // lookup waits until the byte is staged, so the global load has a whole block to arrive
+        auto text_byte = [&](uint32_t j) -> uint32_t { return (j == 0 || j > n) ? 0x100u : (uint32_t)tt[j - 1]; };
+        auto text_entry = [&](uint32_t x) -> uint32_t {                      // ring payload
+            if (x & 0x100u) return ALPHA4 ? 0u : 0xFFFFFF00u;
+            return ALPHA4 ? s_tbl4[x] : x;
         };
-        uint32_t tnext = text_entry((uint32_t)lane);
+        uint32_t tnext = text_byte((uint32_t)lane);
+        auto stamp = [&](int k) {
+            if (A.debug && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); A.debug[8ull * tk + k] = t; }
+        };
+        stamp(0);
 
         for (uint32_t kb = 0; kb < nblk; ++kb) {
             const uint32_t q0 = kb * 32u;
+            if (kb == 1) stamp(4);
+            if (kb == 2) stamp(6);
             // ---- stage columns q0 .. q0+31 of the text and of the band above into the ring ----
             int32_t bnd;
             const uint32_t jcol = q0 + (uint32_t)lane;
             if (band == 0) bnd = LOCAL ? 0 : (int32_t)jcol * gap;            // hw2.cpp:131-136
             else {
-                const uint32_t need = kb + 2u < nblk ? kb + 2u : nblk;
-                while (have < need) { have = ld_acquire_u32(prog_in); if (have < need) __nanosleep(64); }
-                bnd = (jcol >= 1 && jcol <= n) ? __ldcg(bin + jcol) : top0;
+                const bool need = jcol >= 1 && jcol <= n;
+                const int32_t got = (int32_t)bound_wait(bin + jcol, nx, tag_in, need);
+                bnd = need ? got : top0;
+                const uint32_t jn = jcol + 32u;
+                if (jn <= n) nx = ld_relaxed_u64(bin + jn);
             }
             __syncwarp();
-            ring[jcol & 63u] = make_uint2(tnext, (uint32_t)bnd);
+            if (kb == 0) stamp(1);
+            if (kb == 1) stamp(5);
+            ring[jcol & 63u] = make_uint2(text_entry(tnext), (uint32_t)bnd);
             __syncwarp();
-            tnext = text_entry(q0 + 32u + (uint32_t)lane);                   // prefetch the next block's text
+            if (kb == 0) stamp(2);
+            tnext = text_byte(q0 + 32u + (uint32_t)lane);                    // prefetch the next block's text
+            // One wavefront step.  RAMP = false: every lane is inside its row range (steady state).  RAMP = true: lanes
+            // outside 1 <= q - lane <= n keep their H frozen -- done with selects, NOT a branch: a branch per step stops
+            // the scheduler from overlapping the shuffle / shared-memory latencies of neighbouring steps (2.4x slower).
             const bool steady = q0 >= 32u && q0 + 31u <= n;
-
-            auto step = [&](uint32_t q, uint32_t (&S)[R], int f, bool active) {
+            // HM: what the step contributes to the delta word's Horner sum: 0 = start it (S = H), 1 = S = S * 2^K + H, 2 = nothing
+            auto step = [&](uint32_t q, uint32_t (&S)[R], auto hm_tag, auto ramp_tag, bool active) {
+                constexpr bool RAMP = decltype(ramp_tag)::value;
+                constexpr int HM = decltype(hm_tag)::value;
                 int32_t up = __shfl_up_sync(0xFFFFFFFFu, H[R - 1], 1);
                 const uint2 e = ring[(q - (uint32_t)lane) & 63u];   // column q-lane; lane 0 also needs it at q = 0 (H(top,0))
                 if (lane == 0) up = (int32_t)e.y;
-                const int32_t dg0 = dgn;
+                int32_t dg = dgn, u = up;
                 dgn = up;
-                if (active) {
-                    int32_t dg = dg0, u = up;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int32_t s = ALPHA4 ? (int32_t)prmt32(e.x, 0u, pc[r]) : (pc[r] == e.x ? A.match : A.mismatch);
-                        const int32_t ds = dg + s;
-                        dg = H[r];
-                        const int32_t a = __viaddmax_s32(H[r], gap, ds);
-                        const int32_t h = LOCAL ? __viaddmax_s32_relu(u, gap, a) : __viaddmax_s32(u, gap, a);
-                        if (LOCAL) best[r] = max(best[r], h);
-                        H[r] = h; u = h;
-                    }
-                    if (lane == 31 && has_next) __stcg(bout + (q - 31u), H[R - 1]);
+                for (int r = 0; r < R; ++r) {
+                    const int32_t s = ALPHA4 ? (int32_t)prmt32(e.x, 0u, pc[r]) : (pc[r] == e.x ? A.match : A.mismatch);
+                    const int32_t ds = dg + s;
+                    dg = H[r];
+                    const int32_t a = __viaddmax_s32(H[r], gap, ds);
+                    int32_t h = LOCAL ? __viaddmax_s32_relu(u, gap, a) : __viaddmax_s32(u, gap, a);
+                    if (RAMP) h = active ? h : H[r];
+                    if (LOCAL) best[r] = max(best[r], h);        // a frozen H is a border 0 or a value already counted
+                    H[r] = h; u = h;
                 }
-                if (STORE && K < 32) {
+                if (lane == 31) outb[q & 31u] = H[R - 1];        // bottom row of the band at column q - 31 (published per block)
+                if (STORE && K < 32 && HM != 2) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        if (f == 0) S[r] = (uint32_t)H[r];
-                        else if (f < F - 1) S[r] = S[r] * radix + (uint32_t)H[r];
-                    }
+                    for (int r = 0; r < R; ++r) S[r] = HM == 0 ? (uint32_t)H[r] : S[r] * radix + (uint32_t)H[r];
                 }
+            };
+            // The F steps of one delta word.  Deliberately NOT fully unrolled: fully unrolled the two flavours were 38 KB
+            // of straight-line code, and every band of a long pair paid ~6 us of instruction-fetch stalls for its first
+            // (cold) ramp block -- a cost that chains over all bands of the pair (B2A_WIDE_DEBUG timeline, scripts/band_exp.py).
+            auto word_steps = [&](uint32_t qw, uint32_t (&S)[R], auto ramp_tag) {
+                constexpr bool RAMP = decltype(ramp_tag)::value;
+                auto act = [&](uint32_t q) { return !RAMP || (uint32_t)(q - lane - 1u) < n; };
+                if (F == 1) { step(qw, S, std::integral_constant<int, 2>{}, ramp_tag, act(qw)); return; }
+                step(qw, S, std::integral_constant<int, 0>{}, ramp_tag, act(qw));
+#pragma unroll MID_UNROLL
+                for (int f = 1; f < F - 1; ++f) step(qw + (uint32_t)f, S, std::integral_constant<int, 1>{}, ramp_tag, act(qw + (uint32_t)f));
+                step(qw + (uint32_t)(F - 1), S, std::integral_constant<int, 2>{}, ramp_tag, act(qw + (uint32_t)(F - 1)));
             };
 
 #pragma unroll 1
@@ -202,13 +256,11 @@ wide32_fill_kernel(const WideArgs A)
 #pragma unroll
                     for (int r = 0; r < R; ++r) pre[r] = K == 32 ? (0u - (uint32_t)H[r] - g32) : (uint32_t)H[r] * negBpow + negGc;
                     const uint32_t qw = q0 + (uint32_t)(cb * CS + wi * F);
-                    if (steady) {
-#pragma unroll
-                        for (int f = 0; f < F; ++f) step(qw + f, S, f, true);
-                    } else {
-#pragma unroll
-                        for (int f = 0; f < F; ++f) step(qw + f, S, f, (uint32_t)(qw + f - lane - 1u) < n);
-                    }
+                    // Both flavours are straight-line code of the same speed: the last two blocks of band b wait for the last
+                    // block of band b-1, so a slow ramp flavour is paid once PER BAND on the critical path of a long pair.
+                    if (steady) word_steps(qw, S, std::false_type{});
+                    else word_steps(qw, S, std::true_type{});
+                    if (kb == 0 && cb == CPB - 1 && wi == 1) stamp(3);
                     if (STORE) {
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
@@ -225,8 +277,16 @@ wide32_fill_kernel(const WideArgs A)
                     }
                 }
             }
-            if (has_next && lane == 31) st_release_u32(prog_out, kb + 1u);    // lane 31 wrote the row: its release covers it
+            // publish the 32 bottom-row values of this block as tagged entries: ONE coalesced 64-bit store per lane
+            // per block instead of a store per step (the per-step stores cost 8 % on the 120 x 100 kb batch)
+            if (has_next) {
+                __syncwarp();
+                const uint32_t jc = q0 + (uint32_t)lane - 31u;                // lane 31 was at this column at step q0 + lane
+                if (jc - 1u < n) st_relaxed_u64(bout + jc, tag_out | (uint32_t)outb[lane]);
+                __syncwarp();
+            }
         }
+        stamp(7);
         if (LOCAL) {
 #pragma unroll
             for (int r = 0; r < R; ++r) A.rowbest[wp.rowbest_off + ((uint64_t)band * R + r) * 32u + lane] = (uint32_t)best[r];
