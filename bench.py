@@ -172,19 +172,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    from bioinformatics_algorithms_b200.sharding import max_over_ranks, sum_over_ranks
 
     n_pairs = args.pairs
     pat_np, po_np, txt_np, to_np = workload.config2(n_pairs, seed=481 + rank)

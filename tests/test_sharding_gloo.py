@@ -1,0 +1,112 @@
+"""N > 1 host logic on CPU: two gloo processes shard a batch exactly as two GPU ranks would (contiguous pair
+ranges, no data-path collective), the per-shard 'kernel results' are stood in for by the oracle, and the merged
+winner / star sums must equal the serial answer of the reference's loops (hw2.cpp:326-357, hw3.cpp:231-251)."""
+import os
+import random
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle_binding as ob
+from __graft_entry__ import load_package
+
+pkg = load_package()
+from bioinformatics_algorithms_b200 import sharding  # noqa: E402
+
+
+def make_batch(seed, n):
+    rng = random.Random(seed)
+    ps = [bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 40))) for _ in range(n)]
+    ts = [bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 60))) for _ in range(n)]
+    return ps, ts
+
+
+def oracle_results(mode, ps, ts, s):
+    res = np.zeros(len(ps), dtype=pkg.RESULT_DTYPE)
+    for k, (p, t) in enumerate(zip(ps, ts)):
+        a = ob.align(mode, p, t, *s)
+        res[k] = (a.score, a.end_i, a.end_j, a.start_i, a.start_j, a.overlap, len(a.ops), 0)
+    return res
+
+
+def worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        got = []
+        for seed, n in ((1, 37), (2, 2), (3, 1), (4, 64)):
+            ps, ts = make_batch(seed, n)
+            first, count = sharding.pair_range(n, rank, world)
+            for mode in (ob.GLOBAL, ob.LOCAL):
+                res = oracle_results(mode, ps[first:first + count], ts[first:first + count], (1, -1, -1))
+                got.append(sharding.merge_best(mode, res, first))
+        # tie stress: every pair identical -> the lowest global index must win on every rank
+        ps, ts = [b"ACGTACGT"] * 9, [b"ACGTTCGT"] * 9
+        first, count = sharding.pair_range(9, rank, world)
+        got.append(sharding.merge_best(ob.LOCAL, oracle_results(ob.LOCAL, ps[first:first + count], ts[first:first + count], (1, -1, -1)), first))
+        # hw3 distance stage: shard the i < j pair list, add the partial star sums
+        rng = random.Random(9)
+        seqs = [bytes(rng.choice(b"ACGT") for _ in range(rng.randint(20, 50))) for _ in range(6)]
+        ij = [(i, j) for i in range(6) for j in range(i + 1, 6)]
+        first, count = sharding.star_pair_range(6, rank, world)
+        part = np.zeros(6, dtype=np.int64)
+        for i, j in ij[first:first + count]:
+            v = ob.affine_score(seqs[i], seqs[j], 5, -4, -16, -4)
+            part[i] += v; part[j] += v
+        sums, centre = sharding.reduce_star_sums(part)
+        got.append((list(map(int, sums)), centre))
+        got.append(sharding.max_over_ranks(rank + 1.5))
+        got.append(sharding.sum_over_ranks(rank + 1.0))
+        out[rank] = got
+    finally:
+        dist.destroy_process_group()
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_rank_sharding_matches_serial_reference_logic():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(worker, args=(world, free_port(), out), nprocs=world, join=True)
+    assert out[0] == out[1]                       # every rank holds the same merged answer
+    got = out[0]
+    want = []
+    for seed, n in ((1, 37), (2, 2), (3, 1), (4, 64)):
+        ps, ts = make_batch(seed, n)
+        for mode in (ob.GLOBAL, ob.LOCAL):
+            als = [ob.align(mode, p, t, 1, -1, -1) for p, t in zip(ps, ts)]
+            k = ob.select_best(mode, als)
+            want.append((k, als[k].overlap if mode == ob.GLOBAL else als[k].score))
+    want.append((0, ob.align(ob.LOCAL, b"ACGTACGT", b"ACGTTCGT", 1, -1, -1).score))
+    rng = random.Random(9)
+    seqs = [bytes(rng.choice(b"ACGT") for _ in range(rng.randint(20, 50))) for _ in range(6)]
+    sums = [0] * 6
+    for i in range(6):
+        for j in range(i + 1, 6):
+            v = ob.affine_score(seqs[i], seqs[j], 5, -4, -16, -4)
+            sums[i] += v; sums[j] += v
+    want.append((sums, max(range(6), key=lambda i: (sums[i], -i))))
+    want.append(2.5)
+    want.append(3.0)
+    assert [tuple(x) if isinstance(x, (list, tuple)) and len(x) == 2 and not isinstance(x[0], list) else x for x in got] == \
+           [tuple(x) if isinstance(x, tuple) and not isinstance(x[0], list) else x for x in want]
+
+
+def test_pair_range_partitions_exactly():
+    for n in (0, 1, 2, 7, 120, 1_000_000):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.pair_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+            for (f0, c0), (f1, _) in zip(spans, spans[1:]):
+                assert f0 + c0 == f1
