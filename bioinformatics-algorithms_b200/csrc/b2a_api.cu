@@ -157,6 +157,7 @@ struct b2a_ctx {
     DevBuf<uint32_t> d_ops;
     DevBuf<AlphaInfo> d_alpha;                    // one per segment + one for the whole batch (wide32)
     DevBuf<PairResult> d_results;
+    DevBuf<int4> d_endcell;                       // local mode: end cell per pair, written by the short16 fill epilogue
     HostBuf<PPDesc> h_pps;
     HostBuf<uint64_t> h_code_off, h_ops_off;
     HostBuf<AlphaInfo> h_alpha;
@@ -442,6 +443,7 @@ int launch_segment(b2a_ctx* ctx, size_t si, uint64_t* launches)
         a.pat = ctx->d_pat.p; a.txt = ctx->d_txt.p; a.pat_off = ctx->d_pat_off.p; a.txt_off = ctx->d_txt_off.p;
         a.pps = ctx->d_pps.p + sg.pp_first + c.first; a.code_off = ctx->d_code_off.p + sg.pp_first + c.first; a.codes = ln.codes.p;
         a.rowbest = local ? ln.rowbest.p + (size_t)c.first * c.R * 32 : nullptr;
+        a.endcell = ctx->d_endcell.p;
         a.n_pp = c.count; a.tbl_cap = (c.max_n + 3u) & ~3u;
         a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.bias = pl.bias;
         a.radix = 1u << ctx->K;
@@ -459,6 +461,7 @@ int launch_segment(b2a_ctx* ctx, size_t si, uint64_t* launches)
         a.pat = ctx->d_pat.p; a.txt = ctx->d_txt.p; a.pat_off = ctx->d_pat_off.p; a.txt_off = ctx->d_txt_off.p;
         a.pps = ctx->d_pps.p + sg.pp_first + c.first; a.code_off = ctx->d_code_off.p + sg.pp_first + c.first; a.codes = ln.codes.p;
         a.rowbest = local ? ln.rowbest.p + (size_t)c.first * c.R * 32 : nullptr;
+        a.endcell = ctx->d_endcell.p;
         a.results = ctx->d_results.p; a.ops = want_ops ? ctx->d_ops.p : nullptr; a.ops_off = ctx->d_ops_off.p;
         a.n_pp = c.count; a.R = c.R;
         a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.bias = pl.bias;
@@ -625,6 +628,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
     CU(ctx->d_pps.reserve(n_pairs)); CU(ctx->d_code_off.reserve(n_pairs));
     CU(ctx->h_pps.reserve(n_pairs)); CU(ctx->h_code_off.reserve(n_pairs)); CU(ctx->h_ops_off.reserve(n_pairs + 1));
     CU(ctx->d_results.reserve(n_pairs));
+    if (local) CU(ctx->d_endcell.reserve(n_pairs));
     CU(ctx->d_alpha.reserve(ctx->alpha_slots)); CU(ctx->h_alpha.reserve(ctx->alpha_slots));
     if (want_ops) { CU(ctx->d_ops.reserve(ops_bound)); CU(ctx->d_ops_off.reserve(n_pairs + 1)); }
     CU(cudaMemsetAsync(ctx->d_alpha.p, 0, ctx->alpha_slots * sizeof(AlphaInfo), ctx->s_copy));
@@ -908,7 +912,7 @@ void b2a_destroy(b2a_ctx* ctx) {
     if (ctx->s_tb) cudaStreamDestroy(ctx->s_tb);
     ctx->d_pat.release(); ctx->d_txt.release(); ctx->d_pat_off.release(); ctx->d_txt_off.release();
     ctx->d_code_off.release(); ctx->d_ops_off.release(); ctx->d_pps.release();
-    ctx->d_ops.release(); ctx->d_alpha.release(); ctx->d_results.release();
+    ctx->d_ops.release(); ctx->d_alpha.release(); ctx->d_results.release(); ctx->d_endcell.release();
     ctx->h_pps.release(); ctx->h_code_off.release(); ctx->h_ops_off.release(); ctx->h_alpha.release();
     ctx->wide.release();
     for (auto& e : ctx->ev_pool) if (e) cudaEventDestroy(e);

@@ -16,7 +16,12 @@
 //   (active iff 1 <= j <= n, otherwise its H registers are frozen, which makes D = -gap, still in
 //   range).  A word holds F = WBITS/K steps, a 16-byte chunk holds NWORDS words + the anchor
 //   (= H after the chunk's last step) and covers CS = NWORDS*F steps.
-//   chunk index of (band, r, c, L) = ((band*R + r)*NC + c)*32 + L  -> a warp stores 512 contiguous bytes.
+//   wide32 : chunk index of (band, r, c, L) = ((band*R + r)*NC + c)*32 + L  -> a warp stores 512 contiguous bytes;
+//            the chunks of one row are 32 apart.
+//   short16: chunk index of (row i, c) = c*32R + (i-1) = (c*32 + L)*R + r: ROW-MAJOR inside a chunk column, so the
+//            chunks of consecutive DP rows are 16 bytes apart.  A traceback path climbs one row per step: with
+//            this order a 128-byte line holds 8 rows of it (an earlier r-major order put every row change into a
+//            different line: L1 hit rate 16-35 %, 2.5x the DRAM traffic).  The chunks of one row are 32R apart.
 //
 //   short16 family: two pairs of identical shape in the low/high 16-bit halves of every word
 //                   (WBITS = 16, NWORDS = 3, one band, R = ceil(m/32) <= 8, K in {2,4,8}).
@@ -180,9 +185,14 @@ B2A_HD uint32_t row_slot(const PairView& v, uint32_t i, uint32_t& L) {     // ba
     return x - L * (uint32_t)v.R;
 }
 template <class FM>
+B2A_HD uint32_t chunk_stride(const PairView& v) {                          // distance between consecutive chunks of one row
+    return FM::WBITS == 32 ? 32u : 32u * (uint32_t)v.R;
+}
+template <class FM>
 B2A_HD uint64_t chunk_index(const PairView& v, uint32_t i, uint32_t c, uint32_t& L) {
     const uint32_t slot = row_slot<FM>(v, i, L);
-    return ((uint64_t)slot * v.NC + c) * 32u + L;
+    if (FM::WBITS == 32) return ((uint64_t)slot * v.NC + c) * 32u + L;
+    return (uint64_t)c * (32u * (uint32_t)v.R) + (i - 1u);
 }
 B2A_HD int short16_rmagic(int R) { return (65536 + R - 1) / R; }
 
@@ -206,6 +216,7 @@ template <class FM> B2A_HD uint64_t chunk_string(const Chunk& ch, int half) {
     return ((uint64_t)((ch.w0 >> sh) & 0xFFFFu) << 32) | ((uint64_t)((ch.w1 >> sh) & 0xFFFFu) << 16) | ((ch.w2 >> sh) & 0xFFFFu);
 }
 
+// (chunks of a row are chunk_stride() apart)
 // A cursor on one DP row of the record: knows the exact H at its column and can step LEFT for the
 // price of one field extraction (H(i,j-1) = H(i,j) - D(i,j) - gap); a chunk is (re)loaded only when
 // the column crosses a chunk boundary.  Seeking (a new row) costs one chunk load + one popcount sum
@@ -226,7 +237,7 @@ struct RowCursor {
         const uint32_t q = j + L;
         c = (int)(q / (uint32_t)FM::CS);
         const int rem = (int)(q - (uint32_t)c * (uint32_t)FM::CS);
-        cidx = base + (uint64_t)c * 32u;
+        cidx = base + (uint64_t)c * chunk_stride<FM>(v);
         const Chunk ch = ld(cidx);
         X = chunk_string<FM>(ch, v.half);
         off = FM::K * (FM::CS - 1 - rem);
@@ -243,7 +254,7 @@ struct RowCursor {
         off += FM::K;
         if (off == BITS) {
             off = 0;
-            if (!border && c > 0) { --c; cidx -= 32u; X = chunk_string<FM>(ld(cidx), v.half); }
+            if (!border && c > 0) { --c; cidx -= chunk_stride<FM>(v); X = chunk_string<FM>(ld(cidx), v.half); }
             // c == 0: step q = 0, nothing further left is ever read
             else if (!border) off = BITS - FM::K;
         }
@@ -258,7 +269,7 @@ B2A_HD void prefetch_row(const PairView& v, const Loader& ld, uint32_t i, uint32
     if (i == 0) return;
     uint32_t L;
     const uint64_t base = chunk_index<FM>(v, i, 0, L);
-    ld.prefetch(base + (uint64_t)((j + L) / (uint32_t)FM::CS) * 32u);
+    ld.prefetch(base + (uint64_t)((j + L) / (uint32_t)FM::CS) * chunk_stride<FM>(v));
 }
 
 // ---- Needleman-Wunsch traceback, hw2.cpp:158-181 on reconstructed H; directions per hw2.cpp:145-153 ----
@@ -327,7 +338,7 @@ B2A_HD void find_local_end(const PairView& v, Loader ld, int& M, uint32_t& bi, u
     uint32_t q = L + 1u;
     while (q <= L + v.n && bj == 0) {
         const uint32_t c = q / (uint32_t)FM::CS;
-        const Chunk ch = ld(rowbase + (uint64_t)c * 32u);
+        const Chunk ch = ld(rowbase + (uint64_t)c * chunk_stride<FM>(v));
         uint32_t rem = q - c * (uint32_t)FM::CS;
         for (; rem < (uint32_t)FM::CS && q <= L + v.n; ++rem, ++q) {
             const int wi = (int)rem / FM::F, f = (int)rem - wi * FM::F;

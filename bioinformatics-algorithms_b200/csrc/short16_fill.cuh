@@ -12,7 +12,9 @@
 // and the FMA pipe one IMAD that folds the new H into the row's delta word (see b2a_format.h
 // encode_word: the word of horizontal deltas is a polynomial in the packed H values, evaluated in
 // 32-bit ring arithmetic, so no masking, shifting or compare instruction is spent on traceback data).
-// Every 3 words a lane stores one 16-byte chunk {w0,w1,w2,anchor}; a warp store is 512 contiguous bytes.
+// Every 3 words a lane stores one 16-byte chunk {w0,w1,w2,anchor} per row at chunk index (c*32 + lane)*R + r
+// (b2a_format.h: consecutive DP rows are 16 bytes apart, which is what the traceback wants); the R stores of a warp
+// fill 512R contiguous bytes between them.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -34,6 +36,7 @@ struct FillArgs {
     const uint64_t* code_off;   // per pair-pair: first chunk of its record
     Chunk*          codes;
     uint32_t*       rowbest;    // local mode: [n_pp][R][32]
+    int4*           endcell;    // local mode, per PAIR: {score, end_i, end_j, 0} = first row-major maximum (hw2.cpp:225-229)
     uint32_t        n_pp;
     uint32_t        tbl_cap;    // score-table entries (columns) per warp in dynamic shared memory
     int32_t         match, mismatch, gap, bias;
@@ -166,7 +169,7 @@ short16_fill_kernel(const FillArgs A)
                     if (wi == 0) w0[r] = w; else if (wi == 1) w1[r] = w;
                     else {
                         const uint4 v = make_uint4(w0[r], w1[r], w, H[r]);
-                        *reinterpret_cast<uint4*>(&rec[((uint32_t)r * NC + c) * 32u + lane]) = v;
+                        *reinterpret_cast<uint4*>(&rec[((size_t)c * 32u + lane) * R + r]) = v;
                     }
                 }
             }
@@ -185,7 +188,7 @@ short16_fill_kernel(const FillArgs A)
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const uint32_t w = (F > 1 ? S[r] * radm1 : 0u) + H[r] + pre[r];
-                    uint32_t* cw = reinterpret_cast<uint32_t*>(&rec[((uint32_t)r * NC + c) * 32u + lane]);
+                    uint32_t* cw = reinterpret_cast<uint32_t*>(&rec[((size_t)c * 32u + lane) * R + r]);
                     cw[wi] = w;
                     if (wi == 2) cw[3] = H[r];
                 }
@@ -195,6 +198,51 @@ short16_fill_kernel(const FillArgs A)
     if (LOCAL) {
 #pragma unroll
         for (int r = 0; r < R; ++r) A.rowbest[((size_t)pp * R + r) * 32u + lane] = best[r];
+        // ---- end cell of both pairs (hw2.cpp:202-203, :225-229: first strict maximum in row-major order), found by
+        // the warp while the record is still hot: per-row maxima -> first best row, then the row's chunks are rebuilt
+        // backwards from their anchors by the lanes in parallel.  ~2 % of the fill; the traceback kernel (one thread
+        // per pair) used to spend more than its whole walk on this search.
+        __syncwarp();                                            // the chunk stores above are visible to the whole warp
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            int mloc = 0; uint32_t iloc = 0xFFFFFFFFu;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int v = (int)((best[r] >> (16 * half)) & 0xFFFFu);
+                const uint32_t i = (uint32_t)lane * R + r + 1u;
+                if (i <= m && v > mloc) { mloc = v; iloc = i; }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const int om = __shfl_xor_sync(0xFFFFFFFFu, mloc, o);
+                const uint32_t oi = __shfl_xor_sync(0xFFFFFFFFu, iloc, o);
+                if (om > mloc || (om == mloc && oi < iloc)) { mloc = om; iloc = oi; }
+            }
+            uint32_t bi = 0, bj = 0;
+            if (mloc > 0) {
+                bi = iloc;
+                const uint32_t Lb = (bi - 1u) / R;
+                const Chunk* row = rec + (bi - 1u);                   // chunk c of DP row bi sits at c*32R + (bi-1)
+                const int floor_anchor = mloc + (CS - 1) * A.gap;     // H falls by at most |gap| per step to the right
+                uint32_t cand = 0xFFFFFFFFu;                          // smallest step q of the row with H == max
+                for (uint32_t c = (uint32_t)lane; c < NC; c += 32u) {
+                    const uint4 ch = __ldcg(reinterpret_cast<const uint4*>(row + (size_t)c * (32u * R)));
+                    const int sh = 16 * half;
+                    int Hq = (int)((ch.w >> sh) & 0xFFFFu);
+                    if (Hq < floor_anchor) continue;
+                    const uint64_t X = ((uint64_t)((ch.x >> sh) & 0xFFFFu) << 32) | ((uint64_t)((ch.y >> sh) & 0xFFFFu) << 16) | ((ch.z >> sh) & 0xFFFFu);
+                    for (int rem = CS - 1; rem >= 0; --rem) {
+                        const uint32_t q = c * CS + (uint32_t)rem;
+                        if (Hq == mloc && q - Lb - 1u < n) cand = min(cand, q);   // columns 1..n only (frozen steps outside repeat border values)
+                        Hq -= (int)((uint32_t)(X >> (K * (CS - 1 - rem))) & Geo<K>::MASK) + A.gap;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) cand = min(cand, __shfl_xor_sync(0xFFFFFFFFu, cand, o));
+                bj = cand - Lb;
+            }
+            if (lane == 0) A.endcell[half ? d.b : d.a] = make_int4(mloc, (int)bi, (int)bj, 0);
+        }
     }
 }
 

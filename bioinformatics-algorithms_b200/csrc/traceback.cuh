@@ -1,9 +1,21 @@
-// traceback.cuh -- one thread per pair walks the short16 record (b2a_format.h walkers).
+// traceback.cuh -- one thread per pair walks the short16 record.
 //
 // Replaces hw2.cpp:158-188 (NW) / hw2.cpp:235-263 (SW) and overlapLongestExactMatch (hw2.cpp:267-278)
-// for every pair of the batch.  The walk is a dependent chain of 16-byte chunk loads (one per row
-// change), so the kernel is latency/HBM bound; parallelism comes from the batch (one thread per pair,
-// the two halves of a pair-pair in adjacent threads so they share sectors).
+// for every pair of the batch.  The direction of a cell is decided by the reference's own comparisons
+// (hw2.cpp:145-153 NW, hw2.cpp:214-222 SW) on the exact H of the cell and its three neighbours, which the
+// delta record yields in O(1) per cell (one 16-byte chunk load + a popcount prefix sum from the anchor).
+//
+// Shaped for a WARP of 32 independent walks, where anything that is rare per thread happens almost every
+// iteration somewhere in the warp:
+//   * the general step is uniform and branch-free: both rows are re-sought every step (the chunk of the
+//     lower row was loaded as the upper row one step earlier, so it hits L1) instead of carrying cursors
+//     whose chunk-boundary reloads and row changes diverge;
+//   * NW starts with the run of 'l' moves along the last row (the text's tail beyond the pattern): every
+//     thread of the warp is in that phase at the same time and, for pairs of equal shape, crosses chunk
+//     boundaries in the same iteration, so it gets a tight loop on two register-resident field strings;
+//   * SW starts from the end cell the fill kernel's epilogue already found (FillArgs::endcell);
+//   * border tails are emitted in bulk.
+// The generic cursor walkers in b2a_format.h stay the executable specification (CPU host model, wide32 warp walker).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,6 +33,7 @@ struct TbArgs {
     const uint64_t* code_off;
     const Chunk*    codes;
     const uint32_t* rowbest;
+    const int4*     endcell;    // local mode, per pair: {score, end_i, end_j, 0} from the fill kernel
     PairResult*     results;    // indexed by pair
     uint32_t*       ops;        // packed 2-bit ops, may be null
     const uint64_t* ops_off;    // per pair word offset into ops
@@ -44,10 +57,50 @@ struct DevLoader {
 
 constexpr int TB_THREADS = 128;
 
+// one pair's view of its half of a pair-pair record
+template <int K>
+struct S16View {
+    using FM = Short16<K>;
+    const Chunk* rec;
+    uint32_t NC, R, rmagic, stride;    // stride = 32R: distance between consecutive chunks of a row
+    uint32_t sel_lo, sel_hi;     // PRMT selectors of this pair's 16-bit half
+    int gap;
+
+    // first chunk of DP row i >= 1 (its chunks are 32R apart) and the lane that owned the row in the fill
+    // (step q = j + L; no runtime division, see row_slot)
+    __device__ __forceinline__ const Chunk* row_base(uint32_t i, uint32_t& L) const {
+        const uint32_t x = i - 1u;
+        L = (x * rmagic) >> 16;
+        return rec + x;
+    }
+    // field string of a chunk (step rem at bit K*(CS-1-rem)) and its anchor
+    __device__ __forceinline__ uint64_t unpack(const uint4& ch, int& anchor) const {
+        const uint32_t lo = __byte_perm(ch.z, ch.y, sel_lo);              // (w1.half << 16) | w2.half
+        const uint32_t hi = __byte_perm(ch.x, 0u, sel_hi);                // w0.half
+        anchor = (int)__byte_perm(ch.w, 0u, sel_hi);
+        return ((uint64_t)hi << 32) | lo;
+    }
+    // (tried and lost, per 1 M pairs: prefetch.global.L1 of the rows above 6.2 -> 7.9 ms NW / 2.7 -> 6.2 ms SW;
+    //  ld.cg instead of ld.nc for the chunks 6.2 -> 7.2 ms NW; ld.cs 6.2 -> 8.9 ms)
+    // exact (biased) H of cell (i, j), i >= 1, and its horizontal delta D = H(i,j) - H(i,j-1) - gap
+    __device__ __forceinline__ void cell(uint32_t i, uint32_t j, int& H, int& D) const {
+        uint32_t L;
+        const Chunk* rb = row_base(i, L);
+        const uint32_t q = j + L, c = q / (uint32_t)FM::CS, rem = q - c * (uint32_t)FM::CS;
+        const uint4 ch = __ldg(reinterpret_cast<const uint4*>(rb + (size_t)c * stride));
+        int anchor;
+        const uint64_t X = unpack(ch, anchor);
+        const int off = K * (FM::CS - 1 - (int)rem);
+        D = (int)((uint32_t)(X >> off) & FM::MASK);
+        H = anchor - (FM::CS - 1 - (int)rem) * gap - field_sum64<K>(X & ((1ull << off) - 1ull));
+    }
+};
+
 template <int K, bool LOCAL>
 __global__ void __launch_bounds__(TB_THREADS)
 short16_traceback_kernel(const TbArgs A)
 {
+    using FM = Short16<K>;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t pp = t >> 1;
     const int half = (int)(t & 1u);
@@ -55,16 +108,95 @@ short16_traceback_kernel(const TbArgs A)
     const PPDesc d = A.pps[pp];
     if (half && d.b == d.a) return;                       // singleton: the high half is a duplicate
     const uint32_t pair = half ? d.b : d.a;
-    const Chunk* rec = A.codes + A.code_off[pp];
-    PairView v{rec, LOCAL ? A.rowbest + (size_t)pp * A.R * 32u : nullptr,
-               A.pat + A.pat_off[pair], A.txt + A.txt_off[pair],
-               d.m, d.n, num_chunks(d.n, Geo<K>::CS), A.R, half, A.match, A.mismatch, A.gap, A.bias, A.opt, short16_rmagic(A.R)};
-    OpsSink sink(A.ops ? A.ops + A.ops_off[pair] : nullptr);
+    const uint8_t* __restrict__ P = A.pat + A.pat_off[pair];
+    const uint8_t* __restrict__ T = A.txt + A.txt_off[pair];
+    const int gap = A.gap, match = A.match, mismatch = A.mismatch;
+    S16View<K> v{A.codes + A.code_off[pp], num_chunks(d.n, FM::CS), (uint32_t)A.R, (uint32_t)short16_rmagic(A.R), 32u * (uint32_t)A.R,
+                 half ? 0x7632u : 0x5410u, half ? 0x4432u : 0x4410u, gap};
+    uint32_t* out = A.ops ? A.ops + A.ops_off[pair] : nullptr;
+
+    uint32_t i, j, nops = 0, word = 0, fill = 0, wpos = 0;
+    int cur = 0, best = 0;
     PairResult res;
-    if (LOCAL) walk_local<Short16<K>>(v, DevLoader{rec}, sink, res);
-    else walk_global<Short16<K>>(v, DevLoader{rec}, sink, res);
-    sink.flush();
     res.path = 1;
+    auto put = [&](uint32_t op) {
+        word |= op << (2u * fill);
+        if (++fill == 16u) { if (out) out[wpos] = word; ++wpos; word = 0; fill = 0; }
+    };
+    auto put_run = [&](uint32_t op, uint32_t cnt) {
+        while (cnt) {
+            const uint32_t take = min(cnt, 16u - fill);
+            if (op) word |= ((op * 0x55555555u) & (take == 16u ? 0xFFFFFFFFu : ((1u << (2u * take)) - 1u))) << (2u * fill);
+            fill += take; cnt -= take;
+            if (fill == 16u) { if (out) out[wpos] = word; ++wpos; word = 0; fill = 0; }
+        }
+    };
+
+    if (LOCAL) {
+        const int4 e = A.endcell[pair];
+        res.score = e.x; res.end_i = (uint32_t)e.y; res.end_j = (uint32_t)e.z;
+        i = res.end_i; j = res.end_j;
+        if (e.x == 0) { i = 0; j = 0; }                   // hw2.cpp:202-203: best cell stays (0,0), empty alignment
+    } else {
+        i = d.m; j = d.n;
+        res.end_i = i; res.end_j = j;
+        int H, D;
+        v.cell(i, j, H, D);
+        res.score = H - A.bias;                           // hw2.cpp:186
+        // ---- phase A: the run of 'l' moves along the last row (hw2.cpp:146-153 on every cell of the run) ----
+        if (i >= 2u) {
+            uint32_t La, Lb;
+            const Chunk* ra = v.row_base(i, La);
+            const Chunk* rb = v.row_base(i - 1u, Lb);
+            uint32_t qa = j + La, qb = j + Lb;
+            uint32_t ca = qa / (uint32_t)FM::CS, cb = qb / (uint32_t)FM::CS;
+            int offa = K * (FM::CS - 1 - (int)(qa - ca * FM::CS)), offb = K * (FM::CS - 1 - (int)(qb - cb * FM::CS));
+            int anchor, Ha = H, Hb, Db;
+            uint64_t Xa = v.unpack(__ldg(reinterpret_cast<const uint4*>(ra + (size_t)ca * v.stride)), anchor);
+            v.cell(i - 1u, j, Hb, Db);
+            uint64_t Xb = v.unpack(__ldg(reinterpret_cast<const uint4*>(rb + (size_t)cb * v.stride)), anchor);
+            const uint8_t pc = P[i - 1u];
+            uint32_t run = 0;
+            while (j > 0u) {
+                const int Da = (int)((uint32_t)(Xa >> offa) & FM::MASK);
+                Db = (int)((uint32_t)(Xb >> offb) & FM::MASK);
+                const int Hl = Ha - Da - gap, Hd = Hb - Db - gap;
+                const int dv = Hd + (pc == T[j - 1u] ? match : mismatch);
+                if (!(Hl + gap > dv && !(Hb + gap > Hl + gap))) break;     // this cell is not 'l': the general walk takes over
+                Ha = Hl; Hb = Hd; --j; ++run;
+                offa += K; offb += K;
+                if (offa == FM::K * FM::CS) { offa = 0; if (ca) { --ca; Xa = v.unpack(__ldg(reinterpret_cast<const uint4*>(ra + (size_t)ca * v.stride)), anchor); } }
+                if (offb == FM::K * FM::CS) { offb = 0; if (cb) { --cb; Xb = v.unpack(__ldg(reinterpret_cast<const uint4*>(rb + (size_t)cb * v.stride)), anchor); } }
+            }
+            put_run(OP_I, run); nops += run;
+        }
+    }
+
+    // ---- phase B: the general walk, one uniform branch-free step per cell ----
+    while (i > 0u && j > 0u) {
+        int H, D, Hu, Du;
+        v.cell(i, j, H, D);
+        v.cell(i > 1u ? i - 1u : 1u, j, Hu, Du);
+        if (i == 1u) { Hu = LOCAL ? 0 : A.bias + (int)j * gap; Du = LOCAL ? -gap : 0; }     // border row, hw2.cpp:131-136 / :196-197
+        if (LOCAL && H == 0) break;                                                          // hw2.cpp:239
+        const int Hl = H - D - gap, Hd = Hu - Du - gap;
+        const uint8_t pc = P[i - 1u];
+        const bool eq = pc == T[j - 1u];
+        const int dv = Hd + (eq ? match : mismatch);                                         // hw2.cpp:142 / :208
+        uint32_t op;
+        if (LOCAL) op = H == dv ? OP_M : (H == Hu + gap ? OP_D : OP_I);                      // hw2.cpp:214-222 (H != 0 here)
+        else { op = OP_M; int val = dv; if (Hl + gap > val) { val = Hl + gap; op = OP_I; } if (Hu + gap > val) op = OP_D; }   // hw2.cpp:145-153
+        cur = (op == OP_M && eq && pc != (uint8_t)'-') ? cur + 1 : 0;                        // hw2.cpp:267-278
+        best = max(best, cur);
+        i -= op != OP_I; j -= op != OP_D;
+        put(op); ++nops;
+    }
+    if (!LOCAL) {
+        put_run(OP_D, i); nops += i; i = 0;                                                  // column 0 holds 'u' (hw2.cpp:128)
+        put_run(OP_I, j); nops += j; j = 0;                                                  // row 0 holds 'l'    (hw2.cpp:134)
+    }
+    if (fill && out) out[wpos] = word;
+    res.start_i = i; res.start_j = j; res.overlap = best; res.n_ops = nops;
     A.results[pair] = res;
 }
 

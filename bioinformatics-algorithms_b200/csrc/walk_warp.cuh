@@ -64,7 +64,7 @@ __device__ __forceinline__ void warp_prefetch_window(const PairView& v, const Lo
         const uint32_t pi = i - 32u - (uint32_t)lane, pj = j > 32u + (uint32_t)lane ? j - 32u - (uint32_t)lane : 1u;
         uint32_t L;
         const uint64_t base = chunk_index<FM>(v, pi, 0, L);
-        ld.prefetch(base + (uint64_t)((pj + L) / (uint32_t)FM::CS) * 32u);
+        ld.prefetch(base + (uint64_t)((pj + L) / (uint32_t)FM::CS) * chunk_stride<FM>(v));
     }
 }
 
@@ -154,7 +154,7 @@ __device__ __forceinline__ void warp_find_local_end(const PairView& v, const Loa
     const uint32_t c0 = (L + 1u) / (uint32_t)FM::CS, c1 = (L + v.n) / (uint32_t)FM::CS;   // chunks holding columns 1..n
     uint32_t cand = 0xFFFFFFFFu;                                    // smallest step q with H == M
     for (uint32_t c = c0 + (uint32_t)lane; c <= c1; c += 32u) {
-        const Chunk ch = ld(rowbase + (uint64_t)c * 32u);
+        const Chunk ch = ld(rowbase + (uint64_t)c * chunk_stride<FM>(v));
         const uint64_t X = chunk_string<FM>(ch, v.half);
         int H = anchor_of<FM>(ch, v.half);
         for (int rem = FM::CS - 1; rem >= 0; --rem) {

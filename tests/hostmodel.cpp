@@ -85,7 +85,7 @@ int encode(int mode, const uint8_t* pa, const uint8_t* pb, uint32_t m, const uin
                     }
                     if (direct != w[wi]) return -4;
                 }
-                codes[((uint32_t)r * NC + c) * 32u + L] = Chunk{w[0], w[1], w[2], P((int64_t)c * CS + CS - 1)};
+                codes[((size_t)c * 32u + L) * (uint32_t)R + (uint32_t)r] = Chunk{w[0], w[1], w[2], P((int64_t)c * CS + CS - 1)};   // short16: row-major inside a chunk column
             }
         }
     return 0;

@@ -145,11 +145,11 @@ def test_fill_record_matches_host_model_bit_for_bit(eng):
             nn = lib.b2a_debug_copy_record(eng.ctx, got.ctypes.data, got.nbytes, got_rb.ctypes.data, got_rb.nbytes)
             assert nn == got.nbytes
             # rows beyond m are junk (model uses the smallest symbol like the kernel's code 0); compare real lanes' rows
-            g4, w4 = got.reshape(R, -1, 32, 4), want.reshape(R, -1, 32, 4)
+            g4, w4 = got.reshape(-1, 32, R, 4), want.reshape(-1, 32, R, 4)      # [chunk column][lane][row of the lane][word]
             for L in range(32):
                 for r in range(R):
                     if L * R + r < m:
-                        assert np.array_equal(g4[r, :, L, :], w4[r, :, L, :]), (mode, m, n, s, L, r)
+                        assert np.array_equal(g4[:, L, r, :], w4[:, L, r, :]), (mode, m, n, s, L, r)
             if mode == pkg.LOCAL:
                 grb, wrb = got_rb.reshape(R, 32), want_rb.reshape(R, 32)
                 for L in range(32):
