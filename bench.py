@@ -248,8 +248,17 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture, scaled per pair to this launch
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_fill_traffic.json")))
+            per_pair = sum(tr[m]["dram_read_bytes"] + tr[m]["dram_write_bytes"] for m in ("global", "local")) / 2.0 / tr["pairs_per_launch"]
+            traffic, traffic_src = per_pair * n_pairs, tr["source"]
+        except Exception:
+            pass
         roofline = {"bound": "int_alu", "achieved": achieved, "peak": peak_cellops, "unit": "G int16-cell-ops/s",
-                    "frac": achieved / peak_cellops, "traffic": None,
+                    "frac": achieved / peak_cellops, "traffic": traffic, "traffic_unit": "DRAM bytes per fill launch (mean of NW and SW)",
+                    "traffic_source": traffic_src, "algorithmic_bytes_per_launch": fill_bytes,
                     "peak_source": "b2a_microbench_int16x2 kind 0 (VIADDMNMX.S16x2, 8-way ILP, all SMs) measured in this run, x2 cells/lane",
                     "alu_mix_gops": mix_gops, "alu_mix_plus_imad_gops": mix2_gops,
                     "ops_per_cell": {"global": 5, "local": 6},
