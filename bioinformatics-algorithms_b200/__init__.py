@@ -17,9 +17,11 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb2align.so")
 HW2_BIN = os.path.join(HERE, "bin", "hw2")
+HW4_BIN = os.path.join(HERE, "bin", "hw4")
 
 GLOBAL, LOCAL = 0, 1
 SCORE_ONLY = 2
+TIE_HW4 = 4
 OPT_LANES, OPT_SEG_PAIRS, OPT_SEG_BYTES, OPT_TB, OPT_SEG_FIRST = 1, 2, 3, 4, 5
 WANT_OPS = 1
 
@@ -29,6 +31,7 @@ RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<u4"), ("end_j", "<u4"), (
 EXPORTS = ["b2a_device_count", "b2a_create", "b2a_destroy", "b2a_last_error", "b2a_host_alloc", "b2a_host_free",
            "b2a_align_batch", "b2a_affine_score_batch", "b2a_affine_star_scores", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
            "b2a_batch_download", "b2a_batch_times", "b2a_set_option", "b2a_batch_stats", "b2a_render_cigar", "b2a_render_mdz", "b2a_select_best",
+           "b2a_upgma_newick",
            "b2a_microbench_int16x2", "b2a_debug_copy_record"]
 
 
@@ -77,6 +80,8 @@ def load_library():
         lib.b2a_render_mdz.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, P, C.c_uint64]
         lib.b2a_select_best.restype = C.c_int64
         lib.b2a_select_best.argtypes = [C.c_int32, P, C.c_uint64]
+        lib.b2a_upgma_newick.restype = C.c_int64
+        lib.b2a_upgma_newick.argtypes = [P, C.c_uint32, P, P, C.c_uint64]
         lib.b2a_microbench_int16x2.argtypes = [P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
         lib.b2a_affine_score_batch.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, P, P, P, C.c_uint64, P]
         lib.b2a_affine_star_scores.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, P, C.c_uint32,
@@ -188,21 +193,21 @@ class Engine:
 
     # -- the batch call that replaces hw2.cpp:328-338 --
     def align_packed(self, mode, pat, pat_off, txt, txt_off, match, mismatch, gap, want_ops=False, results=None,
-                     score_only=False):
+                     score_only=False, tie_hw4=False):
         n = len(pat_off) - 1
         if results is None:
             results = np.empty(n, dtype=RESULT_DTYPE)
-        prm = Params(mode, match, mismatch, gap, (WANT_OPS if want_ops else 0) | (SCORE_ONLY if score_only else 0))
+        prm = Params(mode, match, mismatch, gap, (WANT_OPS if want_ops else 0) | (SCORE_ONLY if score_only else 0) | (TIE_HW4 if tie_hw4 else 0))
         self._check(self.lib.b2a_align_batch(self.ctx, C.byref(prm), pat.ctypes.data, pat_off.ctypes.data,
                                              txt.ctypes.data, txt_off.ctypes.data, n, results.ctypes.data), "b2a_align_batch")
         return results
 
-    def align_batch(self, mode, patterns, texts, match, mismatch, gap, want_ops=True):
+    def align_batch(self, mode, patterns, texts, match, mismatch, gap, want_ops=True, tie_hw4=False):
         """lists of bytes -> (results recarray, list of op byte-strings in traceback order or None)."""
         assert len(patterns) == len(texts)
         pat, po = pack(patterns)
         txt, to = pack(texts)
-        res = self.align_packed(mode, pat, po, txt, to, match, mismatch, gap, want_ops)
+        res = self.align_packed(mode, pat, po, txt, to, match, mismatch, gap, want_ops, tie_hw4=tie_hw4)
         ops = None
         if want_ops:
             words, off = self.copy_ops(len(patterns))
@@ -300,6 +305,20 @@ class Engine:
 
     def localAlignmentSmithWaterman(self, patterns, references, matchScore, mismatchScore, gapPenalty):
         return self._one(LOCAL, patterns, references, matchScore, mismatchScore, gapPenalty)
+
+
+def upgma_newick(pair_dist, names):
+    """hw4's tree line (without the newline) from the i < j row-major pair distances (hw4.cpp:154-228)."""
+    lib = load_library()
+    d = np.ascontiguousarray(pair_dist, dtype=np.int32)
+    n = len(names)
+    arr = (C.c_char_p * max(n, 1))(*[x if isinstance(x, bytes) else x.encode() for x in names])
+    cap = 64 + sum(len(x) + 64 for x in names)
+    buf = C.create_string_buffer(cap)
+    k = lib.b2a_upgma_newick(d.ctypes.data, n, arr, buf, cap)
+    if k < 0:
+        raise B2AError("b2a_upgma_newick failed")
+    return buf.raw[:k].decode("latin-1")
 
 
 def select_best(mode, results):

@@ -213,18 +213,9 @@ void alpha_from_mask(AlphaInfo& a) {
 
 template <int R, int K>
 cudaError_t launch_fill_rk(bool local, const FillArgs& a, cudaStream_t st) {
-    const size_t smem = (size_t)FILL_WARPS * a.tbl_cap * sizeof(uint2);
     const unsigned grid = (a.n_pp + FILL_WARPS - 1) / FILL_WARPS;
-    cudaError_t e;
-    if (local) {
-        e = cudaFuncSetAttribute(short16_fill_kernel<R, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        short16_fill_kernel<R, K, true><<<grid, FILL_WARPS * 32, smem, st>>>(a);
-    } else {
-        e = cudaFuncSetAttribute(short16_fill_kernel<R, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        short16_fill_kernel<R, K, false><<<grid, FILL_WARPS * 32, smem, st>>>(a);
-    }
+    if (local) short16_fill_kernel<R, K, true><<<grid, FILL_WARPS * 32, 0, st>>>(a);
+    else short16_fill_kernel<R, K, false><<<grid, FILL_WARPS * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
 template <int K>
@@ -398,7 +389,7 @@ int wide_traceback(b2a_ctx* ctx, cudaStream_t st, uint64_t* launches, bool score
     a.ops = (prm.flags & B2A_WANT_OPS) && !score_only ? ctx->d_ops.p : nullptr;
     a.ops_off = ctx->d_ops_off.p;
     a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.score_only = score_only ? 1 : 0;
-    a.opt = ctx->tb_opt;
+    a.opt = (ctx->tb_opt & ~4) | ((prm.flags & B2A_TIE_HW4) ? 4 : 0);
     CU(launch_wide_tb(W.K, prm.mode == B2A_MODE_LOCAL, a, st));
     ++*launches;
     return B2A_OK;
@@ -444,7 +435,7 @@ int launch_segment(b2a_ctx* ctx, size_t si, uint64_t* launches)
         a.pps = ctx->d_pps.p + sg.pp_first + c.first; a.code_off = ctx->d_code_off.p + sg.pp_first + c.first; a.codes = ln.codes.p;
         a.rowbest = local ? ln.rowbest.p + (size_t)c.first * c.R * 32 : nullptr;
         a.endcell = ctx->d_endcell.p;
-        a.n_pp = c.count; a.tbl_cap = (c.max_n + 3u) & ~3u;
+        a.n_pp = c.count;
         a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.bias = pl.bias;
         a.radix = 1u << ctx->K;
         a.alpha = alpha;
@@ -466,6 +457,7 @@ int launch_segment(b2a_ctx* ctx, size_t si, uint64_t* launches)
         a.n_pp = c.count; a.R = c.R;
         a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.bias = pl.bias;
         a.opt = ctx->tb_opt;
+        a.tie_hw4 = (prm.flags & B2A_TIE_HW4) ? 1 : 0;
         a.alpha = alpha;
         CU(launch_tb(ctx->K, local, a, st));
         ++*launches;
@@ -601,6 +593,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
         return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: null argument or bad mode");
     if (n_pairs > 0x7FFFFFF0ull) return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: too many pairs");
     if (pipelined && !results && n_pairs) return fail(ctx, B2A_ERR_ARG, "b2a_align_batch: null results");
+    if ((prm->flags & B2A_TIE_HW4) && prm->mode != B2A_MODE_GLOBAL) return fail(ctx, B2A_ERR_ARG, "B2A_TIE_HW4 applies to the global mode only");
     CU(cudaSetDevice(ctx->device));
     // a previous batch may still own the pinned plan arrays / device buffers
     CU(cudaStreamSynchronize(ctx->s_copy)); CU(cudaStreamSynchronize(ctx->s_down));

@@ -98,7 +98,7 @@ B2A_HD int delta_bits_wide(int match, int mismatch, int gap) {
 struct Short16Plan { int K, R, bias; };
 constexpr int SHORT16_MAX_R = 8;          // rows per lane -> patterns up to 256 bases
 B2A_HD bool short16_plan(int mode, uint32_t m, uint32_t n, int match, int mismatch, int gap, Short16Plan& pl) {
-    if (m == 0 || n == 0 || m > 32u * SHORT16_MAX_R || n > 6000u) return false;
+    if (m == 0 || n == 0 || m > 32u * SHORT16_MAX_R || n > 30000u) return false;     // (the int16 range test below is the real limit on n)
     pl.K = delta_bits(match, mismatch, gap);
     if (pl.K == 0) return false;
     if (match > 127 || match < -128 || mismatch > 127 || mismatch < -128) return false;   // PRMT score tables are int8
@@ -140,7 +140,7 @@ struct PairView {
     uint32_t m, n, NC;
     int R, half;               // half: short16 only, 0 = low 16 bits, 1 = high
     int match, mismatch, gap, bias;
-    int opt;                   // walker tuning bits: 1 = batch runs of 'l' moves, 2 = L2-prefetch rows ahead
+    int opt;                   // walker bits: 1 = batch runs of 'l' moves, 2 = L2-prefetch rows ahead, 4 = hw4 tie order d > u > l
     int rmagic;                // short16: ceil(65536 / R)
 };
 
@@ -290,9 +290,14 @@ B2A_HD void walk_global(const PairView& v, Loader ld, Sink& sink, PairResult& re
         const bool eq = pc == v.t[j - 1];
         int val = Hd + (eq ? v.match : v.mismatch);                  // hw2.cpp:142
         uint32_t op = OP_M;                                          // hw2.cpp:145
-        if (Hl + v.gap > val) { val = Hl + v.gap; op = OP_I; }       // hw2.cpp:146-149 'l'
-        if (Hu + v.gap > val) { op = OP_D; }                         // hw2.cpp:150-153 'u'
-        if (op == OP_I && (v.opt & 1)) {
+        if (v.opt & 4) {                                             // hw4's order d > u > l (hw4.cpp:37-46)
+            if (Hu + v.gap > val) { val = Hu + v.gap; op = OP_D; }
+            if (Hl + v.gap > val) { op = OP_I; }
+        } else {
+            if (Hl + v.gap > val) { val = Hl + v.gap; op = OP_I; }   // hw2.cpp:146-149 'l'
+            if (Hu + v.gap > val) { op = OP_D; }                     // hw2.cpp:150-153 'u'
+        }
+        if (op == OP_I && (v.opt & 1) && !(v.opt & 4)) {
             // a run of 'l' moves stays inside the two chunks in registers: no memory traffic until a chunk edge
             cur = 0;
             for (;;) {

@@ -3,6 +3,7 @@
 // Works on the op list in traceback order plus the raw sequences; no aligned strings are built.
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <string>
 
 #include "../../include/b2align.h"
@@ -69,3 +70,59 @@ int64_t b2a_select_best(int32_t mode, const b2a_result* results, uint64_t n_pair
 }
 
 } // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// hw4's tree stage (hw4/hw4.cpp:154-228): UPGMA over the pair distances, Newick text.
+// Bit-exact contract with the reference: the same double arithmetic in the same order
+// (size-weighted average (d_a * size_a + d_b * size_b) / (size_a + size_b), height = d_min / 2), the
+// first strict minimum in row-major order over the CURRENT cluster order, the merged cluster appended
+// behind the survivors, branch lengths printed with std::to_string (6 decimals).
+// Kept as an index list over one full matrix instead of rebuilding matrices per merge.
+// ---------------------------------------------------------------------------------------------
+#include <cmath>
+#include <limits>
+#include <vector>
+
+extern "C" int64_t b2a_upgma_newick(const int32_t* pair_dist, uint32_t n_seqs, const char* const* names, char* out, uint64_t cap)
+{
+    if (!out || cap == 0 || (n_seqs && !names) || (n_seqs > 1 && !pair_dist)) return B2A_ERR_ARG;
+    if (n_seqs == 0) return B2A_ERR_ARG;                       // the reference indexes clusters[0] unconditionally
+    const size_t total = 2 * (size_t)n_seqs - 1;               // leaves + internal nodes
+    std::vector<double> D(total * total, 0.0);                 // distance between any two nodes ever alive
+    std::vector<int> size(total, 1);
+    std::vector<double> height(total, 0.0);
+    std::vector<std::string> label(total);
+    std::vector<size_t> alive;                                 // current cluster order (hw4.cpp:198-206)
+    for (uint32_t i = 0; i < n_seqs; ++i) { label[i] = names[i] ? names[i] : ""; alive.push_back(i); }
+    size_t p = 0;
+    for (uint32_t i = 0; i < n_seqs; ++i)
+        for (uint32_t j = i + 1; j < n_seqs; ++j, ++p) D[i * total + j] = D[j * total + i] = (double)pair_dist[p];
+    size_t next = n_seqs;
+    while (alive.size() > 1) {
+        double dmin = std::numeric_limits<double>::infinity();
+        size_t ai = 0, aj = 0;
+        for (size_t x = 0; x < alive.size(); ++x)              // hw4.cpp:167-175: first strict minimum, row-major
+            for (size_t y = x + 1; y < alive.size(); ++y) {
+                const double d = D[alive[x] * total + alive[y]];
+                if (d < dmin) { dmin = d; ai = x; aj = y; }
+            }
+        const size_t a = alive[ai], b = alive[aj], c = next++;
+        size[c] = size[a] + size[b];
+        height[c] = dmin / 2.0;
+        label[c] = "(" + label[a] + ":" + std::to_string(std::fabs(height[c] - height[a])) + "," +
+                   label[b] + ":" + std::to_string(std::fabs(height[c] - height[b])) + ")";
+        std::vector<size_t> keep;
+        for (size_t x = 0; x < alive.size(); ++x) if (x != ai && x != aj) keep.push_back(alive[x]);
+        for (size_t k : keep) {                                // hw4.cpp:222: distance of the merged cluster to every survivor
+            const double d = (D[a * total + k] * size[a] + D[b * total + k] * size[b]) / size[c];
+            D[c * total + k] = D[k * total + c] = d;
+        }
+        keep.push_back(c);
+        alive.swap(keep);
+    }
+    const std::string tree = label[alive[0]] + ":0.0;";
+    if (tree.size() + 1 > cap) return B2A_ERR_ARG;
+    std::memcpy(out, tree.data(), tree.size());
+    out[tree.size()] = 0;
+    return (int64_t)tree.size();
+}

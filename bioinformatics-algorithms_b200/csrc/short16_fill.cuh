@@ -38,7 +38,6 @@ struct FillArgs {
     uint32_t*       rowbest;    // local mode: [n_pp][R][32]
     int4*           endcell;    // local mode, per PAIR: {score, end_i, end_j, 0} = first row-major maximum (hw2.cpp:225-229)
     uint32_t        n_pp;
-    uint32_t        tbl_cap;    // score-table entries (columns) per warp in dynamic shared memory
     int32_t         match, mismatch, gap, bias;
     uint32_t        radix;      // 2^K, passed at run time so the word update stays an IMAD (FMA pipe)
     const AlphaInfo* alpha;     // device-resident: the (<= 4) distinct pattern symbols of this sub-batch
@@ -52,13 +51,20 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xFFFFu) | ((uint32_t)v << 16); }
 
 constexpr int FILL_WARPS = 4;
+#ifndef FILL_MIN_CTAS
+#define FILL_MIN_CTAS 6          // measured (1 M pairs): 6 / 7 / 8 CTAs per SM (80 / 72 / 64 registers) give NW 21.4 / 21.6 / 21.3 ms and
+                                 // SW 25.5 / 26.6 / 26.6 ms -- the kernel waits on the DPX pipe, not on occupancy
+#endif
 
 template <int R, int K, bool LOCAL>
-__global__ void __launch_bounds__(FILL_WARPS * 32)
+__global__ void __launch_bounds__(FILL_WARPS * 32, (R <= 5 ? FILL_MIN_CTAS : 1))
 short16_fill_kernel(const FillArgs A)
 {
     constexpr int F = Geo<K>::F, CS = Geo<K>::CS;
-    extern __shared__ uint2 s_tbl_all[];                 // [FILL_WARPS][tbl_cap]: per column (tableA, tableB)
+    // Per warp a MIRRORED ring of the last 128 text columns' score tables (tableA, tableB): entry x lives in slots
+    // x & 127 and (x & 127) + 128, so a chunk reads CS consecutive slots from one base with immediate offsets and never
+    // wraps.  (The first version kept the whole text's tables, 8 KB per warp: shared memory capped the SM at 24 warps.)
+    __shared__ uint2 s_ring[FILL_WARPS][256];
     __shared__ uint32_t s_tbl4[256];                     // byte -> 4 int8 scores against sym[0..3]
 
     if (A.alpha->too_many) return;                       // uniform: the whole grid leaves
@@ -80,7 +86,7 @@ short16_fill_kernel(const FillArgs A)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t pp = blockIdx.x * FILL_WARPS + warp;
     if (pp >= A.n_pp) return;
-    uint2* tbl = s_tbl_all + (size_t)warp * A.tbl_cap;
+    uint2* ring = s_ring[warp];
 
     const PPDesc d = A.pps[pp];
     const uint32_t m = d.m, n = d.n;
@@ -89,7 +95,18 @@ short16_fill_kernel(const FillArgs A)
     const uint8_t* ta = A.txt + A.txt_off[d.a];
     const uint8_t* tb = A.txt + A.txt_off[d.b];
 
-    for (uint32_t j = lane; j < n; j += 32) tbl[j] = make_uint2(s_tbl4[ta[j]], s_tbl4[tb[j]]);
+    uint32_t staged = 0;                                  // text indices [0, staged) have been staged (multiple of 32)
+    uint32_t nxa = (uint32_t)lane < n ? ta[lane] : 0u, nxb = (uint32_t)lane < n ? tb[lane] : 0u;   // bytes of the next block, one block ahead
+    auto stage_block = [&]() {
+        const uint32_t slot = (staged + (uint32_t)lane) & 127u;
+        const uint2 e = make_uint2(s_tbl4[nxa], s_tbl4[nxb]);
+        __syncwarp();
+        ring[slot] = e; ring[slot + 128u] = e;
+        __syncwarp();
+        staged += 32u;
+        const uint32_t x = staged + (uint32_t)lane;
+        nxa = x < n ? ta[x] : 0u; nxb = x < n ? tb[x] : 0u;
+    };
 
     // PRMT selectors of this lane's rows: byte0 = tableA[codeA], byte1 = its sign, byte2 = tableB[codeB], byte3 = its sign
     uint32_t sel[R], H[R], best[R];
@@ -122,16 +139,15 @@ short16_fill_kernel(const FillArgs A)
     const uint32_t bias32 = LOCAL ? 0u : (uint32_t)A.bias * 65537u;     // row-0 border b0(q) = bias32 + q*g32 (ring-exact)
 
     uint32_t dgn = LOCAL ? 0u : (lane == 0 ? bias32 : pack2(A.bias + (int)((uint32_t)lane * R) * A.gap));   // H(L*R, 0)
-    const uint2* tcol = tbl - lane - 1;                   // tcol[q] = tables of column j = q - lane (index j-1)
 
     // one wavefront step for this lane; ACTIVE_CHECK selects the ramp (predicated) flavour
-    auto step = [&](uint32_t q, uint32_t (&S)[R], int f, bool active) {
+    auto step = [&](const uint2* tcol, int k, uint32_t q, uint32_t (&S)[R], int f, bool active) {
         uint32_t up = __shfl_up_sync(0xFFFFFFFFu, H[R - 1], 1);
         if (lane == 0) up = LOCAL ? 0u : bias32 + q * g32;              // row 0 border H(0, q), hw2.cpp:131-136
         const uint32_t dg0 = dgn;
         dgn = up;
         if (active) {
-            const uint2 tw = tcol[q];
+            const uint2 tw = tcol[k];                                   // tables of column j = q - lane (text index j - 1)
             uint32_t dg = dg0, u = up;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -153,6 +169,8 @@ short16_fill_kernel(const FillArgs A)
 
     for (uint32_t c = 0; c < NC; ++c) {
         const uint32_t q0 = c * CS;
+        while (staged < q0 + CS) stage_block();                        // steps q0 .. q0+CS-1 read text indices q0-32 .. q0+CS-2
+        const uint2* tcol = ring + ((q0 - (uint32_t)lane - 1u) & 127u);  // tcol[k] = entry of text index q0 + k - lane - 1
         uint32_t w0[R], w1[R];
         if (q0 >= 32u && q0 + CS - 1 <= n) {
             // steady state: every lane is inside its row range for the whole chunk
@@ -162,7 +180,7 @@ short16_fill_kernel(const FillArgs A)
 #pragma unroll
                 for (int r = 0; r < R; ++r) pre[r] = H[r] * negBpow + negGc;
 #pragma unroll
-                for (int f = 0; f < F; ++f) step(q0 + wi * F + f, S, f, true);
+                for (int f = 0; f < F; ++f) step(tcol, wi * F + f, q0 + wi * F + f, S, f, true);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const uint32_t w = (F > 1 ? S[r] * radm1 : 0u) + H[r] + pre[r];
@@ -183,7 +201,7 @@ short16_fill_kernel(const FillArgs A)
 #pragma unroll
                 for (int f = 0; f < F; ++f) {
                     const uint32_t q = q0 + wi * F + f;
-                    step(q, S, f, (uint32_t)(q - lane - 1u) < n);
+                    step(tcol, wi * F + f, q, S, f, (uint32_t)(q - lane - 1u) < n);
                 }
 #pragma unroll
                 for (int r = 0; r < R; ++r) {

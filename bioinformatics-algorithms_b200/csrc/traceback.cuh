@@ -41,6 +41,7 @@ struct TbArgs {
     int32_t         R;
     int32_t         match, mismatch, gap, bias;
     int32_t         opt;
+    int32_t         tie_hw4;    // global mode: tie order d > u > l (hw4.cpp:37-46) and overlap := hw4's distance
     const AlphaInfo* alpha;
 };
 
@@ -117,6 +118,8 @@ short16_traceback_kernel(const TbArgs A)
 
     uint32_t i, j, nops = 0, word = 0, fill = 0, wpos = 0;
     int cur = 0, best = 0;
+    const bool hw4 = !LOCAL && A.tie_hw4 != 0;
+    uint32_t mism = 0;                                    // hw4: 'M' columns whose bases differ
     PairResult res;
     res.path = 1;
     auto put = [&](uint32_t op) {
@@ -162,7 +165,9 @@ short16_traceback_kernel(const TbArgs A)
                 Db = (int)((uint32_t)(Xb >> offb) & FM::MASK);
                 const int Hl = Ha - Da - gap, Hd = Hb - Db - gap;
                 const int dv = Hd + (pc == T[j - 1u] ? match : mismatch);
-                if (!(Hl + gap > dv && !(Hb + gap > Hl + gap))) break;     // this cell is not 'l': the general walk takes over
+                // 'l' wins iff it beats the diagonal strictly and 'u' does not beat it (hw2) / it beats 'u' strictly too (hw4)
+                const bool is_l = hw4 ? (Hl + gap > dv && Hl + gap > Hb + gap) : (Hl + gap > dv && !(Hb + gap > Hl + gap));
+                if (!is_l) break;                                          // the general walk takes over
                 Ha = Hl; Hb = Hd; --j; ++run;
                 offa += K; offb += K;
                 if (offa == FM::K * FM::CS) { offa = 0; if (ca) { --ca; Xa = v.unpack(__ldg(reinterpret_cast<const uint4*>(ra + (size_t)ca * v.stride)), anchor); } }
@@ -185,7 +190,9 @@ short16_traceback_kernel(const TbArgs A)
         const int dv = Hd + (eq ? match : mismatch);                                         // hw2.cpp:142 / :208
         uint32_t op;
         if (LOCAL) op = H == dv ? OP_M : (H == Hu + gap ? OP_D : OP_I);                      // hw2.cpp:214-222 (H != 0 here)
-        else { op = OP_M; int val = dv; if (Hl + gap > val) { val = Hl + gap; op = OP_I; } if (Hu + gap > val) op = OP_D; }   // hw2.cpp:145-153
+        else if (!hw4) { op = OP_M; int val = dv; if (Hl + gap > val) { val = Hl + gap; op = OP_I; } if (Hu + gap > val) op = OP_D; }   // hw2.cpp:145-153
+        else { op = OP_M; int val = dv; if (Hu + gap > val) { val = Hu + gap; op = OP_D; } if (Hl + gap > val) op = OP_I; }            // hw4.cpp:37-46
+        mism += (op == OP_M && !eq);
         cur = (op == OP_M && eq && pc != (uint8_t)'-') ? cur + 1 : 0;                        // hw2.cpp:267-278
         best = max(best, cur);
         i -= op != OP_I; j -= op != OP_D;
@@ -196,7 +203,8 @@ short16_traceback_kernel(const TbArgs A)
         put_run(OP_I, j); nops += j; j = 0;                                                  // row 0 holds 'l'    (hw2.cpp:134)
     }
     if (fill && out) out[wpos] = word;
-    res.start_i = i; res.start_j = j; res.overlap = best; res.n_ops = nops;
+    res.start_i = i; res.start_j = j; res.n_ops = nops;
+    res.overlap = hw4 ? (int)(nops - (d.m + d.n - nops) + mism) : best;      // gap columns = n_ops - M columns, M columns = m + n - n_ops
     A.results[pair] = res;
 }
 

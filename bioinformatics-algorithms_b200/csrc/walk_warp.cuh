@@ -71,15 +71,16 @@ __device__ __forceinline__ void warp_prefetch_window(const PairView& v, const Lo
 // Walks from (i, j) until the reference's loop would stop; returns the stop cell in (i, j).
 template <class FM, class Loader, bool LOCAL>
 __device__ __forceinline__ void warp_walk(const PairView& v, const Loader& ld, WarpOpsSink& sink, uint32_t& i, uint32_t& j,
-                                           uint32_t& nops, int& best)
+                                           uint32_t& nops, int& best, uint32_t& mism)
 {
     const int lane = (int)(threadIdx.x & 31u);
+    const bool hw4 = !LOCAL && (v.opt & 4) != 0;            // tie order d > u > l (hw4.cpp:37-46) instead of hw2's d > l > u
     int cur = 0, hyp = HYP_DIAG;
     uint32_t last_op = OP_M;
     while (i > 0 && j > 0) {
         const uint32_t di = hyp == HYP_LEFT ? 0u : (uint32_t)lane, dj = hyp == HYP_UP ? 0u : (uint32_t)lane;
         const bool valid = i > di && j > dj;                       // the hypothesised cell is inside the matrix
-        uint32_t op = OP_M; bool stop = false, exact = false;
+        uint32_t op = OP_M; bool stop = false, exact = false, differ = false;
         if (valid) {
             const uint32_t ci = i - di, cj = j - dj;
             RowCursor<FM, Loader, LOCAL> rc, ru;
@@ -93,12 +94,17 @@ __device__ __forceinline__ void warp_walk(const PairView& v, const Loader& ld, W
             if (LOCAL) {                                            // hw2.cpp:239, :214-222
                 stop = H == 0;
                 op = H == dv ? OP_M : (H == Hu + v.gap ? OP_D : OP_I);
-            } else {                                                // hw2.cpp:142-153: d, then l if strictly larger, then u if strictly larger
+            } else if (!hw4) {                                      // hw2.cpp:142-153: d, then l if strictly larger, then u if strictly larger
                 int val = dv;
                 if (Hl + v.gap > val) { val = Hl + v.gap; op = OP_I; }
                 if (Hu + v.gap > val) op = OP_D;
+            } else {                                                // hw4.cpp:37-46: d, then u if strictly larger, then l if strictly larger
+                int val = dv;
+                if (Hu + v.gap > val) { val = Hu + v.gap; op = OP_D; }
+                if (Hl + v.gap > val) op = OP_I;
             }
             exact = eq && pc != (uint8_t)'-';
+            differ = !eq;
         }
         if (hyp == HYP_DIAG) warp_prefetch_window<FM, Loader, LOCAL>(v, ld, i, j, lane);
         const uint32_t want = hyp == HYP_DIAG ? OP_M : (hyp == HYP_UP ? OP_D : OP_I);
@@ -106,7 +112,11 @@ __device__ __forceinline__ void warp_walk(const PairView& v, const Loader& ld, W
         const uint32_t t = ok == 0xFFFFFFFFu ? 32u : (uint32_t)(__ffs(~ok) - 1);     // leading lanes confirming the hypothesis
         if (t) {
             sink.put_run(want, t); nops += t;
-            if (want == OP_M) { overlap_run(__ballot_sync(0xFFFFFFFFu, exact), t, cur, best); i -= t; j -= t; }
+            if (want == OP_M) {
+                overlap_run(__ballot_sync(0xFFFFFFFFu, exact), t, cur, best);
+                mism += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, differ) & (t >= 32u ? 0xFFFFFFFFu : ((1u << t) - 1u)));
+                i -= t; j -= t;
+            }
             else { cur = 0; if (want == OP_D) i -= t; else j -= t; }
             last_op = want;
         }
@@ -118,8 +128,9 @@ __device__ __forceinline__ void warp_walk(const PairView& v, const Loader& ld, W
         if (s_t) break;                                             // local: H == 0
         const uint32_t op_t = __shfl_sync(0xFFFFFFFFu, op, (int)t);
         const uint32_t ex_t = __shfl_sync(0xFFFFFFFFu, (uint32_t)exact, (int)t);
+        const uint32_t df_t = __shfl_sync(0xFFFFFFFFu, (uint32_t)differ, (int)t);
         sink.put_run(op_t, 1u); ++nops;
-        if (op_t == OP_M) { if (ex_t) { if (++cur > best) best = cur; } else cur = 0; --i; --j; }
+        if (op_t == OP_M) { mism += df_t; if (ex_t) { if (++cur > best) best = cur; } else cur = 0; --i; --j; }
         else { cur = 0; if (op_t == OP_D) --i; else --j; }
         // gap runs are short unless proven otherwise: switch hypothesis only after two equal gap moves in a row
         hyp = op_t == OP_M ? HYP_DIAG : (op_t == last_op ? (op_t == OP_D ? HYP_UP : HYP_LEFT) : HYP_DIAG);

@@ -318,7 +318,7 @@ struct WideTbArgs {
     const uint64_t* ops_off;
     int32_t         match, mismatch, gap;
     int32_t         score_only;
-    int32_t         opt;
+    int32_t         opt;            // bit 2 (value 4): hw4 tie order d > u > l, overlap := hw4's distance
 };
 
 struct WideLoader {
@@ -366,24 +366,25 @@ wide32_traceback_kernel(const WideTbArgs A)
                      wp.m, wp.n, num_chunks(wp.n, FM::CS), WIDE_R, 0, A.match, A.mismatch, A.gap, 0, A.opt, 0};
     const WideLoader ld{rec};
     WarpOpsSink sink(A.ops ? A.ops + A.ops_off[wp.pair] : nullptr, lane == 0);
-    uint32_t i, j, nops = 0;
+    uint32_t i, j, nops = 0, mism = 0;
     int best = 0;
     if (LOCAL) {
         int M; uint32_t bi, bj;
         warp_find_local_end<FM>(v, ld, M, bi, bj);
         res.score = M; res.end_i = bi; res.end_j = bj;
         i = bi; j = bj;
-        if (M != 0) warp_walk<FM, WideLoader, true>(v, ld, sink, i, j, nops, best);
+        if (M != 0) warp_walk<FM, WideLoader, true>(v, ld, sink, i, j, nops, best, mism);
     } else {
         i = wp.m; j = wp.n;
         res.end_i = i; res.end_j = j;
         res.score = (i && j) ? A.final_score[t] : (int32_t)(i + j) * A.gap;               // hw2.cpp:186 / borders :125-136
-        warp_walk<FM, WideLoader, false>(v, ld, sink, i, j, nops, best);
+        warp_walk<FM, WideLoader, false>(v, ld, sink, i, j, nops, best, mism);
         sink.put_run(OP_D, i); nops += i; i = 0;                                           // column 0 holds 'u' (hw2.cpp:128)
         sink.put_run(OP_I, j); nops += j; j = 0;                                           // row 0 holds 'l'    (hw2.cpp:134)
     }
     sink.flush();
-    res.start_i = i; res.start_j = j; res.overlap = best; res.n_ops = nops; res.path = 2;
+    res.start_i = i; res.start_j = j; res.n_ops = nops; res.path = 2;
+    res.overlap = (!LOCAL && (A.opt & 4)) ? (int)(nops - (wp.m + wp.n - nops) + mism) : best;       // hw4.cpp:141-152
     if (lane == 0) A.results[wp.pair] = res;
 }
 

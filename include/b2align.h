@@ -41,6 +41,9 @@ extern "C" {
 
 /* b2a_params.flags */
 #define B2A_WANT_OPS      1u  /* keep per-pair traceback ops on the device for b2a_fetch_ops / b2a_copy_ops */
+#define B2A_TIE_HW4       4u  /* global mode only: break ties d > u > l as hw4's own needleman_wunsch does (hw4/hw4.cpp:37-46) instead of
+                                 hw2's d > l > u (hw2.cpp:145-153); b2a_result.overlap then carries hw4's distance = number of alignment
+                                 columns holding a gap or a mismatch (hw4/hw4.cpp:141-152) */
 #define B2A_SCORE_ONLY    2u  /* fill only: results carry the score (hw2.cpp:186 / :225-229), no traceback record,
                                  no coordinates/overlap/ops -- the shape of hw3's distance stage (hw3.cpp:231-241) */
 
@@ -68,7 +71,8 @@ typedef struct b2a_result {
     uint32_t end_j;      /* ... and columns (text): (m,n) global, first row-major arg-max local      */
     uint32_t start_i;    /* cell where the traceback stopped: (0,0) global; H==0 or an edge local    */
     uint32_t start_j;
-    int32_t  overlap;    /* overlapLongestExactMatch(alignedPattern, alignedReference), hw2.cpp:267  */
+    int32_t  overlap;    /* overlapLongestExactMatch(alignedPattern, alignedReference), hw2.cpp:267;
+                            with B2A_TIE_HW4: mismatch + gap columns of the alignment, hw4.cpp:141-152  */
     uint32_t n_ops;      /* alignment columns = length of the traceback op list                      */
     uint32_t path;       /* which kernel family served the pair: 1 = short16 (s16x2), 2 = wide32     */
 } b2a_result;
@@ -155,6 +159,12 @@ int64_t b2a_render_mdz(const char* ops, uint64_t n_ops, const uint8_t* pattern, 
 /* Batch winner, hw2.cpp:326-357: key = overlap (global) / score (local), strict '>' from
  * -1000000 so the lowest index wins ties; -1 for an empty batch. */
 int64_t b2a_select_best(int32_t mode, const b2a_result* results, uint64_t n_pairs);
+
+/* ---- hw4's tree stage: UPGMA over the all-vs-all distances + Newick text (hw4/hw4.cpp:154-228) ---- */
+/* pair_dist holds the n(n-1)/2 distances of pairs (i, j), i < j, in row-major order (the order of the loop
+ * hw4.cpp:138-139); names are the FASTA ids.  Writes the line hw4 writes to its tree file WITHOUT the trailing
+ * newline ("(...):0.0;").  Host only.  Returns the length or <0 (buffer too small / bad argument). */
+int64_t b2a_upgma_newick(const int32_t* pair_dist, uint32_t n_seqs, const char* const* names, char* out, uint64_t cap);
 
 /* ---- measurement helper: sustained issue rate of the packed int16x2 DPX instructions ------- */
 /* Runs the microbenchmark kernel on ctx's device; *gops = 1e9 lane-instructions/s sustained by

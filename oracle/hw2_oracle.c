@@ -236,3 +236,42 @@ int orc_affine_score(const uint8_t* s1, uint32_t m, const uint8_t* s2, uint32_t 
     free(V);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * hw4's own Needleman-Wunsch (/root/reference/hw4/hw4.cpp:16-72) and its distance (hw4.cpp:141-152).
+ * Same recurrence as hw2's, but the tie order is d > u > l (hw4.cpp:37-46: 'U' overrides the diagonal if
+ * strictly larger, then 'L' overrides if strictly larger) -- NOT hw2's d > l > u (SURVEY.md trap T3).
+ * distance = number of alignment columns holding a gap or a mismatch.  ops in traceback order, hw2's
+ * letters: 'M' diagonal, 'D' sequence1 base over '-', 'I' '-' over sequence2 base.
+ * ------------------------------------------------------------------------------------------------ */
+int orc_hw4_nw(const uint8_t* s1, uint32_t m, const uint8_t* s2, uint32_t n, int match, int mismatch, int gap,
+               int32_t* score, int32_t* distance, uint32_t* n_ops, uint8_t* ops)
+{
+    size_t W = (size_t)n + 1;
+    int32_t* dp = (int32_t*)malloc(sizeof(int32_t) * (m + 1) * W);
+    char*    tb = (char*)malloc((size_t)(m + 1) * W);
+    if (!dp || !tb) { free(dp); free(tb); return -1; }
+    dp[0] = 0; tb[0] = 0;
+    for (uint32_t i = 1; i <= m; ++i) { dp[i * W] = dp[(i - 1) * W] + gap; tb[i * W] = 'U'; }   /* hw4.cpp:21-24 */
+    for (uint32_t j = 1; j <= n; ++j) { dp[j] = dp[j - 1] + gap; tb[j] = 'L'; }                 /* hw4.cpp:25-28 */
+    for (uint32_t i = 1; i <= m; ++i)
+        for (uint32_t j = 1; j <= n; ++j) {                                                     /* hw4.cpp:30-48 */
+            int up = dp[(i - 1) * W + j] + gap, left = dp[i * W + j - 1] + gap;
+            int v = dp[(i - 1) * W + j - 1] + (s1[i - 1] == s2[j - 1] ? match : mismatch);
+            char d = 'D';
+            if (up > v)   { v = up;   d = 'U'; }
+            if (left > v) { v = left; d = 'L'; }
+            dp[i * W + j] = v; tb[i * W + j] = d;
+        }
+    uint32_t i = m, j = n, k = 0; int32_t dist = 0;
+    while (i > 0 || j > 0) {                                                                    /* hw4.cpp:52-68 */
+        if (i > 0 && j > 0 && tb[i * W + j] == 'D') { if (s1[i - 1] != s2[j - 1]) ++dist; if (ops) ops[k] = 'M'; ++k; --i; --j; }
+        else if (i > 0 && tb[i * W + j] == 'U')     { ++dist; if (ops) ops[k] = 'D'; ++k; --i; }
+        else                                         { ++dist; if (ops) ops[k] = 'I'; ++k; --j; }
+    }
+    if (score) *score = dp[m * W + n];
+    if (distance) *distance = dist;
+    if (n_ops) *n_ops = k;
+    free(dp); free(tb);
+    return 0;
+}

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_HW2 = os.path.join(ORACLE_DIR, "_ref", "hw2")
 REF_HW3 = os.path.join(ORACLE_DIR, "_ref", "hw3")
+REF_HW4 = os.path.join(ORACLE_DIR, "_ref", "hw4")
 
 GLOBAL, LOCAL = 0, 1
 
@@ -37,6 +38,7 @@ def lib():
         _lib.orc_cigar.restype = C.c_size_t
         _lib.orc_mdz.restype = C.c_size_t
         _lib.orc_affine_score.restype = C.c_int
+        _lib.orc_hw4_nw.restype = C.c_int
     return _lib
 
 
@@ -90,6 +92,18 @@ def affine_score(s1: bytes, s2: bytes, match, mismatch, gopen, gext) -> int:
     if rc != 0:
         raise RuntimeError(f"orc_affine_score rc={rc}")
     return out.value
+
+
+def hw4_nw(s1: bytes, s2: bytes, match, mismatch, gap):
+    """hw4's NW (tie order d > u > l): returns (score, distance, ops in traceback order)."""
+    L = lib()
+    score, dist, nops = C.c_int32(), C.c_int32(), C.c_uint32()
+    ops = C.create_string_buffer(len(s1) + len(s2) + 1)
+    rc = L.orc_hw4_nw(s1, C.c_uint32(len(s1)), s2, C.c_uint32(len(s2)), C.c_int(match), C.c_int(mismatch), C.c_int(gap),
+                      C.byref(score), C.byref(dist), C.byref(nops), ops)
+    if rc != 0:
+        raise RuntimeError(f"orc_hw4_nw rc={rc}")
+    return score.value, dist.value, ops.raw[:nops.value]
 
 
 def select_best(mode, alignments):

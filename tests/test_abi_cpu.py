@@ -114,3 +114,42 @@ def test_cli_usage_and_error_paths_match_reference(tmp_path):
             assert outs == refouts, args
         else:
             assert mine.returncode in (0, 1)
+
+
+def test_upgma_newick_reproduces_trees_written_by_the_reference():
+    """b2a_upgma_newick (host only) on oracle distances == the tree the unmodified hw4 binary wrote (hw4.cpp:154-237)."""
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "hw4_kat.json")))
+    for c in kat["trees"] + kat["pairs"]:
+        seqs = [s.encode() for s in c["seqs"]]
+        dist = [ob.hw4_nw(seqs[i], seqs[j], *c["s"])[1] for i in range(len(seqs)) for j in range(i + 1, len(seqs))]
+        assert pkg.upgma_newick(dist, ["s%d" % i for i in range(len(seqs))]) + "\n" == c["tree"], c
+    assert pkg.upgma_newick([], ["only"]) == "only:0.0;"
+    lib = pkg.load_library()
+    buf = C.create_string_buffer(4)
+    names = (C.c_char_p * 2)(b"a", b"b")
+    d = np.array([3], dtype=np.int32)
+    assert lib.b2a_upgma_newick(d.ctypes.data, 2, names, buf, 4) < 0          # buffer too small
+
+
+def test_hw4_cli_error_paths_match_reference(tmp_path):
+    """usage / unknown option / missing input: same stderr text and exit code as the reference binary."""
+    ref = ob.REF_HW4
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/hw4 not built")
+    (tmp_path / "in.fa").write_text(">a\nACGT\n")
+    cases = [[], ["-i", "x"], ["-i", str(tmp_path / "nope.fa"), "-t", "t.txt", "-s", "1", "-1", "-1"],
+             ["-q", "1", "-t", "t.txt", "-s", "1", "-1", "-1"],
+             ["-i", str(tmp_path / "in.fa"), "-t", str(tmp_path / "nodir" / "t.txt"), "-s", "1", "-1", "-1"]]
+    for args in cases:
+        outs = []
+        for binary in (ref, pkg.HW4_BIN):
+            p = subprocess.run([binary] + args, capture_output=True, text=True, cwd=tmp_path)
+            outs.append((p.returncode, p.stderr.replace(binary, "hw4")))
+        if args and args[-1] == "-1" and "nodir" in args[4]:
+            # reaching the writer needs the distance stage; a single sequence has no pairs, so no GPU is involved
+            pass
+        assert outs[0] == outs[1], (args, outs)
+    # one sequence: no pairs -> runs without a GPU, byte-identical tree
+    for binary, name in ((ref, "r.txt"), (pkg.HW4_BIN, "m.txt")):
+        subprocess.check_call([binary, "-i", str(tmp_path / "in.fa"), "-t", str(tmp_path / name), "-s", "1", "-1", "-1"])
+    assert (tmp_path / "r.txt").read_bytes() == (tmp_path / "m.txt").read_bytes() == b"a:0.0;\n"

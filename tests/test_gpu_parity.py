@@ -345,3 +345,34 @@ def test_affine_tandem_repeats_10k(eng):
     got = eng.affine_scores([a, b, c], [c, a, b], *s)
     for g, (x, y) in zip(got, ((a, c), (b, a), (c, b))):
         assert int(g) == ob.affine_score(x, y, *s)
+
+
+# ---------------- hw4: NW with tie order d > u > l, distance, UPGMA tree ----------------
+def test_hw4_tie_order_and_distance_vs_oracle(eng):
+    """B2A_TIE_HW4 through both kernel families: ops and distance equal hw4's own needleman_wunsch (hw4.cpp:16-72, :141-152)."""
+    rng = random.Random(51)
+    ps, ts = [], []
+    for _ in range(60):
+        alpha = rng.choice([b"ACGT", b"AC", b"A"])
+        m, n = rng.choice([(5, 7), (20, 20), (150, 1000), (100, 90), (300, 280), (1, 40), (700, 650)])
+        t = rnd(rng, n, alpha)
+        ps.append((mutate(rng, t, alpha=alpha) + rnd(rng, m, alpha))[:m]); ts.append(t)
+    ps += [(b"ACGTA" * 300)[:1210], b"", b"ACGT"]; ts += [(b"ACGTACG" * 200)[:1200], b"ACGT", b""]
+    for s in ((1, -1, -1), (2, -3, -4), (5, -4, -16), (1, 0, 0), (300, -200, -500)):
+        res, ops = eng.align_batch(pkg.GLOBAL, ps, ts, *s, want_ops=True, tie_hw4=True)
+        for k, (p, t) in enumerate(zip(ps, ts)):
+            score, dist, want_ops = ob.hw4_nw(p, t, *s)
+            assert (int(res["score"][k]), int(res["overlap"][k]), ops[k]) == (score, dist, want_ops), (k, len(p), len(t), s)
+        if s == (1, -1, -1):
+            assert {int(x) for x in res["path"]} == {1, 2}          # both kernel families took part
+
+
+def test_hw4_cli_byte_exact(eng, tmp_path):
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "hw4_kat.json")))
+    (tmp_path / "in.fa").write_text(kat["shipped"]["fasta"])
+    subprocess.check_call([pkg.HW4_BIN, "-i", "in.fa", "-t", "tree.txt", "-s", "1", "-1", "-1"], cwd=tmp_path)
+    assert (tmp_path / "tree.txt").read_text() == kat["shipped"]["tree"]
+    for c in kat["trees"][:12] + kat["pairs"][:12]:
+        (tmp_path / "in.fa").write_text("".join(">s%d\n%s\n" % (i, s) for i, s in enumerate(c["seqs"])))
+        subprocess.check_call([pkg.HW4_BIN, "-i", "in.fa", "-t", "tree.txt", "-s", *map(str, c["s"])], cwd=tmp_path)
+        assert (tmp_path / "tree.txt").read_text() == c["tree"], c

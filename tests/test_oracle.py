@@ -165,3 +165,31 @@ def test_affine_restatement_reproduces_hw3_centre_golden():
                 sums[j] += v
         idx = max(range(k), key=lambda i: (sums[i], -i))          # first strict max, hw3.cpp:244-251
         assert parse_phy(c["phy"])[0][0] == "s%d" % idx, c
+
+
+# ---------------- hw4: own NW (tie order d > u > l) + distance, pinned by trees the real hw4 wrote ----------------
+HW4_KAT = json.load(open(os.path.join(HERE, "golden", "hw4_kat.json")))
+
+
+def test_hw4_restatement_matches_two_sequence_trees_golden():
+    """For two sequences hw4 writes "(a:h,b:h):0.0;" with h = distance / 2 (hw4.cpp:179-190)."""
+    for c in HW4_KAT["pairs"]:
+        a, b = c["seqs"]
+        score, dist, ops = ob.hw4_nw(a.encode(), b.encode(), *c["s"])
+        assert c["tree"] == "(s0:%f,s1:%f):0.0;\n" % (dist / 2.0, dist / 2.0), c
+        assert len(ops) - (len(a) + len(b) - len(ops)) <= dist
+
+
+@pytest.mark.skipif(not os.path.exists(ob.REF_HW4), reason="oracle/_ref/hw4 not built")
+def test_hw4_restatement_live_against_reference_binary(tmp_path):
+    import subprocess
+    rng = random.Random(44)
+    for it in range(120):
+        alpha = rng.choice([b"ACGT", b"AC", b"A", b"ACGTN"])
+        a = bytes(rng.choice(alpha) for _ in range(rng.randint(1, 90)))
+        b = bytes(rng.choice(alpha) for _ in range(rng.randint(1, 90)))
+        s = rng.choice([(1, -1, -1), (2, -3, -4), (1, -1, 0), (3, 1, -2), (0, 0, 0)])
+        (tmp_path / "in.fa").write_bytes(b">x\n" + a + b"\n>y\n" + b + b"\n")
+        subprocess.check_call([ob.REF_HW4, "-i", str(tmp_path / "in.fa"), "-t", str(tmp_path / "t.txt"), "-s", *map(str, s)])
+        _, dist, _ = ob.hw4_nw(a, b, *s)
+        assert (tmp_path / "t.txt").read_text() == "(x:%f,y:%f):0.0;\n" % (dist / 2.0, dist / 2.0), (a, b, s)
