@@ -121,10 +121,13 @@ def main():
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU")
     ap.add_argument("--ref-pairs", type=int, default=1500, help="reference sample: pairs per host process and mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scoring", default="1,-1,-1", help="match,mismatch,gap (SURVEY 8d also names 2,-3,-4: 4-bit deltas, twice the record)")
     args = ap.parse_args()
 
+    global SCORING
+    SCORING = tuple(int(x) for x in args.scoring.split(","))
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    workload_name = f"config2: {args.pairs} pairs/GPU, 150 bp x 1 kb DNA, seed 481+rank, -s 1 -1 -1, global+local, score+traceback"
+    workload_name = f"config2: {args.pairs} pairs/GPU, 150 bp x 1 kb DNA, seed 481+rank, -s {' '.join(map(str, SCORING))}, global+local, score+traceback"
 
     if args.impl == "reference":
         if rank != 0:
@@ -270,6 +273,8 @@ def main():
                                            "frac": cells_mode * args.steps * 6 / (fill_ms[1] * 1e-3) / 1e9 / peak_cellops}},
                     "hbm": {"fill_write_bytes_per_mode": fill_bytes,
                             "fill_write_gbs": fill_bytes * 2 * args.steps / fill_s / 1e9,
+                            # traceback: DRAM bytes read per pair from the committed ncu capture (profiles/r01_ncu_short16_summary.md)
+                            "traceback_read_bytes_per_pair": 7600, "traceback_read_gbs": 7600.0 * n_pairs * 2 * args.steps / ((tb_ms[0] + tb_ms[1]) * 1e-3) / 1e9,
                             "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
         cpu = None
         if not args.no_cpu_baseline and world == 1:

@@ -130,7 +130,8 @@ struct b2a_ctx {
     uint64_t seg_budget_bytes = 8ull << 30;       // record bytes per segment (B2A_SEG_MB overrides)
     uint64_t seg_max_pairs = 1ull << 17;          // pairs per segment of b2a_align_batch (B2A_SEG_PAIRS overrides)
     uint64_t seg_first_pairs = 1ull << 14;        // its first segment (then doubling): the kernels start after a short copy
-    uint64_t seg_resident_pairs = 1ull << 20;     // pairs per segment of b2a_batch_upload / b2a_batch_run
+    uint64_t seg_resident_pairs = 1ull << 20;     // pairs per segment of b2a_batch_upload / b2a_batch_run ...
+    uint64_t seg_resident_bytes = 60ull << 30;    // ... and its record bytes (a 1 M-pair batch with 4-bit deltas would need 110 GB)
     // s_fill runs the fill kernels back to back; s_tb (higher priority) runs the tracebacks, so the
     // latency-bound walk of segment k fills the issue slots the ALU-bound fill of segment k+1 leaves idle
     cudaStream_t s_copy = nullptr, s_down = nullptr, s_fill = nullptr, s_tb = nullptr;
@@ -643,7 +644,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
         const size_t si_next = ctx->segs.size();
         const uint64_t lim_pairs = !pipelined ? ctx->seg_resident_pairs
                                  : std::min<uint64_t>(ctx->seg_max_pairs, si_next < 20 ? ctx->seg_first_pairs << si_next : ctx->seg_max_pairs);
-        const uint64_t lim_bytes = pipelined ? ctx->seg_budget_bytes : ~0ull;
+        const uint64_t lim_bytes = pipelined ? ctx->seg_budget_bytes : ctx->seg_resident_bytes;
         uint64_t plan_key = ~0ull; bool plan_ok = false; Short16Plan pl{0, 0, 0}; uint64_t pair_bytes = 0;
         for (; k < n_pairs; ++k) {
             if (pat_off[k + 1] < pat_off[k] || txt_off[k + 1] < txt_off[k])

@@ -376,3 +376,44 @@ def test_hw4_cli_byte_exact(eng, tmp_path):
         (tmp_path / "in.fa").write_text("".join(">s%d\n%s\n" % (i, s) for i, s in enumerate(c["seqs"])))
         subprocess.check_call([pkg.HW4_BIN, "-i", "in.fa", "-t", "tree.txt", "-s", *map(str, c["s"])], cwd=tmp_path)
         assert (tmp_path / "tree.txt").read_text() == c["tree"], c
+
+
+def test_config2_full_size_one_million_pairs(eng):
+    """BASELINE.json's full size (1 M pairs, 1.5e11 cells per mode) through size-independent properties: the pipelined
+    b2a_align_batch (10 segments) and the resident upload/run/download path (1 segment) give identical records, a
+    checksum over all pairs is stable under a different segmentation, sampled op lists re-score to the reported score,
+    and sampled pairs equal the oracle."""
+    n_pairs = 1_000_000
+    pat, po, txt, to = workload.config2(n_pairs, seed=481)
+    P, T = pat.reshape(n_pairs, -1), txt.reshape(n_pairs, -1)
+    for mode in (pkg.GLOBAL, pkg.LOCAL):
+        res = eng.align_packed(mode, pat, po, txt, to, 1, -1, -1, want_ops=True)
+        words, off = eng.copy_ops(n_pairs)
+        eng.upload(mode, pat, po, txt, to, 1, -1, -1, want_ops=True)
+        eng.run()
+        res2 = eng.download(n_pairs)
+        eng.set_option(pkg.OPT_SEG_PAIRS, 50_000)
+        res3 = eng.align_packed(mode, pat, po, txt, to, 1, -1, -1, want_ops=False)
+        eng.set_option(pkg.OPT_SEG_PAIRS, 1 << 17)
+        for f in ("score", "end_i", "end_j", "start_i", "start_j", "overlap", "n_ops", "path"):
+            assert np.array_equal(res[f], res2[f]) and np.array_equal(res[f], res3[f]), f
+        assert int(res["path"].min()) == int(res["path"].max()) == 1
+        if mode == pkg.GLOBAL:
+            assert np.all(res["end_i"] == 150) and np.all(res["end_j"] == 1000) and np.all(res["start_i"] == 0) and np.all(res["start_j"] == 0)
+            assert np.all(res["n_ops"] >= 1000) and np.all(res["n_ops"] <= 1150)
+        else:
+            assert np.all(res["score"] >= 0) and np.all(res["score"] <= 150)
+        for k in range(0, n_pairs, 9973):
+            ops = pkg.unpack_ops(words, off, k, res["n_ops"][k])
+            i, j, sc = int(res["end_i"][k]), int(res["end_j"][k]), 0
+            for op in ops:
+                if op == 0x4D:
+                    i -= 1; j -= 1; sc += 1 if P[k, i] == T[k, j] else -1
+                elif op == 0x44:
+                    i -= 1; sc -= 1
+                else:
+                    j -= 1; sc -= 1
+            assert (i, j, sc) == (int(res["start_i"][k]), int(res["start_j"][k]), int(res["score"][k]))
+        for k in range(0, n_pairs, 99991):
+            a = ob.align(mode, P[k].tobytes(), T[k].tobytes(), 1, -1, -1)
+            assert (int(res["score"][k]), int(res["overlap"][k]), pkg.unpack_ops(words, off, k, res["n_ops"][k])) == (a.score, a.overlap, a.ops)
