@@ -29,7 +29,7 @@ RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<u4"), ("end_j", "<u4"), (
                          ("start_j", "<u4"), ("overlap", "<i4"), ("n_ops", "<u4"), ("path", "<u4")])
 
 EXPORTS = ["b2a_device_count", "b2a_create", "b2a_destroy", "b2a_last_error", "b2a_host_alloc", "b2a_host_free",
-           "b2a_align_batch", "b2a_affine_score_batch", "b2a_affine_star_scores", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
+           "b2a_align_batch", "b2a_affine_score_batch", "b2a_affine_align_batch", "b2a_affine_fetch_ops", "b2a_affine_star_scores", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
            "b2a_batch_download", "b2a_batch_times", "b2a_set_option", "b2a_batch_stats", "b2a_render_cigar", "b2a_render_mdz", "b2a_select_best",
            "b2a_upgma_newick",
            "b2a_microbench_int16x2", "b2a_debug_copy_record"]
@@ -84,6 +84,9 @@ def load_library():
         lib.b2a_upgma_newick.argtypes = [P, C.c_uint32, P, P, C.c_uint64]
         lib.b2a_microbench_int16x2.argtypes = [P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
         lib.b2a_affine_score_batch.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, P, P, P, C.c_uint64, P]
+        lib.b2a_affine_align_batch.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, P, P, P, C.c_uint64, P, P]
+        lib.b2a_affine_fetch_ops.restype = C.c_int64
+        lib.b2a_affine_fetch_ops.argtypes = [P, C.c_uint64, P, C.c_uint64]
         lib.b2a_affine_star_scores.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, P, C.c_uint32,
                                                C.c_uint32, C.c_uint32, P, P, P]
         _lib = lib
@@ -263,6 +266,24 @@ class Engine:
                                                     po.ctypes.data, txt.ctypes.data, to.ctypes.data, len(patterns),
                                                     out.ctypes.data), "b2a_affine_score_batch")
         return out
+
+    def affine_align(self, patterns, texts, match, mismatch, gap_open, gap_extend):
+        """hw3's affine_alignment WITH traceback (hw3.cpp:23-135): (int32 scores, list of op byte-strings in traceback order)"""
+        assert len(patterns) == len(texts)
+        pat, po = pack(patterns)
+        txt, to = pack(texts)
+        n = len(patterns)
+        sc = np.zeros(max(n, 1), dtype=np.int32)
+        nops = np.zeros(max(n, 1), dtype=np.uint32)
+        self._check(self.lib.b2a_affine_align_batch(self.ctx, match, mismatch, gap_open, gap_extend, pat.ctypes.data, po.ctypes.data,
+                                                    txt.ctypes.data, to.ctypes.data, n, sc.ctypes.data, nops.ctypes.data),
+                    "b2a_affine_align_batch")
+        ops = []
+        for k in range(n):
+            buf = C.create_string_buffer(int(nops[k]) + 1)
+            got = self._check(self.lib.b2a_affine_fetch_ops(self.ctx, k, buf, int(nops[k])), "b2a_affine_fetch_ops")
+            ops.append(buf.raw[:got])
+        return sc[:n], ops
 
     def affine_star_scores(self, seqs, match, mismatch, gap_open, gap_extend, pair_first=0, pair_count=None):
         """All-vs-all (i < j) scores of one sequence set, the star sums and the centre index (hw3.cpp:231-251)."""

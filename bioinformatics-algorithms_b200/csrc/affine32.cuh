@@ -38,7 +38,20 @@ struct AffineArgs {
     int32_t         match, mismatch, gopen, gext;
     uint32_t        epoch_tag;
     const AlphaInfo* alpha;         // ALPHA4 variant only
+    uint4*          codes;          // TRACE variant: 4-bit trace codes, 32 cells per 16 bytes, at WidePair::code_off
 };
+
+// Trace code of a cell (TRACE variant).  Every decision hw3's traceback reads is a property of ONE cell's (V, F, E):
+//   bits 0-1  which of V, F, E is the largest, the later one winning only when strictly larger (hw3.cpp:59-68 as seen from
+//             the cell diagonally below, and the final-state pick hw3.cpp:86-98): what traceV of the next cell will say
+//   bit 2     F + Ge > V + Go + Ge: the vertical gap of the cell below extends (traceF = 1, hw3.cpp:70-75)
+//   bit 3     E + Ge > V + Go + Ge: the horizontal gap of the cell to the right extends (traceE = 1, hw3.cpp:77-82)
+// Layout: chunk ((band*4 + r)*nblk + kb)*32 + L holds the 32 steps of block kb of row r of lane L, step f in nibble f.
+__device__ __forceinline__ uint32_t affine_code(int32_t v, int32_t f, int32_t e, int32_t vg, int32_t ge) {
+    uint32_t b3 = f > v ? 1u : 0u;
+    if (e > max(v, f)) b3 = 2u;
+    return b3 | (f + ge > vg ? 4u : 0u) | (e + ge > vg ? 8u : 0u);
+}
 
 #ifndef AFFINE_UNROLL
 #define AFFINE_UNROLL 32
@@ -46,7 +59,7 @@ struct AffineArgs {
 constexpr int AFF_UNROLL = AFFINE_UNROLL;
 constexpr int32_t AFFINE_NEG = INT32_MIN / 2;        // hw3.cpp:16
 
-template <bool ALPHA4>
+template <bool ALPHA4, bool TRACE>
 __global__ void __launch_bounds__(WIDE_WARPS * 32)
 affine32_score_kernel(const AffineArgs A)
 {
@@ -148,8 +161,13 @@ affine32_score_kernel(const AffineArgs A)
             tnext = text_byte(q0 + 32u + (uint32_t)lane);
 
             const bool steady = q0 >= 32u && q0 + 31u <= n;
+            uint32_t cw[R][4];                                               // TRACE: the block's codes of this lane's rows
+            if (TRACE) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) { cw[r][0] = cw[r][1] = cw[r][2] = cw[r][3] = 0u; }
+            }
             // RAMP flavour freezes the lanes outside 1 <= q - lane <= n with selects, not a branch (see wide32.cuh)
-            auto step = [&](uint32_t q, auto ramp_tag, bool active) {
+            auto step = [&](uint32_t q, int fi, auto ramp_tag, bool active) {
                 constexpr bool RAMP = decltype(ramp_tag)::value;
                 int32_t uVg = __shfl_up_sync(0xFFFFFFFFu, Vg[R - 1], 1);
                 int32_t uF  = __shfl_up_sync(0xFFFFFFFFu, Fk, 1);
@@ -167,6 +185,7 @@ affine32_score_kernel(const AffineArgs A)
                     const int32_t ee = __viaddmax_s32(E[r], ge, Vg[r]);      // hw3.cpp:77-82
                     const int32_t vg = v + goe;
                     const int32_t m3 = __vimax3_s32(v, f, ee);
+                    if (TRACE) cw[r][fi >> 3] |= affine_code(v, f, ee, vg, ge) << (4 * (fi & 7));   // cells outside the matrix: never read
                     if (RAMP) { M3[r] = active ? m3 : M3[r]; Vg[r] = active ? vg : Vg[r]; E[r] = active ? ee : E[r]; }
                     else { M3[r] = m3; Vg[r] = vg; E[r] = ee; }
                     uVg = vg; uF = f;
@@ -177,10 +196,15 @@ affine32_score_kernel(const AffineArgs A)
             // small unroll on purpose: compact code keeps a band's first (cold) blocks cheap, see wide32.cuh
             if (steady) {
 #pragma unroll AFF_UNROLL
-                for (int f = 0; f < 32; ++f) step(q0 + (uint32_t)f, std::false_type{}, true);
+                for (int f = 0; f < 32; ++f) step(q0 + (uint32_t)f, f, std::false_type{}, true);
             } else {
 #pragma unroll AFF_UNROLL
-                for (int f = 0; f < 32; ++f) step(q0 + (uint32_t)f, std::true_type{}, (uint32_t)(q0 + (uint32_t)f - lane - 1u) < n);
+                for (int f = 0; f < 32; ++f) step(q0 + (uint32_t)f, f, std::true_type{}, (uint32_t)(q0 + (uint32_t)f - lane - 1u) < n);
+            }
+            if (TRACE) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    A.codes[wp.code_off + (((uint64_t)band * R + r) * nblk + kb) * 32u + lane] = make_uint4(cw[r][0], cw[r][1], cw[r][2], cw[r][3]);
             }
             if (has_next) {                                                  // publish the block's bottom row, one coalesced store per plane
                 __syncwarp();
@@ -206,6 +230,64 @@ affine32_score_kernel(const AffineArgs A)
         }
         __syncwarp();
     }
+}
+
+// ---- traceback over the trace codes: one WARP per pair, hw3.cpp:100-135 ----
+// State machine of the reference (state V: emit a column of two bases, go diagonally, next state = traceV; state F: base over '-',
+// go up, next state F iff traceF says "extended"; state E: '-' over base, go left).  Each state continues in one direction while one
+// bit of the cells it passes stays set, so the 32 lanes read the codes of the next 32 cells of that direction and the leading run is
+// accepted at once (same idea as walk_warp.cuh).  Ops use hw2's letters: M diagonal, D string1 base over '-', I '-' over string2 base.
+struct AffineTbArgs {
+    const WidePair* pairs;
+    uint32_t        n_wide;
+    const uint4*    codes;
+    uint32_t*       n_ops;          // per pair (indexed by WidePair::pair)
+    uint32_t*       ops;
+    const uint64_t* ops_off;        // per pair word offset
+};
+
+__global__ void __launch_bounds__(WIDE_TB_WARPS * 32)
+affine32_traceback_kernel(const AffineTbArgs A)
+{
+    constexpr int R = WIDE_R;
+    const int lane = (int)(threadIdx.x & 31u);
+    const uint32_t t = blockIdx.x * WIDE_TB_WARPS + (threadIdx.x >> 5);
+    if (t >= A.n_wide) return;
+    const WidePair wp = A.pairs[t];
+    const uint32_t nblk = (wp.n + 32u + 31u) / 32u;
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(A.codes + wp.code_off);
+    auto code_at = [&](uint32_t i, uint32_t j) -> uint32_t {                 // 1 <= i <= m, 1 <= j <= n
+        const uint32_t x = i - 1u, band = x / (32u * R), L = (x / R) & 31u, r = x % R, q = j + L;
+        const uint64_t chunk = (((uint64_t)band * R + r) * nblk + (q >> 5)) * 32u + L;
+        return (__ldg(base + chunk * 4u + ((q & 31u) >> 3)) >> (4u * (q & 7u))) & 15u;
+    };
+    WarpOpsSink sink(A.ops + A.ops_off[wp.pair], lane == 0);
+    uint32_t i = wp.m, j = wp.n, nops = 0;
+    uint32_t state = (i && j) ? (code_at(i, j) & 3u) : 0u;                   // hw3.cpp:86-98
+    while (i > 0u || j > 0u) {
+        if (j == 0u) { sink.put_run(OP_D, i); nops += i; break; }            // column 0 is all F (traceF[i][0], hw3.cpp:44-45)
+        if (i == 0u) { sink.put_run(OP_I, j); nops += j; break; }            // row 0 is all E    (traceE[0][j], hw3.cpp:50-51)
+        const uint32_t k = (uint32_t)lane + 1u;
+        const uint32_t ci = state == 2u ? i : i - min(k, i), cj = state == 1u ? j : j - min(k, j);
+        const bool valid = ci >= 1u && cj >= 1u && (state == 2u || i > (uint32_t)lane) && (state == 1u || j > (uint32_t)lane);
+        const uint32_t c = valid ? code_at(ci, cj) : 0u;
+        const bool cont = valid && (state == 0u ? (c & 3u) == 0u : (state == 1u ? (c & 4u) != 0u : (c & 8u) != 0u));
+        const uint32_t okm = __ballot_sync(0xFFFFFFFFu, cont);
+        const uint32_t lead = okm == 0xFFFFFFFFu ? 32u : (uint32_t)(__ffs(~okm) - 1);
+        const uint32_t steps = min(lead + 1u, 32u);                          // the current cell's own move + the confirmed ones
+        const uint32_t op = state == 0u ? OP_M : (state == 1u ? OP_D : OP_I);
+        sink.put_run(op, steps); nops += steps;
+        if (state != 2u) i -= steps;
+        if (state != 1u) j -= steps;
+        if (lead < 32u) {                                                    // lane `lead` saw where the run ends
+            const uint32_t v_t = __shfl_sync(0xFFFFFFFFu, (uint32_t)valid, (int)lead);
+            const uint32_t c_t = __shfl_sync(0xFFFFFFFFu, c, (int)lead);
+            if (v_t) state = state == 0u ? (c_t & 3u) : 0u;                  // traceV names the next state; a gap that stops extending was opened from V
+            // !v_t: a border was reached (i == 0 or j == 0), handled at the top of the loop
+        }
+    }
+    sink.flush();
+    if (lane == 0) A.n_ops[wp.pair] = nops;
 }
 
 } // namespace b2a

@@ -142,6 +142,7 @@ struct b2a_ctx {
 
     // batch state
     bool have_batch = false, ran = false;
+    bool affine_ops = false;                      // the last call was b2a_affine_align_batch: d_ops / d_nops hold its op lists
     b2a_params prm{};
     uint64_t n_pairs = 0;
     int K = 0;
@@ -155,7 +156,7 @@ struct b2a_ctx {
     DevBuf<uint8_t> d_pat, d_txt;
     DevBuf<uint64_t> d_pat_off, d_txt_off, d_code_off, d_ops_off;
     DevBuf<PPDesc> d_pps;
-    DevBuf<uint32_t> d_ops;
+    DevBuf<uint32_t> d_ops, d_nops;
     DevBuf<AlphaInfo> d_alpha;                    // one per segment + one for the whole batch (wide32)
     DevBuf<PairResult> d_results;
     DevBuf<int4> d_endcell;                       // local mode: end cell per pair, written by the short16 fill epilogue
@@ -480,49 +481,41 @@ int join_tracebacks(b2a_ctx* ctx) {
 struct AffSpec { uint64_t pat_off, txt_off; uint32_t m, n; };
 
 int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const uint8_t* pat, uint64_t pat_bytes,
-               const uint8_t* txt, uint64_t txt_bytes, bool same_buffer, const std::vector<AffSpec>& specs, int32_t* scores)
+               const uint8_t* txt, uint64_t txt_bytes, bool same_buffer, const std::vector<AffSpec>& specs, int32_t* scores,
+               bool trace, uint32_t* n_ops_out)
 {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->s_copy)); CU(cudaStreamSynchronize(ctx->s_down));
     CU(cudaStreamSynchronize(ctx->s_fill)); CU(cudaStreamSynchronize(ctx->s_tb));
-    ctx->have_batch = false; ctx->ran = false;              // the batch buffers are reused below
+    ctx->have_batch = false; ctx->ran = false; ctx->affine_ops = false;   // the batch buffers are reused below
     ctx->cells = ctx->fill_bytes = ctx->launches = ctx->h2d = ctx->d2h = 0;
     const int64_t smag = std::max<int64_t>({std::llabs((long long)match), std::llabs((long long)mismatch),
                                             std::llabs((long long)gopen) + std::llabs((long long)gext)});
-    WideState& W = ctx->wide;
-    W.pairs.clear(); W.tasks.clear();
-    W.bound_words = 0;
-    uint32_t max_bands = 0;
-    std::vector<uint32_t> slot(specs.size(), 0xFFFFFFFFu);
-    for (size_t k = 0; k < specs.size(); ++k) {
+    const size_t n = specs.size();
+    uint64_t opsw = 0;
+    if (trace) CU(ctx->h_ops_off.reserve(n + 1));
+    for (size_t k = 0; k < n; ++k) {
         const AffSpec& sp = specs[k];
         // the sentinel arithmetic of hw3.cpp:16 must not wrap: NEG - (m+n)*max|score| has to stay above INT_MIN
         if (((uint64_t)sp.m + sp.n + 2) * (uint64_t)smag >= (1ull << 30))
             return fail(ctx, B2A_ERR_RANGE, "b2a_affine: (m+n)*max|score| exceeds 2^30 (hw3's INT_MIN/2 sentinel would wrap)");
+        if ((sp.m + 32u * WIDE_R - 1u) / (32u * WIDE_R) >= (1u << 20))
+            return fail(ctx, B2A_ERR_RANGE, "b2a_affine: sequence too long (band index must fit 20 bits)");
         ctx->cells += (uint64_t)sp.m * sp.n;
-        if (sp.m == 0 || sp.n == 0) continue;                // borders only: answered on the host below
-        WidePair p{};
-        p.pat_off = sp.pat_off; p.txt_off = sp.txt_off; p.m = sp.m; p.n = sp.n; p.pair = (uint32_t)k;
-        p.nbands = (sp.m + 32u * WIDE_R - 1u) / (32u * WIDE_R);
-        p.bound_stride = ((sp.n + 64u) + 31u) & ~31u;
-        if (p.nbands >= (1u << 20)) return fail(ctx, B2A_ERR_RANGE, "b2a_affine: sequence too long (band index must fit 20 bits)");
-        p.bound_off = W.bound_words; if (p.nbands > 1u) W.bound_words += 6ull * p.bound_stride;   // 2 buffers x {Vg, F, M3}
-        max_bands = std::max(max_bands, p.nbands);
-        slot[k] = (uint32_t)W.pairs.size();
-        W.pairs.push_back(p);
+        if (trace) { ctx->h_ops_off.p[k] = opsw; opsw += ((uint64_t)sp.m + sp.n + 15) / 16 + 1; }
     }
-    std::vector<uint32_t> order(W.pairs.size());
-    for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return W.pairs[a].nbands > W.pairs[b].nbands; });
-    for (uint32_t b = 0; b < max_bands; ++b)                 // band-major tickets: a band's producer always holds an earlier ticket
-        for (uint32_t i : order) { if (W.pairs[i].nbands <= b) break; W.tasks.push_back(WideTask{i, b}); }
-
+    WideState& W = ctx->wide;
     cudaStream_t st = ctx->s_fill;
     CU(ctx->d_pat.reserve(pat_bytes + 16));
     if (!same_buffer) CU(ctx->d_txt.reserve(txt_bytes + 16));
     CU(ctx->d_alpha.reserve(2)); CU(ctx->h_alpha.reserve(2));
-    CU(W.d_pairs.reserve(W.pairs.size())); CU(W.d_tasks.reserve(W.tasks.size()));
-    CU(W.d_final.reserve(W.pairs.size())); CU(W.d_progress.reserve(1));
+    CU(W.d_progress.reserve(1));
+    if (trace) {
+        ctx->h_ops_off.p[n] = opsw;
+        CU(ctx->d_ops.reserve(opsw)); CU(ctx->d_ops_off.reserve(n + 1)); CU(ctx->d_nops.reserve(n));
+        CU(cudaMemcpyAsync(ctx->d_ops_off.p, ctx->h_ops_off.p, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (n) CU(cudaMemsetAsync(ctx->d_nops.p, 0, n * 4, st));
+    }
     if (pat_bytes) CU(cudaMemcpyAsync(ctx->d_pat.p, pat, pat_bytes, cudaMemcpyHostToDevice, st));
     if (!same_buffer && txt_bytes) CU(cudaMemcpyAsync(ctx->d_txt.p, txt, txt_bytes, cudaMemcpyHostToDevice, st));
     ctx->h2d += pat_bytes + (same_buffer ? 0 : txt_bytes);
@@ -536,43 +529,105 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
     alphabet_finish_kernel<<<1, 32, 0, st>>>(ctx->d_alpha.p);
     CU(cudaGetLastError()); ++launches;
     CU(cudaMemcpyAsync(ctx->h_alpha.p, ctx->d_alpha.p, sizeof(AlphaInfo), cudaMemcpyDeviceToHost, st));
-    if (!W.pairs.empty()) {
-        CU(cudaMemcpyAsync(W.d_pairs.p, W.pairs.data(), W.pairs.size() * sizeof(WidePair), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(W.d_tasks.p, W.tasks.data(), W.tasks.size() * sizeof(WideTask), cudaMemcpyHostToDevice, st));
-        ctx->h2d += W.pairs.size() * sizeof(WidePair) + W.tasks.size() * sizeof(WideTask);
-    }
     CU(cudaStreamSynchronize(st));
     const bool alpha4 = !ctx->h_alpha.p[0].too_many && match <= 127 && match >= -128 && mismatch <= 127 && mismatch >= -128;
-    std::vector<int32_t> fin(W.pairs.size());
-    float ms = 0;
-    if (!W.tasks.empty()) {
-        CU(cudaMemsetAsync(W.d_progress.p, 0, 4, st));
-        AffineArgs a{};
-        CU(W.next_epoch(W.bound_words, st, &a.epoch_tag));
-        a.pat = ctx->d_pat.p; a.txt = same_buffer ? ctx->d_pat.p : ctx->d_txt.p; a.pairs = W.d_pairs.p; a.tasks = W.d_tasks.p;
-        a.n_tasks = (uint32_t)W.tasks.size(); a.ticket = W.d_progress.p;
-        a.bound = W.d_bound.p; a.final_score = W.d_final.p;
-        a.match = match; a.mismatch = mismatch; a.gopen = gopen; a.gext = gext; a.alpha = ctx->d_alpha.p;
-        const unsigned need = (unsigned)((W.tasks.size() + WIDE_WARPS - 1) / WIDE_WARPS);
-        const unsigned grid = std::min<unsigned>(need, (unsigned)ctx->sm_count * 8u);
-        CU(cudaEventRecord(ctx->ev_begin, st));
-        if (alpha4) affine32_score_kernel<true><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
-        else affine32_score_kernel<false><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
-        CU(cudaGetLastError()); ++launches;
-        CU(cudaEventRecord(ctx->ev_end, st));
-        CU(cudaMemcpyAsync(fin.data(), W.d_final.p, fin.size() * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        CU(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
-        ctx->d2h += fin.size() * 4;
+
+    // pairs are served in groups whose trace codes (0.5 byte per cell) fit the budget; score-only runs are one group
+    const uint64_t code_budget_chunks = (48ull << 30) / sizeof(Chunk);
+    float ms_total = 0;
+    size_t first = 0;
+    while (first < n) {
+        W.pairs.clear(); W.tasks.clear();
+        W.bound_words = 0; W.chunks = 0;
+        uint32_t max_bands = 0;
+        std::vector<uint32_t> slot;                         // spec index of every planned pair of the group
+        size_t k = first;
+        for (; k < n; ++k) {
+            const AffSpec& sp = specs[k];
+            if (sp.m == 0 || sp.n == 0) continue;           // borders only: answered on the host below
+            WidePair p{};
+            p.pat_off = sp.pat_off; p.txt_off = sp.txt_off; p.m = sp.m; p.n = sp.n; p.pair = (uint32_t)k;
+            p.nbands = (sp.m + 32u * WIDE_R - 1u) / (32u * WIDE_R);
+            const uint64_t need = trace ? (uint64_t)p.nbands * WIDE_R * ((sp.n + 63u) / 32u) * 32u : 0;
+            if (trace && !W.pairs.empty() && W.chunks + need > code_budget_chunks) break;
+            p.code_off = W.chunks; W.chunks += need;
+            p.bound_stride = ((sp.n + 64u) + 31u) & ~31u;
+            p.bound_off = W.bound_words; if (p.nbands > 1u) W.bound_words += 6ull * p.bound_stride;   // 2 buffers x {Vg, F, M3}
+            max_bands = std::max(max_bands, p.nbands);
+            slot.push_back((uint32_t)k);
+            W.pairs.push_back(p);
+        }
+        const size_t group_end = k;
+        std::vector<uint32_t> order(W.pairs.size());
+        for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return W.pairs[a].nbands > W.pairs[b].nbands; });
+        for (uint32_t b = 0; b < max_bands; ++b)             // band-major tickets: a band's producer always holds an earlier ticket
+            for (uint32_t i : order) { if (W.pairs[i].nbands <= b) break; W.tasks.push_back(WideTask{i, b}); }
+        std::vector<int32_t> fin(W.pairs.size());
+        if (!W.tasks.empty()) {
+            CU(W.d_pairs.reserve(W.pairs.size())); CU(W.d_tasks.reserve(W.tasks.size())); CU(W.d_final.reserve(W.pairs.size()));
+            if (trace) CU(W.d_codes.reserve(W.chunks));
+            CU(cudaMemcpyAsync(W.d_pairs.p, W.pairs.data(), W.pairs.size() * sizeof(WidePair), cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(W.d_tasks.p, W.tasks.data(), W.tasks.size() * sizeof(WideTask), cudaMemcpyHostToDevice, st));
+            ctx->h2d += W.pairs.size() * sizeof(WidePair) + W.tasks.size() * sizeof(WideTask);
+            CU(cudaMemsetAsync(W.d_progress.p, 0, 4, st));
+            AffineArgs a{};
+            CU(W.next_epoch(W.bound_words, st, &a.epoch_tag));
+            a.pat = ctx->d_pat.p; a.txt = same_buffer ? ctx->d_pat.p : ctx->d_txt.p; a.pairs = W.d_pairs.p; a.tasks = W.d_tasks.p;
+            a.n_tasks = (uint32_t)W.tasks.size(); a.ticket = W.d_progress.p;
+            a.bound = W.d_bound.p; a.final_score = W.d_final.p;
+            a.match = match; a.mismatch = mismatch; a.gopen = gopen; a.gext = gext; a.alpha = ctx->d_alpha.p;
+            a.codes = trace ? reinterpret_cast<uint4*>(W.d_codes.p) : nullptr;
+            const unsigned need = (unsigned)((W.tasks.size() + WIDE_WARPS - 1) / WIDE_WARPS);
+            const unsigned grid = std::min<unsigned>(need, (unsigned)ctx->sm_count * 8u);
+            CU(cudaEventRecord(ctx->ev_begin, st));
+            if (trace) { if (alpha4) affine32_score_kernel<true, true><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
+                         else affine32_score_kernel<false, true><<<grid, WIDE_WARPS * 32, 0, st>>>(a); }
+            else       { if (alpha4) affine32_score_kernel<true, false><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
+                         else affine32_score_kernel<false, false><<<grid, WIDE_WARPS * 32, 0, st>>>(a); }
+            CU(cudaGetLastError()); ++launches;
+            if (trace) {
+                AffineTbArgs ta{W.d_pairs.p, (uint32_t)W.pairs.size(), reinterpret_cast<const uint4*>(W.d_codes.p), ctx->d_nops.p, ctx->d_ops.p, ctx->d_ops_off.p};
+                affine32_traceback_kernel<<<(unsigned)((W.pairs.size() + WIDE_TB_WARPS - 1) / WIDE_TB_WARPS), WIDE_TB_WARPS * 32, 0, st>>>(ta);
+                CU(cudaGetLastError()); ++launches;
+                ctx->fill_bytes += W.chunks * sizeof(Chunk);
+            }
+            CU(cudaEventRecord(ctx->ev_end, st));
+            CU(cudaMemcpyAsync(fin.data(), W.d_final.p, fin.size() * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+            ms_total += ms;
+            ctx->d2h += fin.size() * 4;
+        }
+        for (size_t q = 0; q < slot.size(); ++q) scores[slot[q]] = fin[q];
+        first = group_end;
     }
-    for (size_t k = 0; k < specs.size(); ++k) {
+    for (size_t k = 0; k < n; ++k) {
         const AffSpec& sp = specs[k];
-        if (slot[k] != 0xFFFFFFFFu) scores[k] = fin[slot[k]];
-        else if (sp.m == 0 && sp.n == 0) scores[k] = 0;                                  // V[0][0]               hw3.cpp:40
+        if (sp.m && sp.n) continue;
+        if (sp.m == 0 && sp.n == 0) scores[k] = 0;                                       // V[0][0]               hw3.cpp:40
         else if (sp.m == 0) scores[k] = gopen + gext * (int32_t)(sp.n - 1);              // E[0][n]               hw3.cpp:50
         else scores[k] = gopen + gext * (int32_t)(sp.m - 1);                             // F[m][0]               hw3.cpp:44
     }
-    ctx->last_fill_ms = ms; ctx->last_tb_ms = 0; ctx->last_total_ms = ms;
+    if (trace) {
+        std::vector<uint32_t> nops(n);
+        if (n) CU(cudaMemcpy(nops.data(), ctx->d_nops.p, n * 4, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < n; ++k) {
+            const AffSpec& sp = specs[k];
+            if (sp.m == 0 || sp.n == 0) {
+                // one gap run along a border (hw3.cpp:42-53): all 'D' (column 0) or all 'I' (row 0); written from the host
+                const uint32_t len = sp.m + sp.n, op = sp.n == 0 ? OP_D : OP_I;
+                std::vector<uint32_t> w(((uint64_t)len + 15) / 16 + 1, op * 0x55555555u);
+                if (len) CU(cudaMemcpy(ctx->d_ops.p + ctx->h_ops_off.p[k], w.data(), (((uint64_t)len + 15) / 16) * 4, cudaMemcpyHostToDevice));
+                nops[k] = len;
+            }
+            if (n_ops_out) n_ops_out[k] = nops[k];
+        }
+        if (n) CU(cudaMemcpy(ctx->d_nops.p, nops.data(), n * 4, cudaMemcpyHostToDevice));
+        ctx->affine_ops = true; ctx->n_pairs = n; ctx->total_ops_words = opsw;
+    }
+    ctx->last_fill_ms = ms_total; ctx->last_tb_ms = 0; ctx->last_total_ms = ms_total;
     ctx->launches = launches;
     return B2A_OK;
 }
@@ -599,7 +654,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
     // a previous batch may still own the pinned plan arrays / device buffers
     CU(cudaStreamSynchronize(ctx->s_copy)); CU(cudaStreamSynchronize(ctx->s_down));
     CU(cudaStreamSynchronize(ctx->s_fill)); CU(cudaStreamSynchronize(ctx->s_tb));
-    ctx->have_batch = false; ctx->ran = false;
+    ctx->have_batch = false; ctx->ran = false; ctx->affine_ops = false;
     ctx->prm = *prm; ctx->n_pairs = n_pairs;
     ctx->segs.clear(); ctx->wide_pairs.clear();
     ctx->cells = ctx->fill_bytes = ctx->launches = ctx->h2d = ctx->d2h = 0;
@@ -906,7 +961,7 @@ void b2a_destroy(b2a_ctx* ctx) {
     if (ctx->s_tb) cudaStreamDestroy(ctx->s_tb);
     ctx->d_pat.release(); ctx->d_txt.release(); ctx->d_pat_off.release(); ctx->d_txt_off.release();
     ctx->d_code_off.release(); ctx->d_ops_off.release(); ctx->d_pps.release();
-    ctx->d_ops.release(); ctx->d_alpha.release(); ctx->d_results.release(); ctx->d_endcell.release();
+    ctx->d_ops.release(); ctx->d_alpha.release(); ctx->d_results.release(); ctx->d_endcell.release(); ctx->d_nops.release();
     ctx->h_pps.release(); ctx->h_code_off.release(); ctx->h_ops_off.release(); ctx->h_alpha.release();
     ctx->wide.release();
     for (auto& e : ctx->ev_pool) if (e) cudaEventDestroy(e);
@@ -1018,7 +1073,45 @@ int b2a_affine_score_batch(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_
         if (m + n >= 0x7FFFFFF0ull) return fail(ctx, B2A_ERR_RANGE, "b2a_affine_score_batch: sequence too long");
         specs[k] = AffSpec{pat_off[k], txt_off[k], (uint32_t)m, (uint32_t)n};
     }
-    return affine_run(ctx, match, mismatch, gap_open, gap_extend, pat, pat_bytes, txt, txt_bytes, false, specs, scores);
+    return affine_run(ctx, match, mismatch, gap_open, gap_extend, pat, pat_bytes, txt, txt_bytes, false, specs, scores, false, nullptr);
+}
+
+int b2a_affine_align_batch(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                           const uint8_t* pat, const uint64_t* pat_off, const uint8_t* txt, const uint64_t* txt_off,
+                           uint64_t n_pairs, int32_t* scores, uint32_t* n_ops)
+{
+    if (!ctx) return B2A_ERR_ARG;
+    if (!pat_off || !txt_off || (!scores && n_pairs)) return fail(ctx, B2A_ERR_ARG, "b2a_affine_align_batch: null argument");
+    if (n_pairs > 0x7FFFFFF0ull) return fail(ctx, B2A_ERR_ARG, "b2a_affine_align_batch: too many pairs");
+    const uint64_t pat_bytes = n_pairs ? pat_off[n_pairs] : 0, txt_bytes = n_pairs ? txt_off[n_pairs] : 0;
+    if ((pat_bytes && !pat) || (txt_bytes && !txt)) return fail(ctx, B2A_ERR_ARG, "b2a_affine_align_batch: null sequence buffer");
+    std::vector<AffSpec> specs(n_pairs);
+    for (uint64_t k = 0; k < n_pairs; ++k) {
+        if (pat_off[k + 1] < pat_off[k] || txt_off[k + 1] < txt_off[k])
+            return fail(ctx, B2A_ERR_ARG, "b2a_affine_align_batch: offsets must be non-decreasing");
+        const uint64_t m = pat_off[k + 1] - pat_off[k], n = txt_off[k + 1] - txt_off[k];
+        if (m + n >= 0x7FFFFFF0ull) return fail(ctx, B2A_ERR_RANGE, "b2a_affine_align_batch: sequence too long");
+        specs[k] = AffSpec{pat_off[k], txt_off[k], (uint32_t)m, (uint32_t)n};
+    }
+    return affine_run(ctx, match, mismatch, gap_open, gap_extend, pat, pat_bytes, txt, txt_bytes, false, specs, scores, true, n_ops);
+}
+
+int64_t b2a_affine_fetch_ops(b2a_ctx* ctx, uint64_t pair, char* ops, uint64_t ops_cap)
+{
+    if (!ctx) return B2A_ERR_ARG;
+    if (!ctx->affine_ops) return fail(ctx, B2A_ERR_STATE, "b2a_affine_fetch_ops: call b2a_affine_align_batch first");
+    if (pair >= ctx->n_pairs) return fail(ctx, B2A_ERR_ARG, "b2a_affine_fetch_ops: pair index out of range");
+    CU(cudaSetDevice(ctx->device));
+    uint32_t n_ops = 0;
+    CU(cudaMemcpy(&n_ops, ctx->d_nops.p + pair, 4, cudaMemcpyDeviceToHost));
+    if (n_ops > ops_cap) return fail(ctx, B2A_ERR_ARG, "b2a_affine_fetch_ops: buffer too small");
+    const uint64_t nw = ((uint64_t)n_ops + 15) / 16;
+    std::vector<uint32_t> w(nw);
+    if (nw) CU(cudaMemcpy(w.data(), ctx->d_ops.p + ctx->h_ops_off.p[pair], nw * 4, cudaMemcpyDeviceToHost));
+    ctx->d2h += 4 + nw * 4;
+    static const char L[4] = {'M', 'D', 'I', '?'};
+    for (uint32_t t = 0; t < n_ops; ++t) ops[t] = L[(w[t >> 4] >> (2 * (t & 15))) & 3u];
+    return (int64_t)n_ops;
 }
 
 int b2a_affine_star_scores(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
@@ -1043,7 +1136,7 @@ int b2a_affine_star_scores(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_
             ij.emplace_back(i, j);
         }
     std::vector<int32_t> sc(specs.size());
-    int rc = affine_run(ctx, match, mismatch, gap_open, gap_extend, seqs, n_seqs ? seq_off[n_seqs] : 0, nullptr, 0, true, specs, sc.data());
+    int rc = affine_run(ctx, match, mismatch, gap_open, gap_extend, seqs, n_seqs ? seq_off[n_seqs] : 0, nullptr, 0, true, specs, sc.data(), false, nullptr);
     if (rc != B2A_OK) return rc;
     if (pair_scores) std::copy(sc.begin(), sc.end(), pair_scores);
     if (sum_scores) {                                                        // hw3.cpp:238-239 (partial sums of this pair range)

@@ -130,6 +130,14 @@ int b2a_batch_stats(const b2a_ctx* ctx, uint64_t* kernel_launches, uint64_t* cel
 int b2a_affine_score_batch(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
                            const uint8_t* pat, const uint64_t* pat_off, const uint8_t* txt, const uint64_t* txt_off,
                            uint64_t n_pairs, int32_t* scores);
+/* The same alignment WITH its traceback (hw3.cpp:100-135), as hw3 runs it for the centre against every other
+ * sequence (hw3.cpp:259-266): the op list (traceback order, hw2's letters: 'M' column of two bases, 'D' string1 base
+ * over '-', 'I' '-' over string2 base) stays on the device for b2a_affine_fetch_ops; n_ops (may be NULL) receives the
+ * alignment lengths.  Trace decisions are the reference's: V/F/E priority with strict '>' (hw3.cpp:59-82, :86-98). */
+int b2a_affine_align_batch(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                           const uint8_t* pat, const uint64_t* pat_off, const uint8_t* txt, const uint64_t* txt_off,
+                           uint64_t n_pairs, int32_t* scores, uint32_t* n_ops);
+int64_t b2a_affine_fetch_ops(b2a_ctx* ctx, uint64_t pair, char* ops, uint64_t ops_cap);
 /* The loop hw3.cpp:231-251 itself over one sequence set: pairs (i, j), i < j, in the reference's
  * row-major order; this call serves pairs [pair_first, pair_first + pair_count) of that order (so the
  * n(n-1)/2 pairs can be sharded over GPUs), writes their scores, the star sums sum_scores[n_seqs]

@@ -275,3 +275,52 @@ int orc_hw4_nw(const uint8_t* s1, uint32_t m, const uint8_t* s2, uint32_t n, int
     free(dp); free(tb);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * hw3's affine_alignment WITH its traceback (/root/reference/Multiple_Sequence_Alignment/hw3.cpp:23-135).
+ * Full V/F/E + trace matrices, so for test sizes only.  ops in traceback order, hw2's letters:
+ * 'M' column of two bases (state V), 'D' string1 base over '-' (state F), 'I' '-' over string2 base (state E).
+ * ------------------------------------------------------------------------------------------------ */
+int orc_affine_align(const uint8_t* s1, uint32_t m, const uint8_t* s2, uint32_t n, int match, int mismatch,
+                     int gopen, int gext, int32_t* score, uint32_t* n_ops, uint8_t* ops)
+{
+    const int32_t NEG = INT32_MIN / 2;
+    size_t W = (size_t)n + 1, cells = (size_t)(m + 1) * W;
+    int32_t* V = (int32_t*)malloc(sizeof(int32_t) * cells * 3);
+    int8_t*  T = (int8_t*)malloc(cells * 3);
+    if (!V || !T) { free(V); free(T); return -1; }
+    int32_t *F = V + cells, *E = V + 2 * cells;
+    int8_t *tV = T, *tF = T + cells, *tE = T + 2 * cells;
+    for (size_t k = 0; k < cells; ++k) { V[k] = F[k] = E[k] = NEG; tV[k] = tF[k] = tE[k] = -1; }      /* hw3.cpp:28-37 */
+    V[0] = 0;                                                                                          /* hw3.cpp:40 */
+    for (uint32_t i = 1; i <= m; ++i) { F[i * W] = gopen + gext * (int32_t)(i - 1); tF[i * W] = i == 1 ? 0 : 1; }   /* :42-47 */
+    for (uint32_t j = 1; j <= n; ++j) { E[j] = gopen + gext * (int32_t)(j - 1); tE[j] = j == 1 ? 0 : 1; }           /* :48-53 */
+    for (uint32_t i = 1; i <= m; ++i)
+        for (uint32_t j = 1; j <= n; ++j) {                                                            /* hw3.cpp:55-84 */
+            size_t c = i * W + j, d = (i - 1) * W + j - 1, u = (i - 1) * W + j, l = i * W + j - 1;
+            int s = s1[i - 1] == s2[j - 1] ? match : mismatch;
+            V[c] = V[d] + s; tV[c] = 0;
+            if (F[d] + s > V[c]) { V[c] = F[d] + s; tV[c] = 1; }
+            if (E[d] + s > V[c]) { V[c] = E[d] + s; tV[c] = 2; }
+            F[c] = V[u] + gopen + gext; tF[c] = 0;
+            if (F[u] + gext > F[c]) { F[c] = F[u] + gext; tF[c] = 1; }
+            E[c] = V[l] + gopen + gext; tE[c] = 0;
+            if (E[l] + gext > E[c]) { E[c] = E[l] + gext; tE[c] = 1; }
+        }
+    size_t end = (size_t)m * W + n;
+    int state = 0; int32_t best = V[end];                                                              /* hw3.cpp:86-98 */
+    if (F[end] > best) { best = F[end]; state = 1; }
+    if (E[end] > best) { best = E[end]; state = 2; }
+    if (score) *score = best;
+    uint32_t i = m, j = n, k = 0;
+    while (i > 0 || j > 0) {                                                                           /* hw3.cpp:105-131 */
+        size_t c = (size_t)i * W + j;
+        if (state == 0) { int prev = tV[c]; if (ops) ops[k] = 'M'; ++k; --i; --j; state = prev; }
+        else if (state == 1) { state = tF[c] == 0 ? 0 : 1; if (ops) ops[k] = 'D'; ++k; --i; }
+        else { state = tE[c] == 0 ? 0 : 2; if (ops) ops[k] = 'I'; ++k; --j; }
+        if (k > m + n) break;                                                                          /* (the reference would run off the matrix) */
+    }
+    if (n_ops) *n_ops = k;
+    free(V); free(T);
+    return 0;
+}

@@ -39,6 +39,7 @@ def lib():
         _lib.orc_mdz.restype = C.c_size_t
         _lib.orc_affine_score.restype = C.c_int
         _lib.orc_hw4_nw.restype = C.c_int
+        _lib.orc_affine_align.restype = C.c_int
     return _lib
 
 
@@ -92,6 +93,32 @@ def affine_score(s1: bytes, s2: bytes, match, mismatch, gopen, gext) -> int:
     if rc != 0:
         raise RuntimeError(f"orc_affine_score rc={rc}")
     return out.value
+
+
+def affine_align(s1: bytes, s2: bytes, match, mismatch, gopen, gext):
+    """hw3's affine_alignment with traceback: (score, ops in traceback order)."""
+    L = lib()
+    score, nops = C.c_int32(), C.c_uint32()
+    ops = C.create_string_buffer(len(s1) + len(s2) + 2)
+    rc = L.orc_affine_align(s1, C.c_uint32(len(s1)), s2, C.c_uint32(len(s2)), C.c_int(match), C.c_int(mismatch),
+                            C.c_int(gopen), C.c_int(gext), C.byref(score), C.byref(nops), ops)
+    if rc != 0:
+        raise RuntimeError(f"orc_affine_align rc={rc}")
+    return score.value, ops.raw[:nops.value]
+
+
+def aligned_rows(ops: bytes, s1: bytes, s2: bytes):
+    """(alignmentString1, alignmentString2) of hw3.cpp:100-135 from an op list in traceback order"""
+    a, b = bytearray(), bytearray()
+    i = j = 0
+    for op in reversed(ops):
+        if op == 0x4D:
+            a.append(s1[i]); b.append(s2[j]); i += 1; j += 1
+        elif op == 0x44:
+            a.append(s1[i]); b.append(0x2D); i += 1
+        else:
+            a.append(0x2D); b.append(s2[j]); j += 1
+    return bytes(a), bytes(b)
 
 
 def hw4_nw(s1: bytes, s2: bytes, match, mismatch, gap):

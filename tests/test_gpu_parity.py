@@ -417,3 +417,30 @@ def test_config2_full_size_one_million_pairs(eng):
         for k in range(0, n_pairs, 99991):
             a = ob.align(mode, P[k].tobytes(), T[k].tobytes(), 1, -1, -1)
             assert (int(res["score"][k]), int(res["overlap"][k]), pkg.unpack_ops(words, off, k, res["n_ops"][k])) == (a.score, a.overlap, a.ops)
+
+
+# ---------------- hw3 traceback: affine alignment with ops ----------------
+def test_affine_alignments_equal_hw3_golden_and_oracle(eng):
+    from test_oracle import HW3_KAT, parse_phy
+    by = {}
+    for c in HW3_KAT["pairs"]:
+        by.setdefault(tuple(c["s"]), []).append(c)
+    for s, cases in by.items():
+        ps = [c["seqs"][0].encode() for c in cases]
+        ts = [c["seqs"][1].encode() for c in cases]
+        sc, ops = eng.affine_align(ps, ts, *s)
+        for k, c in enumerate(cases):
+            (_, a1), (_, a2) = parse_phy(c["phy"])
+            assert ob.aligned_rows(ops[k], ps[k], ts[k]) == (a1.encode(), a2.encode()), c
+    rng = random.Random(61)
+    for alpha in (b"ACGT", b"AC", b"ACDEFGHIKLMNPQRSTVWY"):
+        ps, ts = [], []
+        for m, n in ((1, 1), (1, 40), (40, 1), (127, 128), (129, 130), (300, 270), (700, 900), (1300, 1100), (5, 2000), (1500, 60), (0, 5), (5, 0), (0, 0)):
+            t = rnd(rng, n, alpha)
+            ps.append((mutate(rng, t, alpha=alpha) + rnd(rng, m, alpha))[:m]); ts.append(t)
+        ps += [(b"ACGTA" * 500)[:2010], (b"AC" * 600)[:1111]]; ts += [(b"ACGTACG" * 300)[:2000], (b"A" * 1200)]      # tie stress
+        for s in ((5, -4, -16, -4), (1, -1, -2, -1), (2, -3, -5, -2), (3, -1, 0, -2), (4, -6, -10, 0)):
+            sc, ops = eng.affine_align(ps, ts, *s)
+            for k in range(len(ps)):
+                want_score, want_ops = ob.affine_align(ps[k], ts[k], *s)
+                assert (int(sc[k]), ops[k]) == (want_score, want_ops), (alpha, len(ps[k]), len(ts[k]), s)

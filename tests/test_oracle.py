@@ -193,3 +193,13 @@ def test_hw4_restatement_live_against_reference_binary(tmp_path):
         subprocess.check_call([ob.REF_HW4, "-i", str(tmp_path / "in.fa"), "-t", str(tmp_path / "t.txt"), "-s", *map(str, s)])
         _, dist, _ = ob.hw4_nw(a, b, *s)
         assert (tmp_path / "t.txt").read_text() == "(x:%f,y:%f):0.0;\n" % (dist / 2.0, dist / 2.0), (a, b, s)
+
+
+def test_affine_traceback_restatement_equals_hw3_alignments_golden():
+    """Two-sequence outputs of the unmodified hw3: the PHYLIP rows ARE alignmentString1/2 of affine_alignment(centre, other)."""
+    for c in HW3_KAT["pairs"]:
+        s1, s2 = (x.encode() for x in c["seqs"])
+        score, ops = ob.affine_align(s1, s2, *c["s"])
+        (_, a1), (_, a2) = parse_phy(c["phy"])
+        assert ob.aligned_rows(ops, s1, s2) == (a1.encode(), a2.encode()), c
+        assert score == ob.affine_score(s1, s2, *c["s"]) == alignment_score(a1, a2, *c["s"])
