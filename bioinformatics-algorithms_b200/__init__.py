@@ -17,6 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb2align.so")
 HW2_BIN = os.path.join(HERE, "bin", "hw2")
+HW3_BIN = os.path.join(HERE, "bin", "hw3")
 HW4_BIN = os.path.join(HERE, "bin", "hw4")
 
 GLOBAL, LOCAL = 0, 1
@@ -31,7 +32,7 @@ RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<u4"), ("end_j", "<u4"), (
 EXPORTS = ["b2a_device_count", "b2a_create", "b2a_destroy", "b2a_last_error", "b2a_host_alloc", "b2a_host_free",
            "b2a_align_batch", "b2a_affine_score_batch", "b2a_affine_align_batch", "b2a_affine_fetch_ops", "b2a_affine_star_scores", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
            "b2a_batch_download", "b2a_batch_times", "b2a_set_option", "b2a_batch_stats", "b2a_render_cigar", "b2a_render_mdz", "b2a_select_best",
-           "b2a_upgma_newick",
+           "b2a_upgma_newick", "b2a_center_star_phylip",
            "b2a_microbench_int16x2", "b2a_debug_copy_record"]
 
 
@@ -80,6 +81,8 @@ def load_library():
         lib.b2a_render_mdz.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, P, C.c_uint64]
         lib.b2a_select_best.restype = C.c_int64
         lib.b2a_select_best.argtypes = [C.c_int32, P, C.c_uint64]
+        lib.b2a_center_star_phylip.restype = C.c_int64
+        lib.b2a_center_star_phylip.argtypes = [C.c_uint32, C.c_uint32, P, P, P, P, P, P, C.c_uint64]
         lib.b2a_upgma_newick.restype = C.c_int64
         lib.b2a_upgma_newick.argtypes = [P, C.c_uint32, P, P, C.c_uint64]
         lib.b2a_microbench_int16x2.argtypes = [P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
@@ -326,6 +329,25 @@ class Engine:
 
     def localAlignmentSmithWaterman(self, patterns, references, matchScore, mismatchScore, gapPenalty):
         return self._one(LOCAL, patterns, references, matchScore, mismatchScore, gapPenalty)
+
+
+def center_star_phylip(names, seqs, centre, ops):
+    """hw3's output file (hw3.cpp:253-357) from the op lists of affine_alignment(seqs[centre], seqs[i]); ops[centre] is ignored."""
+    lib = load_library()
+    n = len(seqs)
+    enc = [x if isinstance(x, bytes) else x.encode() for x in names]
+    ops = [o if o is not None else b"" for o in ops]
+    name_arr = (C.c_char_p * n)(*enc)
+    seq_arr = (C.c_char_p * n)(*seqs)
+    ops_arr = (C.c_char_p * n)(*ops)
+    slen = np.array([len(s) for s in seqs], dtype=np.uint64)
+    olen = np.array([len(o) for o in ops], dtype=np.uint64)
+    cap = 64 + n * (sum(len(s) for s in seqs) * 12 // 10 + 64)
+    buf = C.create_string_buffer(cap)
+    k = lib.b2a_center_star_phylip(n, centre, name_arr, seq_arr, slen.ctypes.data, ops_arr, olen.ctypes.data, buf, cap)
+    if k < 0:
+        raise B2AError("b2a_center_star_phylip failed")
+    return buf.raw[:k].decode("latin-1")
 
 
 def upgma_newick(pair_dist, names):

@@ -1,10 +1,14 @@
 // b2a_host.cpp -- host-only pieces of the C ABI: result formatting and batch selection.
 // (prepareCigarString hw2.cpp:59-78, prepareMDZString hw2.cpp:80-116, selection hw2.cpp:326-357.)
 // Works on the op list in traceback order plus the raw sequences; no aligned strings are built.
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <string>
+#include <vector>
 
 #include "../../include/b2align.h"
 
@@ -79,9 +83,6 @@ int64_t b2a_select_best(int32_t mode, const b2a_result* results, uint64_t n_pair
 // behind the survivors, branch lengths printed with std::to_string (6 decimals).
 // Kept as an index list over one full matrix instead of rebuilding matrices per merge.
 // ---------------------------------------------------------------------------------------------
-#include <cmath>
-#include <limits>
-#include <vector>
 
 extern "C" int64_t b2a_upgma_newick(const int32_t* pair_dist, uint32_t n_seqs, const char* const* names, char* out, uint64_t cap)
 {
@@ -125,4 +126,75 @@ extern "C" int64_t b2a_upgma_newick(const int32_t* pair_dist, uint32_t n_seqs, c
     std::memcpy(out, tree.data(), tree.size());
     out[tree.size()] = 0;
     return (int64_t)tree.size();
+}
+
+// ---------------------------------------------------------------------------------------------
+// hw3's assembly stage (hw3.cpp:253-357): centre-star merge of the pairwise alignments + PHYLIP text.
+// Works on op lists (traceback order; 'M' centre base over other base, 'D' centre base over '-',
+// 'I' '-' over other base) instead of aligned strings: the gap pattern of pair i is the number of 'I'
+// columns in front of every centre base (hw3.cpp:270-277), the merged pattern is the per-position
+// maximum (hw3.cpp:284-289), and every row is written block by block: pair i's own inserted bases
+// first, then padding '-' up to the merged width, then its column for the centre base -- which is what
+// the reference's character walk (hw3.cpp:303-325) produces for centre sequences without a literal '-'.
+// ---------------------------------------------------------------------------------------------
+extern "C" int64_t b2a_center_star_phylip(uint32_t n_seqs, uint32_t centre, const char* const* names,
+                                          const uint8_t* const* seqs, const uint64_t* seq_len,
+                                          const char* const* ops, const uint64_t* n_ops, char* out, uint64_t cap)
+{
+    if (!out || cap == 0 || n_seqs == 0 || centre >= n_seqs || !names || !seqs || !seq_len || (n_seqs > 1 && (!ops || !n_ops))) return B2A_ERR_ARG;
+    const uint64_t L = seq_len[centre];
+    std::vector<std::vector<uint32_t>> gaps(n_seqs);                 // per pair: 'I' columns in front of centre position k (k = 0..L)
+    std::vector<uint32_t> merged(L + 1, 0);
+    for (uint32_t i = 0; i < n_seqs; ++i) {
+        if (i == centre) continue;
+        gaps[i].assign(L + 1, 0);
+        uint64_t pos = 0;
+        for (uint64_t t = n_ops[i]; t-- > 0;) {                      // alignment order = reverse traceback order
+            const char op = ops[i][t];
+            if (op == 'I') { if (pos > L) return B2A_ERR_ARG; ++gaps[i][pos]; }
+            else if (op == 'M' || op == 'D') ++pos;
+            else return B2A_ERR_ARG;
+        }
+        if (pos != L) return B2A_ERR_ARG;                            // the ops must consume the whole centre
+        for (uint64_t k = 0; k <= L; ++k) merged[k] = std::max(merged[k], gaps[i][k]);
+    }
+    std::vector<std::string> rows(n_seqs);
+    for (uint64_t k = 0; k <= L; ++k) {                              // centre row, hw3.cpp:293-299
+        rows[centre].append(merged[k], '-');
+        if (k < L) rows[centre].push_back((char)seqs[centre][k]);
+    }
+    for (uint32_t i = 0; i < n_seqs; ++i) {
+        if (i == centre) continue;
+        std::string& r = rows[i];
+        r.reserve(rows[centre].size());
+        uint64_t k = 0, q = 0, own = 0;                              // centre position, position in sequence i, inserted bases seen in this block
+        for (uint64_t t = n_ops[i]; t-- > 0;) {
+            const char op = ops[i][t];
+            if (op == 'I') { if (q >= seq_len[i]) return B2A_ERR_ARG; r.push_back((char)seqs[i][q++]); ++own; continue; }
+            r.append(merged[k] - own, '-');                          // pad the gap block of centre position k
+            if (op == 'M') { if (q >= seq_len[i]) return B2A_ERR_ARG; r.push_back((char)seqs[i][q++]); }
+            else r.push_back('-');
+            ++k; own = 0;
+        }
+        r.append(merged[L] - own, '-');                              // trailing block, hw3.cpp:320-324
+        if (q != seq_len[i]) return B2A_ERR_ARG;
+    }
+    // hw3.cpp:330-331: the centre trades places with the first sequence; hw3.cpp:339-357: 10-char id, blocks of 10
+    std::vector<uint32_t> order(n_seqs);
+    for (uint32_t i = 0; i < n_seqs; ++i) order[i] = i;
+    std::swap(order[0], order[centre]);
+    std::string text = std::to_string(n_seqs) + " " + std::to_string(rows[centre].size()) + "\n";
+    for (uint32_t o = 0; o < n_seqs; ++o) {
+        const uint32_t i = order[o];
+        std::string id = names[i] ? names[i] : "";
+        if (id.size() > 10) id.resize(10); else id.append(10 - id.size(), ' ');
+        text += id;
+        const std::string& r = rows[i];
+        for (size_t j = 0; j < r.size(); ++j) { if (j && j % 10 == 0) text.push_back(' '); text.push_back(r[j]); }
+        text.push_back('\n');
+    }
+    if (text.size() + 1 > cap) return B2A_ERR_ARG;
+    std::memcpy(out, text.data(), text.size());
+    out[text.size()] = 0;
+    return (int64_t)text.size();
 }

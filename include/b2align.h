@@ -174,6 +174,14 @@ int64_t b2a_select_best(int32_t mode, const b2a_result* results, uint64_t n_pair
  * newline ("(...):0.0;").  Host only.  Returns the length or <0 (buffer too small / bad argument). */
 int64_t b2a_upgma_newick(const int32_t* pair_dist, uint32_t n_seqs, const char* const* names, char* out, uint64_t cap);
 
+/* ---- hw3's assembly stage: centre-star merge + PHYLIP text (hw3.cpp:253-357) ------------------------------- */
+/* ops[i] / n_ops[i] (ignored for i == centre): the op list of affine_alignment(seqs[centre], seqs[i]) in traceback
+ * order as b2a_affine_fetch_ops returns it.  Writes the whole file hw3 writes (header line, one row per sequence with
+ * the centre first, 10-character ids, blocks of 10).  Host only.  Returns the length or <0. */
+int64_t b2a_center_star_phylip(uint32_t n_seqs, uint32_t centre, const char* const* names,
+                               const uint8_t* const* seqs, const uint64_t* seq_len,
+                               const char* const* ops, const uint64_t* n_ops, char* out, uint64_t cap);
+
 /* ---- measurement helper: sustained issue rate of the packed int16x2 DPX instructions ------- */
 /* Runs the microbenchmark kernel on ctx's device; *gops = 1e9 lane-instructions/s sustained by
  * kind 0: VIADDMNMX.S16x2 only, 1: the fill kernel's ALU mix, 2: ALU mix + IMAD (both pipes). */

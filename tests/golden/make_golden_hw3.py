@@ -63,7 +63,12 @@ def main():
         seqs = [mutate(rng, base, b"ACGT", rng.randint(0, 15)) for _ in range(k)]
         sc = rng.choice(scorings)
         stars.append({"seqs": [s.decode() for s in seqs], "s": list(sc), "phy": run_hw3(seqs, sc)})
-    out = {"generator": "tests/golden/make_golden_hw3.py over oracle/_ref/hw3 (unmodified reference)", "pairs": pairs, "stars": stars}
+    ship = os.path.join("/root/reference", "Multiple_Sequence_Alignment")
+    shipped = {"fasta": open(os.path.join(ship, "input.fasta")).read(), "phy": open(os.path.join(ship, "output.phy")).read(), "s": [5, -4, -16, -4]}
+    with tempfile.TemporaryDirectory() as td:      # the shipped golden must be what the binary writes today
+        subprocess.check_call([HW3, "-i", os.path.join(ship, "input.fasta"), "-o", os.path.join(td, "o.phy"), "-s", "5:-4:-16:-4"], stdout=subprocess.DEVNULL)
+        assert open(os.path.join(td, "o.phy")).read() == shipped["phy"]
+    out = {"generator": "tests/golden/make_golden_hw3.py over oracle/_ref/hw3 (unmodified reference)", "pairs": pairs, "stars": stars, "shipped": shipped}
     json.dump(out, open(os.path.join(ROOT, "tests", "golden", "hw3_kat.json"), "w"), indent=0)
     print("wrote", len(pairs), "pair vectors and", len(stars), "star vectors")
 

@@ -153,3 +153,40 @@ def test_hw4_cli_error_paths_match_reference(tmp_path):
     for binary, name in ((ref, "r.txt"), (pkg.HW4_BIN, "m.txt")):
         subprocess.check_call([binary, "-i", str(tmp_path / "in.fa"), "-t", str(tmp_path / name), "-s", "1", "-1", "-1"])
     assert (tmp_path / "r.txt").read_bytes() == (tmp_path / "m.txt").read_bytes() == b"a:0.0;\n"
+
+
+def test_center_star_phylip_reproduces_files_written_by_the_reference():
+    """b2a_center_star_phylip (host only) on oracle op lists == the file the unmodified hw3 binary wrote (hw3.cpp:231-357)."""
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "hw3_kat.json")))
+    for c in kat["stars"] + kat["pairs"]:
+        seqs = [s.encode() for s in c["seqs"]]
+        k = len(seqs)
+        sums = [0] * k
+        for i in range(k):
+            for j in range(i + 1, k):
+                v = ob.affine_score(seqs[i], seqs[j], *c["s"])
+                sums[i] += v; sums[j] += v
+        centre = max(range(k), key=lambda i: (sums[i], -i))
+        ops = [None if i == centre else ob.affine_align(seqs[centre], seqs[i], *c["s"])[1] for i in range(k)]
+        assert pkg.center_star_phylip(["s%d" % i for i in range(k)], seqs, centre, ops) == c["phy"], c
+
+
+def test_hw3_cli_messages_match_reference(tmp_path):
+    """usage / unknown argument / bad score string / missing input / no or one sequence: same stdout, exit code and files."""
+    ref = ob.REF_HW3
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/hw3 not built")
+    (tmp_path / "one.fa").write_text("junk before\n>a b\nAC GT\nTT\n")
+    (tmp_path / "none.fa").write_text("ACGT\n\n")
+    cases = [[], ["-i", "x"], ["-i", "one.fa", "-q", "o.phy", "-s", "1:2:3:4"], ["-i", "one.fa", "-o", "o.phy", "-s", "1:2:3"],
+             ["-i", "nope.fa", "-o", "o.phy", "-s", "5:-4:-16:-4"], ["-i", "none.fa", "-o", "o.phy", "-s", "5:-4:-16:-4"],
+             ["-i", "one.fa", "-o", "o.phy", "-s", "5:-4:-16:-4"]]
+    for args in cases:
+        outs = []
+        for binary in (ref, pkg.HW3_BIN):
+            if (tmp_path / "o.phy").exists():
+                (tmp_path / "o.phy").unlink()
+            p = subprocess.run([binary] + args, capture_output=True, text=True, cwd=tmp_path)
+            body = (tmp_path / "o.phy").read_bytes() if (tmp_path / "o.phy").exists() else None
+            outs.append((p.returncode, p.stdout.replace(binary, "hw3"), p.stderr, body))
+        assert outs[0] == outs[1], (args, outs)

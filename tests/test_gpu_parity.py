@@ -444,3 +444,27 @@ def test_affine_alignments_equal_hw3_golden_and_oracle(eng):
             for k in range(len(ps)):
                 want_score, want_ops = ob.affine_align(ps[k], ts[k], *s)
                 assert (int(sc[k]), ops[k]) == (want_score, want_ops), (alpha, len(ps[k]), len(ts[k]), s)
+
+
+def test_hw3_cli_byte_exact(eng, tmp_path):
+    """bin/hw3 against files written by the unmodified hw3 (tests/golden/hw3_kat.json) incl. a reconstruction of the shipped run."""
+    from test_oracle import HW3_KAT
+    (tmp_path / "input.fasta").write_text(HW3_KAT["shipped"]["fasta"])          # the reference's own fixture: input.fasta -> output.phy
+    subprocess.check_call([pkg.HW3_BIN, "-i", "input.fasta", "-o", "output.phy", "-s", "5:-4:-16:-4"], cwd=tmp_path)
+    assert (tmp_path / "output.phy").read_text() == HW3_KAT["shipped"]["phy"]
+    for c in HW3_KAT["stars"][:14] + HW3_KAT["pairs"][:10]:
+        (tmp_path / "in.fa").write_text("".join(">s%d\n%s\n" % (i, s) for i, s in enumerate(c["seqs"])))
+        subprocess.check_call([pkg.HW3_BIN, "-i", "in.fa", "-o", "out.phy", "-s", "%d:%d:%d:%d" % tuple(c["s"])], cwd=tmp_path)
+        assert (tmp_path / "out.phy").read_text() == c["phy"], c
+    if os.path.exists(ob.REF_HW3):                      # live: longer, multi-band sequences with wrapped FASTA lines
+        rng = random.Random(71)
+        base = rnd(rng, 1500)
+        seqs = [mutate(rng, base, psub=0.1, pindel=0.03) for _ in range(6)]
+        with open(tmp_path / "big.fa", "wb") as f:
+            for i, s in enumerate(seqs):
+                f.write(b">seq_number_%d long header\n" % i)
+                for k in range(0, len(s), 70):
+                    f.write(s[k:k + 70] + b"\n")
+        for binary, name in ((ob.REF_HW3, "ref.phy"), (pkg.HW3_BIN, "mine.phy")):
+            subprocess.check_call([binary, "-i", "big.fa", "-o", name, "-s", "5:-4:-16:-4"], cwd=tmp_path)
+        assert (tmp_path / "ref.phy").read_bytes() == (tmp_path / "mine.phy").read_bytes()
