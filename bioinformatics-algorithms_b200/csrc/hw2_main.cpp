@@ -8,9 +8,11 @@
 // one host thread + context per device, host-side first-index arg-max).  No CPU alignment path:
 // without a usable GPU the program says so on stderr and exits 1.
 #include <cctype>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <string>
@@ -30,22 +32,43 @@ struct FastaBatch {                      // sequences only, concatenated, with o
 
 // hw2.cpp:25-57 semantics: trailing CR/whitespace stripped per line, blank lines skipped, '>' lines
 // flush the current record only if it is non-empty, everything else is appended verbatim.
+// The file is read in one piece and scanned with memchr (a 1 GB text file parses in ~0.4 s; getline took 1.2 s).
 bool load_fasta(const std::string& path, FastaBatch& out)
 {
-    std::ifstream in(path.c_str(), std::ios::binary);
-    if (!in) return false;
-    std::string line;
-    bool open_record = false;            // bytes appended since the last flush
-    while (std::getline(in, line)) {
-        size_t e = line.size();
-        while (e > 0 && (line[e - 1] == '\r' || std::isspace((unsigned char)line[e - 1]))) --e;
-        if (e == 0) continue;
-        if (line[0] == '>') {
-            if (open_record) { out.off.push_back(out.bytes.size()); open_record = false; }
-        } else {
-            out.bytes.insert(out.bytes.end(), line.begin(), line.begin() + e);
-            open_record = true;
+    std::FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::vector<char> buf;
+    if (std::fseek(f, 0, SEEK_END) == 0) {
+        const long sz = std::ftell(f);
+        std::rewind(f);
+        if (sz > 0) buf.resize((size_t)sz);
+    }
+    size_t got = buf.empty() ? 0 : std::fread(buf.data(), 1, buf.size(), f);
+    if (got == buf.size()) {                                 // pipes / growing files: keep reading
+        char tmp[1 << 16];
+        size_t k;
+        while ((k = std::fread(tmp, 1, sizeof tmp, f)) > 0) { buf.insert(buf.end(), tmp, tmp + k); got += k; }
+    }
+    std::fclose(f);
+    buf.resize(got);
+    out.bytes.reserve(out.bytes.size() + got);
+    bool open_record = false;                                // bytes appended since the last flush
+    const char* p = buf.data();
+    const char* const end = p + got;
+    while (p < end) {
+        const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+        const char* stop = nl ? nl : end;
+        const char* e = stop;
+        while (e > p && (e[-1] == '\r' || std::isspace((unsigned char)e[-1]))) --e;
+        if (e > p) {
+            if (*p == '>') {
+                if (open_record) { out.off.push_back(out.bytes.size()); open_record = false; }
+            } else {
+                out.bytes.insert(out.bytes.end(), p, e);
+                open_record = true;
+            }
         }
+        p = nl ? nl + 1 : end;
     }
     if (open_record) out.off.push_back(out.bytes.size());
     return true;
@@ -78,13 +101,26 @@ int main(int argc, char** argv)
         else if (a == "-s" && i + 3 < argc) { match = std::atoi(argv[++i]); mismatch = std::atoi(argv[++i]); gap = std::atoi(argv[++i]); }
     }
 
+    const bool timing = std::getenv("HW2_TIMING") != nullptr;           // phase times on stderr (not part of the drop-in contract)
+    const auto t_start = std::chrono::steady_clock::now();
+    auto stamp = [&](const char* what) {
+        if (timing) std::fprintf(stderr, "[hw2 timing] %-28s %8.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+    };
+    // (creating the CUDA contexts in the background while the FASTA files are parsed was measured: no gain, more variance)
     FastaBatch pats, txts;
-    if (!load_fasta(pattern_path, pats)) { std::cerr << "Error: Cannot open file " << pattern_path << std::endl; return 1; }
-    if (!load_fasta(text_path, txts))    { std::cerr << "Error: Cannot open file " << text_path << std::endl; return 1; }
+    bool ok_p = false, ok_t = false;
+    {
+        std::thread tp([&]() { ok_p = load_fasta(pattern_path, pats); });       // the two files are independent
+        ok_t = load_fasta(text_path, txts);
+        tp.join();
+    }
+    if (!ok_p) { std::cerr << "Error: Cannot open file " << pattern_path << std::endl; return 1; }
+    if (!ok_t) { std::cerr << "Error: Cannot open file " << text_path << std::endl; return 1; }
     if (pats.count() != txts.count()) {
         std::cerr << "Error: Number of patterns and references do not match." << std::endl;
         return 1;
     }
+    stamp("FASTA loaded");
     const uint64_t n_pairs = pats.count();
     const int mode = global ? B2A_MODE_GLOBAL : B2A_MODE_LOCAL;       // -g wins when both are given (hw2.cpp:331)
 
@@ -116,6 +152,7 @@ int main(int argc, char** argv)
             });
         }
         for (auto& t : th) t.join();
+        stamp("aligned");
         for (int d = 0; d < ndev; ++d)
             if (shards[d].rc != B2A_OK) {
                 std::cerr << "Error: alignment engine failed: " << shards[d].err << std::endl;
@@ -140,9 +177,10 @@ int main(int argc, char** argv)
                            r.start_i, r.start_j, buf.data(), buf.size());
             mdz = buf.data();
         }
+        stamp("winner rendered");
         for (b2a_ctx* c : ctxs) b2a_destroy(c);
+        stamp("contexts destroyed");
     }
-
     std::ofstream out(out_path.c_str(), std::ios::binary);
     if (!out) { std::cerr << "Error: Cannot open output file " << out_path << std::endl; return 1; }
     if ((global || local) && best >= 0) {
@@ -154,5 +192,6 @@ int main(int argc, char** argv)
             << "MD:Z=" << mdz << '\n';
     }
     out.close();
+    stamp("done");
     return 0;
 }
