@@ -7,6 +7,7 @@
 // include/b2align.h to the sm_100a kernels, sharded over every visible GPU (contiguous pair ranges,
 // one host thread + context per device, host-side first-index arg-max).  No CPU alignment path:
 // without a usable GPU the program says so on stderr and exits 1.
+#include <algorithm>
 #include <cctype>
 #include <chrono>
 #include <cstdint>
@@ -128,9 +129,17 @@ int main(int argc, char** argv)
     int64_t best = -1;
     std::string cigar, mdz;
     if (n_pairs > 0) {
+        // A CUDA context costs ~1 s to create, initialising the driver for 8 visible GPUs several seconds, and one GPU fills
+        // > 5e12 cells per second: another device only pays for itself from ~1e12 cells per device on (measured: a 16 x 100 kb
+        // hw3 run took 2.7 s on a 1-GPU box and 9 s on an 8-GPU box).  A job that needs one device is shown one device.
+        double cells = 0;
+        for (uint64_t k = 0; k < n_pairs; ++k) cells += (double)(pats.off[k + 1] - pats.off[k]) * (double)(txts.off[k + 1] - txts.off[k]);
+        const bool all_gpus = std::getenv("B2A_ALL_GPUS") != nullptr;
+        if (!all_gpus && cells < 2e12) setenv("CUDA_VISIBLE_DEVICES", "0", 0);       // no-op if the user set it
         int ndev = b2a_device_count();
         if (ndev <= 0) { std::cerr << "Error: no usable CUDA device (this build has no CPU alignment path)" << std::endl; return 1; }
         if ((uint64_t)ndev > n_pairs) ndev = (int)n_pairs;
+        if (!all_gpus) ndev = (int)std::max(1.0, std::min((double)ndev, cells / 1e12));
         std::vector<Shard> shards(ndev);
         std::vector<b2a_ctx*> ctxs(ndev, nullptr);
         std::vector<std::thread> th;

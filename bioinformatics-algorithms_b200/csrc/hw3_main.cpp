@@ -8,6 +8,7 @@
 // ABI, sharded over every visible device: the all-vs-all score-only distance stage (hw3.cpp:231-241 ->
 // b2a_affine_star_scores) and the centre-vs-others alignments with traceback (hw3.cpp:259-266 ->
 // b2a_affine_align_batch); the merge + PHYLIP text (hw3.cpp:253-357) is host code behind b2a_center_star_phylip.
+#include <algorithm>
 #include <cctype>
 #include <cstdint>
 #include <cstdlib>
@@ -68,8 +69,15 @@ int main(int argc, char** argv)
         return 0;
     }
 
+    // a CUDA context costs ~1 s, driver initialisation for 8 visible GPUs several seconds; one GPU does ~2.5e12 affine cells
+    // per second: spread out only from ~1e12 cells per device on, and show a one-device job one device
+    double cells = 0;
+    for (uint32_t i = 0; i < n; ++i) for (uint32_t j = i + 1; j < n; ++j) cells += (double)seqs[i].size() * (double)seqs[j].size();
+    const bool all_gpus = std::getenv("B2A_ALL_GPUS") != nullptr;
+    if (!all_gpus && cells < 2e12) setenv("CUDA_VISIBLE_DEVICES", "0", 0);           // no-op if the user set it
     int ndev = b2a_device_count();
     if (ndev <= 0) { std::cout << "Error: no usable CUDA device (this build has no CPU alignment path)" << std::endl; return 1; }
+    if (!all_gpus) ndev = (int)std::max(1.0, std::min((double)ndev, cells / 1e12));
     std::vector<uint8_t> all;
     std::vector<uint64_t> off{0};
     for (const std::string& s : seqs) { all.insert(all.end(), s.begin(), s.end()); off.push_back(all.size()); }

@@ -6,6 +6,7 @@
 // (hw4.cpp:137-159: n(n-1)/2 Needleman-Wunsch alignments with hw4's own tie order d > u > l, distance =
 // mismatch + gap columns) runs on the GPUs through the C ABI (B2A_TIE_HW4), pair-sharded over every visible
 // device; UPGMA + Newick (hw4.cpp:162-237) is host code behind b2a_upgma_newick.  No CPU alignment path.
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -63,9 +64,16 @@ int main(int argc, char** argv)
     const uint64_t n_pairs = po.size() - 1;
     std::vector<b2a_result> results(n_pairs);
     if (n_pairs > 0) {
+        // a CUDA context costs ~1 s, driver initialisation for 8 visible GPUs several seconds: spread out only from ~1e12
+        // cells per device on, and show a one-device job one device
+        double cells = 0;
+        for (uint64_t k = 0; k < n_pairs; ++k) cells += (double)(po[k + 1] - po[k]) * (double)(to[k + 1] - to[k]);
+        const bool all_gpus = std::getenv("B2A_ALL_GPUS") != nullptr;
+        if (!all_gpus && cells < 2e12) setenv("CUDA_VISIBLE_DEVICES", "0", 0);       // no-op if the user set it
         int ndev = b2a_device_count();
         if (ndev <= 0) { std::cerr << "Error: no usable CUDA device (this build has no CPU alignment path)" << std::endl; return 1; }
         if ((uint64_t)ndev > n_pairs) ndev = (int)n_pairs;
+        if (!all_gpus) ndev = (int)std::max(1.0, std::min((double)ndev, cells / 1e12));
         std::vector<int> rc(ndev, 0);
         std::vector<std::string> err(ndev);
         std::vector<std::thread> th;
