@@ -468,3 +468,18 @@ def test_hw3_cli_byte_exact(eng, tmp_path):
         for binary, name in ((ob.REF_HW3, "ref.phy"), (pkg.HW3_BIN, "mine.phy")):
             subprocess.check_call([binary, "-i", "big.fa", "-o", name, "-s", "5:-4:-16:-4"], cwd=tmp_path)
         assert (tmp_path / "ref.phy").read_bytes() == (tmp_path / "mine.phy").read_bytes()
+
+
+def test_short16_long_texts_through_the_ring(eng):
+    """texts far longer than the 128-column score-table ring (and than the former 6000-column table limit), all on the s16x2 path"""
+    rng = random.Random(81)
+    ps, ts = [], []
+    for m, n in ((150, 20000), (150, 20000), (256, 7000), (33, 29999), (1, 9000), (200, 129), (200, 127), (64, 128)):
+        t = rnd(rng, n)
+        k = rng.randrange(0, max(1, n - m))
+        ps.append((mutate(rng, t[k:k + m]) + rnd(rng, m))[:m]); ts.append(t)
+    ps.append((b"ACGTA" * 60)[:256]); ts.append((b"ACGTA" * 3000)[:15000])          # ties all along a long text
+    for mode in (pkg.GLOBAL, pkg.LOCAL):
+        check_batch(eng, mode, ps, ts, (1, -1, -1), expect_path=1)
+    res, _ = check_batch(eng, pkg.LOCAL, ps, ts, (2, -3, -4))                          # 4-bit deltas; SW needs no bias, so it stays on short16
+    assert {int(x) for x in res["path"]} == {1}
