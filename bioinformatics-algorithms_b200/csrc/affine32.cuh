@@ -59,11 +59,14 @@ __device__ __forceinline__ uint32_t affine_code(int32_t v, int32_t f, int32_t e,
 constexpr int AFF_UNROLL = AFFINE_UNROLL;
 constexpr int32_t AFFINE_NEG = INT32_MIN / 2;        // hw3.cpp:16
 
-template <bool ALPHA4, bool TRACE>
+// R rows per lane: 4 with TRACE (the codes of 4 rows x 32 steps already take 16 registers), 8 for score-only runs, where the
+// per-step overhead (3 shuffles, ring read, boundary staging) is then shared by twice the cells (+20 % on the 120-pair batch).
+constexpr int AFFINE_R_SCORE = 8;
+
+template <bool ALPHA4, bool TRACE, int R>
 __global__ void __launch_bounds__(WIDE_WARPS * 32)
 affine32_score_kernel(const AffineArgs A)
 {
-    constexpr int R = WIDE_R;
     __shared__ uint4 s_ring[WIDE_WARPS][64];       // per 1-based column j (slot j & 63): {text entry, Vg, F, M3 of the row above the band}
     __shared__ uint4 s_out[WIDE_WARPS][32];        // {Vg, F, M3} of the band's bottom row, produced by lane 31 during the current block
     __shared__ uint32_t s_tbl4[256];

@@ -547,7 +547,8 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
             if (sp.m == 0 || sp.n == 0) continue;           // borders only: answered on the host below
             WidePair p{};
             p.pat_off = sp.pat_off; p.txt_off = sp.txt_off; p.m = sp.m; p.n = sp.n; p.pair = (uint32_t)k;
-            p.nbands = (sp.m + 32u * WIDE_R - 1u) / (32u * WIDE_R);
+            const uint32_t band_rows = 32u * (uint32_t)(trace ? WIDE_R : AFFINE_R_SCORE);
+            p.nbands = (sp.m + band_rows - 1u) / band_rows;
             const uint64_t need = trace ? (uint64_t)p.nbands * WIDE_R * ((sp.n + 63u) / 32u) * 32u : 0;
             if (trace && !W.pairs.empty() && W.chunks + need > code_budget_chunks) break;
             p.code_off = W.chunks; W.chunks += need;
@@ -581,10 +582,10 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
             const unsigned need = (unsigned)((W.tasks.size() + WIDE_WARPS - 1) / WIDE_WARPS);
             const unsigned grid = std::min<unsigned>(need, (unsigned)ctx->sm_count * 8u);
             CU(cudaEventRecord(ctx->ev_begin, st));
-            if (trace) { if (alpha4) affine32_score_kernel<true, true><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
-                         else affine32_score_kernel<false, true><<<grid, WIDE_WARPS * 32, 0, st>>>(a); }
-            else       { if (alpha4) affine32_score_kernel<true, false><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
-                         else affine32_score_kernel<false, false><<<grid, WIDE_WARPS * 32, 0, st>>>(a); }
+            if (trace) { if (alpha4) affine32_score_kernel<true, true, WIDE_R><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
+                         else affine32_score_kernel<false, true, WIDE_R><<<grid, WIDE_WARPS * 32, 0, st>>>(a); }
+            else       { if (alpha4) affine32_score_kernel<true, false, AFFINE_R_SCORE><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
+                         else affine32_score_kernel<false, false, AFFINE_R_SCORE><<<grid, WIDE_WARPS * 32, 0, st>>>(a); }
             CU(cudaGetLastError()); ++launches;
             if (trace) {
                 AffineTbArgs ta{W.d_pairs.p, (uint32_t)W.pairs.size(), reinterpret_cast<const uint4*>(W.d_codes.p), ctx->d_nops.p, ctx->d_ops.p, ctx->d_ops_off.p};
