@@ -125,10 +125,9 @@ struct b2a_ctx {
     int device = 0;
     int sm_count = 0;
     int n_lanes = 1;
-    int exp_bits = 0;                             // B2A_EXP: experiment toggles
     bool trace = false;                           // B2A_TRACE=1: per-segment timeline of b2a_align_batch on stderr
     uint64_t seg_budget_bytes = 8ull << 30;       // record bytes per segment (B2A_SEG_MB overrides)
-    uint64_t seg_max_pairs = 1ull << 17;          // pairs per segment of b2a_align_batch (B2A_SEG_PAIRS overrides)
+    uint64_t seg_max_pairs = 98304;               // pairs per segment of b2a_align_batch (B2A_SEG_PAIRS overrides; swept in scripts/seg_e2e_sweep.py)
     uint64_t seg_first_pairs = 1ull << 14;        // its first segment (then doubling): the kernels start after a short copy
     uint64_t seg_resident_pairs = 1ull << 20;     // pairs per segment of b2a_batch_upload / b2a_batch_run ...
     uint64_t seg_resident_bytes = 60ull << 30;    // ... and its record bytes (a 1 M-pair batch with 4-bit deltas would need 110 GB)
@@ -682,7 +681,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
     CU(ctx->d_alpha.reserve(ctx->alpha_slots)); CU(ctx->h_alpha.reserve(ctx->alpha_slots));
     if (want_ops) { CU(ctx->d_ops.reserve(ops_bound)); CU(ctx->d_ops_off.reserve(n_pairs + 1)); }
     CU(cudaMemsetAsync(ctx->d_alpha.p, 0, ctx->alpha_slots * sizeof(AlphaInfo), ctx->s_copy));
-    const bool async_down = pipelined && results && is_pinned(results) && !(ctx->exp_bits & 1);
+    const bool async_down = pipelined && results && is_pinned(results);
     uint64_t launches = 0;
     using clk = std::chrono::steady_clock;
     const clk::time_point t_begin = clk::now();
@@ -928,7 +927,6 @@ b2a_ctx* b2a_create(int device) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = std::getenv("B2A_TB_OPT")) ctx->tb_opt = std::atoi(e);
-    if (const char* e = std::getenv("B2A_EXP")) ctx->exp_bits = std::atoi(e);
     if (const char* e = std::getenv("B2A_TRACE")) ctx->trace = std::atoi(e) != 0;
     if (const char* e = std::getenv("B2A_LANES")) ctx->n_lanes = std::max(1, std::min(MAX_LANES, std::atoi(e)));
     if (const char* e = std::getenv("B2A_SEG_MB")) ctx->seg_budget_bytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;
