@@ -243,9 +243,20 @@ cudaError_t launch_fill(int K, int R, bool local, const FillArgs& a, cudaStream_
 }
 cudaError_t launch_tb(int K, bool local, const TbArgs& a, cudaStream_t st) {
     const unsigned threads = TB_THREADS, grid = (2u * a.n_pp + threads - 1) / threads;
+    const unsigned pad = 0;
+    static const bool once = []() {            // the walk lives on L1 hits (measured: any shared-memory carve-out costs 2-4x): ask for all of it
+        cudaFuncSetAttribute(short16_traceback_kernel<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+        cudaFuncSetAttribute(short16_traceback_kernel<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+        cudaFuncSetAttribute(short16_traceback_kernel<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+        cudaFuncSetAttribute(short16_traceback_kernel<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+        cudaFuncSetAttribute(short16_traceback_kernel<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+        cudaFuncSetAttribute(short16_traceback_kernel<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+        return true;
+    }();
+    (void)once;
     switch (K * 2 + (local ? 1 : 0)) {
-        case 4:  short16_traceback_kernel<2, false><<<grid, threads, 0, st>>>(a); break;
-        case 5:  short16_traceback_kernel<2, true><<<grid, threads, 0, st>>>(a); break;
+        case 4:  short16_traceback_kernel<2, false><<<grid, threads, pad, st>>>(a); break;
+        case 5:  short16_traceback_kernel<2, true><<<grid, threads, pad, st>>>(a); break;
         case 8:  short16_traceback_kernel<4, false><<<grid, threads, 0, st>>>(a); break;
         case 9:  short16_traceback_kernel<4, true><<<grid, threads, 0, st>>>(a); break;
         case 16: short16_traceback_kernel<8, false><<<grid, threads, 0, st>>>(a); break;

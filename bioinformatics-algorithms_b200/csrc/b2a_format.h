@@ -110,6 +110,9 @@ B2A_HD bool short16_plan(int mode, uint32_t m, uint32_t n, int match, int mismat
     long bias = 0;
     if (mode == 0) bias = (rows + (long)n) * (long)(-gap) + margin;
     if (bias + top > 32767) return false;
+    // NW fill works on S = H - (i + j) gap + 32|gap| (short16_fill.cuh): frozen lanes run up to 31 columns past either end,
+    // and the score table holds s - 2 gap as int8
+    if (mode == 0 && (bias + top + 64L * (long)(-gap) > 32767 || smax - 2L * gap > 127 || smin - 2L * gap < -128)) return false;
     pl.bias = (int)bias;
     return true;
 }

@@ -20,6 +20,12 @@ __global__ void __launch_bounds__(256) microbench_kernel(uint32_t* out, int iter
         for (int c = 0; c < 8; ++c) {
             if (KIND == 0) {
                 h[c] = __viaddmax_s16x2(h[c], g, x);
+            } else if (KIND == 3) {
+                h[c] = __vmaxs2(h[c], x + it);                  // VIMNMX.S16x2 (plain packed max)
+            } else if (KIND == 4) {
+                h[c] = __vimax3_s16x2(h[c], x, g + it);         // VIMNMX3.S16x2
+            } else if (KIND == 5) {
+                h[c] = __vadd2(h[c], x);                        // VIADD.16x2
             } else {
                 uint32_t s;
                 asm("prmt.b32 %0, %1, %2, %3;" : "=r"(s) : "r"(h[c]), "r"(x), "r"(sel));
@@ -50,7 +56,10 @@ inline cudaError_t run_microbench(int kind, int sm_count, cudaStream_t st, doubl
         cudaEventRecord(a, st);
         if (kind == 0) microbench_kernel<0><<<blocks, threads, 0, st>>>(d, iters, 0xFFFFFFFFu, 0x5140u, 4u, 0x00100010u);
         else if (kind == 1) microbench_kernel<1><<<blocks, threads, 0, st>>>(d, iters, 0xFFFFFFFFu, 0x5140u, 4u, 0x00100010u);
-        else microbench_kernel<2><<<blocks, threads, 0, st>>>(d, iters, 0xFFFFFFFFu, 0x5140u, 4u, 0x00100010u);
+        else if (kind == 2) microbench_kernel<2><<<blocks, threads, 0, st>>>(d, iters, 0xFFFFFFFFu, 0x5140u, 4u, 0x00100010u);
+        else if (kind == 3) microbench_kernel<3><<<blocks, threads, 0, st>>>(d, iters, 0xFFFFFFFFu, 0x5140u, 4u, 0x00100010u);
+        else if (kind == 4) microbench_kernel<4><<<blocks, threads, 0, st>>>(d, iters, 0xFFFFFFFFu, 0x5140u, 4u, 0x00100010u);
+        else microbench_kernel<5><<<blocks, threads, 0, st>>>(d, iters, 0xFFFFFFFFu, 0x5140u, 4u, 0x00100010u);
         cudaEventRecord(b, st);
         e = cudaEventSynchronize(b);
         if (e != cudaSuccess) break;
@@ -58,7 +67,7 @@ inline cudaError_t run_microbench(int kind, int sm_count, cudaStream_t st, doubl
         if (rep > 0 && ms < best) best = ms;
     }
     if (e == cudaSuccess) e = cudaGetLastError();
-    const double alu_per_iter = kind == 0 ? 8.0 : 32.0;
+    const double alu_per_iter = (kind == 0 || kind >= 3) ? 8.0 : 32.0;
     *gops = (double)threads * blocks * iters * alu_per_iter / (best * 1e-3) / 1e9;
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);

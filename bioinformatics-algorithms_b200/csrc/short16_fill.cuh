@@ -12,6 +12,13 @@
 // and the FMA pipe one IMAD that folds the new H into the row's delta word (see b2a_format.h
 // encode_word: the word of horizontal deltas is a polynomial in the packed H values, evaluated in
 // 32-bit ring arithmetic, so no masking, shifting or compare instruction is spent on traceback data).
+// NW runs the recurrence on S = H - (i + j) * gap (+ const): both borders become one constant, "left + gap" and "up + gap"
+// become plain S values and the diagonal's -2*gap folds into the score table, so a packed cell pair costs
+//     PRMT   VIADDMNMX.S16x2 (max(diag + s', left))   VIMNMX.S16x2 (max(., up))
+// -- and the plain packed max issues at full rate, while VIADD.16x2 / VIADDMNMX / VIMNMX3 are half rate on sm_100
+// (scripts/mb.py).  Horizontal differences of S ARE the stored deltas, the anchor is converted back to H when a chunk
+// is stored: the record is bit-identical to the H-space formulation (white-box test against tests/hostmodel.cpp).
+// SW stays in H space: its per-row maximum and its floor at 0 do not survive the transform.
 // Every 3 words a lane stores one 16-byte chunk {w0,w1,w2,anchor} per row at chunk index (c*32 + lane)*R + r
 // (b2a_format.h: consecutive DP rows are 16 bytes apart, which is what the traceback wants); the R stores of a warp
 // fill 512R contiguous bytes between them.
@@ -76,7 +83,7 @@ short16_fill_kernel(const FillArgs A)
         uint32_t w = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int sc = (c < nsym && sym[c] == (uint8_t)b) ? A.match : A.mismatch;
+            const int sc = ((c < nsym && sym[c] == (uint8_t)b) ? A.match : A.mismatch) - (LOCAL ? 0 : 2 * A.gap);
             w |= ((uint32_t)sc & 0xFFu) << (8 * c);
         }
         s_tbl4[b] = w;
@@ -121,7 +128,10 @@ short16_fill_kernel(const FillArgs A)
             for (int c = 1; c < 4; ++c) { if (xa == sym[c]) ca = c; if (xb == sym[c]) cb = c; }
         }
         sel[r] = ca | ((8u | ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
-        H[r] = LOCAL ? 0u : pack2(A.bias + (int)(i0 + 1) * A.gap);      // column-0 border, hw2.cpp:125-130
+        // LOCAL: H of the column-0 border (0, hw2.cpp:196-197).  NW: S of the frozen border H(i, 0) = i*gap (hw2.cpp:125-130) as
+        // seen from this lane's column before step 0, j = -1 - lane: Z - (lane + 1)|gap|; it grows by |gap| per frozen step
+        // and reaches Z = 32|gap| at column 0 (every border cell has S = Z).
+        H[r] = LOCAL ? 0u : pack2((31 - lane) * -A.gap);
         best[r] = 0u;
     }
     __syncwarp();
@@ -135,15 +145,19 @@ short16_fill_kernel(const FillArgs A)
     for (int t = 0; t < F; ++t) geo = geo * radix + 1u;
 #pragma unroll
     for (int t = 0; t < F - 1; ++t) bpow *= radix;
-    const uint32_t negGc = 0u - g32 * geo, negBpow = 0u - bpow, radm1 = radix - 1u;
-    const uint32_t bias32 = LOCAL ? 0u : (uint32_t)A.bias * 65537u;     // row-0 border b0(q) = bias32 + q*g32 (ring-exact)
+    // delta word = sum B^(F-1-t) (P_t - P_{t-1} - g): in S space the differences already exclude the gap, so the constant term goes
+    const uint32_t negGc = LOCAL ? 0u - g32 * geo : 0u, negBpow = 0u - bpow, radm1 = radix - 1u;
+    const uint32_t ag2 = pack2(-A.gap), Z = pack2(-32 * A.gap);         // NW: |gap| packed; S of every border cell
+    // NW: stored anchor = H + bias = S + (i + j)*gap + (bias - 32|gap|), i + j = lane*(R-1) + r + 1 + q at step q
+    const int abase = ((int)lane * (R - 1) + 1) * A.gap + A.bias + 32 * A.gap;
+    auto anchor_of_S = [&](uint32_t Sv, int r, uint32_t q) { return __vadd2(Sv, pack2(abase + (r + (int)q) * A.gap)); };
 
-    uint32_t dgn = LOCAL ? 0u : (lane == 0 ? bias32 : pack2(A.bias + (int)((uint32_t)lane * R) * A.gap));   // H(L*R, 0)
+    uint32_t dgn = LOCAL ? 0u : pack2((31 - lane) * -A.gap);             // value the row above had one column to the left (see H[r] above)
 
     // one wavefront step for this lane; ACTIVE_CHECK selects the ramp (predicated) flavour
     auto step = [&](const uint2* tcol, int k, uint32_t q, uint32_t (&S)[R], int f, bool active) {
         uint32_t up = __shfl_up_sync(0xFFFFFFFFu, H[R - 1], 1);
-        if (lane == 0) up = LOCAL ? 0u : bias32 + q * g32;              // row 0 border H(0, q), hw2.cpp:131-136
+        if (lane == 0) up = LOCAL ? 0u : Z;                              // row 0 border, hw2.cpp:131-136 (S = Z) / :196-197
         const uint32_t dg0 = dgn;
         dgn = up;
         if (active) {
@@ -152,13 +166,24 @@ short16_fill_kernel(const FillArgs A)
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const uint32_t s  = prmt(tw.x, tw.y, sel[r]);
-                const uint32_t ds = __vadd2(dg, s);
-                dg = H[r];
-                const uint32_t a = __viaddmax_s16x2(H[r], g2, ds);
-                const uint32_t h = LOCAL ? __viaddmax_s16x2_relu(u, g2, a) : __viaddmax_s16x2(u, g2, a);
-                if (LOCAL) best[r] = __vmaxs2(best[r], h);
+                uint32_t h;
+                if (LOCAL) {
+                    const uint32_t ds = __vadd2(dg, s);
+                    dg = H[r];
+                    const uint32_t a = __viaddmax_s16x2(H[r], g2, ds);
+                    h = __viaddmax_s16x2_relu(u, g2, a);
+                    best[r] = __vmaxs2(best[r], h);
+                } else {
+                    const uint32_t a = __viaddmax_s16x2(dg, s, H[r]);   // max(diag + s - 2 gap, left)   in S space
+                    dg = H[r];
+                    h = __vmaxs2(a, u);                                  // max(., up)
+                }
                 H[r] = h; u = h;
             }
+        } else if (!LOCAL) {
+            // a frozen H is a growing S (the lane's column still moves): keeps the record identical to the H-space formulation
+#pragma unroll
+            for (int r = 0; r < R; ++r) H[r] = __vadd2(H[r], ag2);
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -186,7 +211,8 @@ short16_fill_kernel(const FillArgs A)
                     const uint32_t w = (F > 1 ? S[r] * radm1 : 0u) + H[r] + pre[r];
                     if (wi == 0) w0[r] = w; else if (wi == 1) w1[r] = w;
                     else {
-                        const uint4 v = make_uint4(w0[r], w1[r], w, H[r]);
+                        const uint32_t anchor = LOCAL ? H[r] : anchor_of_S(H[r], r, q0 + CS - 1);
+                        const uint4 v = make_uint4(w0[r], w1[r], w, anchor);
                         *reinterpret_cast<uint4*>(&rec[((size_t)c * 32u + lane) * R + r]) = v;
                     }
                 }
@@ -208,7 +234,7 @@ short16_fill_kernel(const FillArgs A)
                     const uint32_t w = (F > 1 ? S[r] * radm1 : 0u) + H[r] + pre[r];
                     uint32_t* cw = reinterpret_cast<uint32_t*>(&rec[((size_t)c * 32u + lane) * R + r]);
                     cw[wi] = w;
-                    if (wi == 2) cw[3] = H[r];
+                    if (wi == 2) cw[3] = LOCAL ? H[r] : anchor_of_S(H[r], r, q0 + CS - 1);
                 }
             }
         }

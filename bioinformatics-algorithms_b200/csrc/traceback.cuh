@@ -97,8 +97,11 @@ struct S16View {
     }
 };
 
+#ifndef TB_MIN_CTAS
+#define TB_MIN_CTAS 1
+#endif
 template <int K, bool LOCAL>
-__global__ void __launch_bounds__(TB_THREADS)
+__global__ void __launch_bounds__(TB_THREADS, TB_MIN_CTAS)
 short16_traceback_kernel(const TbArgs A)
 {
     using FM = Short16<K>;
