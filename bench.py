@@ -62,7 +62,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02)
 
     def summary(self):
         self.stop_flag = True
