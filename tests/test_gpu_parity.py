@@ -483,3 +483,54 @@ def test_short16_long_texts_through_the_ring(eng):
         check_batch(eng, mode, ps, ts, (1, -1, -1), expect_path=1)
     res, _ = check_batch(eng, pkg.LOCAL, ps, ts, (2, -3, -4))                          # 4-bit deltas; SW needs no bias, so it stays on short16
     assert {int(x) for x in res["path"]} == {1}
+
+
+def test_cli_fasta_dialects_match_reference(eng, tmp_path):
+    """FASTA quirks of readFasta (hw2.cpp:25-57): CRLF, blank lines, empty records, text before the first header, trailing
+    blanks, case, no final newline, count mismatch, empty files -- exit code, stderr and output bytes as the reference's."""
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "hw2_fasta_kat.json")))
+    for c in kat["cases"]:
+        with open(tmp_path / "p.fa", "w", newline="") as f:
+            f.write(c["patterns"])
+        with open(tmp_path / "t.fa", "w", newline="") as f:
+            f.write(c["texts"])
+        if (tmp_path / "o.txt").exists():
+            (tmp_path / "o.txt").unlink()
+        p = subprocess.run([pkg.HW2_BIN, c["flag"], "-p", "p.fa", "-t", "t.fa", "-o", "o.txt", "-s", *map(str, c["s"])],
+                           cwd=tmp_path, capture_output=True, text=True)
+        body = (tmp_path / "o.txt").read_text() if (tmp_path / "o.txt").exists() else None
+        assert (p.returncode, p.stderr, body) == (c["rc"], c["stderr"], c["output"]), c
+
+
+def test_abi_error_paths(eng):
+    """status codes of the C ABI: bad arguments, unsupported range, call-order violations (no crash, no silent success)"""
+    lib = eng.lib
+    pat, po = pkg.pack([b"ACGT", b"AC"])
+    txt, to = pkg.pack([b"ACGA", b"AC"])
+    res = np.empty(2, dtype=pkg.RESULT_DTYPE)
+    P = lambda a: a.ctypes.data
+    def call(prm, po_=po, to_=to, res_=res, n=2):
+        return lib.b2a_align_batch(eng.ctx, C.byref(prm), P(pat), P(po_), P(txt), P(to_), n, P(res_) if res_ is not None else None)
+    assert call(pkg.Params(7, 1, -1, -1, 0)) == -1                                  # bad mode            B2A_ERR_ARG
+    assert call(pkg.Params(pkg.LOCAL, 1, -1, -1, pkg.TIE_HW4)) == -1                # hw4 order is global-only
+    bad = po.copy(); bad[1] = 9; bad[2] = 6
+    assert call(pkg.Params(pkg.GLOBAL, 1, -1, -1, 0), po_=bad) == -1                # decreasing offsets
+    assert call(pkg.Params(pkg.GLOBAL, 1 << 30, -1, -1, 0)) == -4                   # (m+n)*max|score| beyond int32: B2A_ERR_RANGE
+    assert lib.b2a_align_batch(eng.ctx, C.byref(pkg.Params(0, 1, -1, -1, 0)), P(pat), P(po), P(txt), P(to), 2, None) == -1
+    assert b"" != lib.b2a_last_error(eng.ctx)
+    assert call(pkg.Params(pkg.GLOBAL, 1, -1, -1, 0)) == 0                          # a good batch without WANT_OPS ...
+    buf = C.create_string_buffer(16)
+    assert lib.b2a_fetch_ops(eng.ctx, 0, buf, 16) == -5                             # ... has no ops to fetch: B2A_ERR_STATE
+    assert call(pkg.Params(pkg.GLOBAL, 1, -1, -1, pkg.WANT_OPS)) == 0
+    assert lib.b2a_fetch_ops(eng.ctx, 5, buf, 16) == -1                             # pair out of range
+    assert lib.b2a_fetch_ops(eng.ctx, 0, buf, 1) == -1                              # buffer too small
+    assert lib.b2a_fetch_ops(eng.ctx, 0, buf, 16) == 4 and buf.raw[:4] == b"MMMM"
+    assert lib.b2a_affine_fetch_ops(eng.ctx, 0, buf, 16) == -5                      # no affine batch yet
+    sc = np.zeros(2, dtype=np.int32)
+    assert lib.b2a_affine_score_batch(eng.ctx, 1 << 29, -1, -2, -1, P(pat), P(po), P(txt), P(to), 2, P(sc)) == -4    # sentinel would wrap
+    assert lib.b2a_set_option(eng.ctx, 99, 1) == -1 and lib.b2a_set_option(eng.ctx, pkg.OPT_LANES, 3) == -1
+    fresh = pkg.Engine(0)
+    assert fresh.lib.b2a_batch_run(fresh.ctx, None, None) == -5                     # run before upload
+    assert fresh.lib.b2a_batch_download(fresh.ctx, P(res)) == -5
+    fresh.close()
+    check_batch(eng, pkg.GLOBAL, [b"ACGT"], [b"ACGA"], (1, -1, -1))                 # the context still works after all that
