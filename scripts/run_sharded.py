@@ -7,7 +7,7 @@ Each rank owns a contiguous pair range (sharding.pair_range), runs it on its GPU
 per-rank winner / 16 partial sums cross ranks.  Rank 0 prints one JSON line per config with the max-over-ranks time."""
 import argparse, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -19,7 +19,6 @@ ap = argparse.ArgumentParser()
 ap.add_argument("what", choices=["c3", "c5"])
 ap.add_argument("--pairs", type=int, default=200_000)
 ap.add_argument("--len", type=int, default=100_000)
-ap.add_argument("--check", action="store_true", help="rank 0 re-derives the answer with the oracle (small sizes only)")
 args = ap.parse_args()
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr)
@@ -45,11 +44,6 @@ if args.what == "c3":
         best, key = sharding.merge_best(mode, res, first)
         dt = sharding.max_over_ranks(time.perf_counter() - t0)
         out[name] = {"winner": best, "key": key, "ms": dt * 1e3, "gcups_e2e": args.pairs * m * n / dt / 1e9}
-        if args.check and rank == 0:
-            import oracle_binding as ob
-            P, T = pat.reshape(args.pairs, m), txt.reshape(args.pairs, n)
-            als = [ob.align(mode, P[k].tobytes(), T[k].tobytes(), 1, -1, -1) for k in range(args.pairs)]
-            out[name]["oracle_ok"] = bool(ob.select_best(mode, als) == best)
     if rank == 0:
         print(json.dumps({"config": "c3", "n_gpus": world, "pairs": args.pairs, **out}))
 else:
