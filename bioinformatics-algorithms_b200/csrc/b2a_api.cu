@@ -124,7 +124,8 @@ constexpr uint64_t SEG_MIN_PAIRS = 2048;          // a segment is never closed b
 struct b2a_ctx {
     int device = 0;
     int sm_count = 0;
-    int n_lanes = 1;
+    int n_lanes = 2;                              // DP records the segments alternate over: the traceback of segment k (s_tb) then overlaps
+                                                  // the fill of segment k+1 (s_fill); end to end 61.8 -> 59.1 ms per 1 M pairs NW+SW
     bool trace = false;                           // B2A_TRACE=1: per-segment timeline of b2a_align_batch on stderr
     uint64_t seg_budget_bytes = 8ull << 30;       // record bytes per segment (B2A_SEG_MB overrides)
     uint64_t seg_max_pairs = 98304;               // pairs per segment of b2a_align_batch (B2A_SEG_PAIRS overrides; swept in scripts/seg_e2e_sweep.py)

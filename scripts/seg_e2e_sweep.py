@@ -13,8 +13,8 @@ po = pkg.pinned_empty(len(po_np), np.uint64); po[:] = po_np
 to = pkg.pinned_empty(len(to_np), np.uint64); to[:] = to_np
 res = pkg.pinned_empty(n, pkg.RESULT_DTYPE)
 e = pkg.Engine(0)
-for first, mx in ((16384, 131072), (16384, 65536), (8192, 65536), (16384, 98304), (32768, 131072), (4096, 131072)):
-    e.set_option(pkg.OPT_SEG_PAIRS, mx); e.set_option(pkg.OPT_SEG_FIRST, first); e.set_option(pkg.OPT_SEG_BYTES, 1 << 40)
+for lanes, first, mx in ((1, 16384, 98304), (2, 16384, 98304), (2, 16384, 65536), (2, 16384, 131072), (2, 32768, 131072), (2, 8192, 65536), (2, 16384, 49152)):
+    e.set_option(pkg.OPT_LANES, lanes); e.set_option(pkg.OPT_SEG_PAIRS, mx); e.set_option(pkg.OPT_SEG_FIRST, first); e.set_option(pkg.OPT_SEG_BYTES, 1 << 40)
     tot = 0.0
     for mode in (0, 1):
         e.align_packed(mode, pat, po, txt, to, 1, -1, -1, want_ops=True, results=res)
@@ -24,5 +24,5 @@ for first, mx in ((16384, 131072), (16384, 65536), (8192, 65536), (16384, 98304)
             e.align_packed(mode, pat, po, txt, to, 1, -1, -1, want_ops=True, results=res)
             w.append((time.perf_counter() - t0) * 1e3)
         tot += min(w)
-    print(f"first {first:7d} max {mx:7d}: NW+SW e2e {tot:6.2f} ms", flush=True)
+    print(f"lanes {lanes} first {first:7d} max {mx:7d}: NW+SW e2e {tot:6.2f} ms", flush=True)
 e.close()
