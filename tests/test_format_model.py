@@ -195,3 +195,30 @@ def test_wide_every_k_on_the_same_input():
     for K in (2, 4, 8, 16, 32):
         for mode in (ob.GLOBAL, ob.LOCAL):
             check_wide(lib, mode, p, t, (1, -1, -1), K)
+
+
+def test_walker_with_hw4_tie_order_matches_hw4_oracle():
+    """walker bit 4 = hw4's tie order d > u > l (hw4.cpp:37-46): ops must equal hw4's own needleman_wunsch, and differ from hw2's
+    order on inputs where 'u' and 'l' tie (the delta record itself is tie-order agnostic)."""
+    lib = hostmodel()
+    rng = random.Random(17)
+    differs = 0
+    try:
+        for it in range(120):
+            alpha = rng.choice([b"ACGT", b"AC", b"A"])
+            m, n = rng.randint(1, 60), rng.randint(1, 80)
+            pa, pb = rnd(rng, m, alpha), rnd(rng, m, alpha)
+            ta, tb = rnd(rng, n, alpha), rnd(rng, n, alpha)
+            s = rng.choice([(1, -1, -1), (2, -3, -4), (1, 0, 0)])
+            for opt in (4, 4 | 2):
+                lib.hm_set_opt(opt)
+                got = model_pairpair(lib, ob.GLOBAL, pa, ta, pb, tb, s)
+                if got is None:
+                    continue
+                for (r, ops), (p, t) in zip(got[0], ((pa, ta), (pb, tb))):
+                    score, dist, want = ob.hw4_nw(p, t, *s)
+                    assert (r.score, ops) == (score, want), (p, t, s)
+                    differs += ops != ob.align(ob.GLOBAL, p, t, *s).ops
+    finally:
+        lib.hm_set_opt(3)
+    assert differs > 0
