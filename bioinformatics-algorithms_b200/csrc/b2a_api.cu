@@ -231,6 +231,9 @@ cudaError_t launch_fill_k(int R, bool local, const FillArgs& a, cudaStream_t st)
         case 6: return launch_fill_rk<6, K>(local, a, st);
         case 7: return launch_fill_rk<7, K>(local, a, st);
         case 8: return launch_fill_rk<8, K>(local, a, st);
+        case 10: return launch_fill_rk<10, K>(local, a, st);
+        case 12: return launch_fill_rk<12, K>(local, a, st);
+        case 16: return launch_fill_rk<16, K>(local, a, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -764,7 +767,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
             if (have_last) {                                             // the previous pair found no neighbour: park it
                 auto it = pending.find(last_key);
                 const uint32_t lm = (uint32_t)(last_key >> 32), ln = (uint32_t)last_key;
-                if (it != pending.end()) { pps[(lm + 31) / 32].push_back(PPDesc{it->second, last_idx, lm, ln}); pending.erase(it); }
+                if (it != pending.end()) { pps[short16_R(lm)].push_back(PPDesc{it->second, last_idx, lm, ln}); pending.erase(it); }
                 else pending[last_key] = last_idx;
                 have_last = false;
             }
@@ -775,12 +778,12 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
         if (have_last) {
             auto it = pending.find(last_key);
             const uint32_t lm = (uint32_t)(last_key >> 32), ln = (uint32_t)last_key;
-            if (it != pending.end()) { pps[(lm + 31) / 32].push_back(PPDesc{it->second, last_idx, lm, ln}); pending.erase(it); }
+            if (it != pending.end()) { pps[short16_R(lm)].push_back(PPDesc{it->second, last_idx, lm, ln}); pending.erase(it); }
             else pending[last_key] = last_idx;
         }
         for (auto& kv : pending) {                                       // unpaired leftovers: both halves carry the same pair
             const uint32_t lm = (uint32_t)(kv.first >> 32), ln = (uint32_t)kv.first;
-            pps[(lm + 31) / 32].push_back(PPDesc{kv.second, kv.second, lm, ln});
+            pps[short16_R(lm)].push_back(PPDesc{kv.second, kv.second, lm, ln});
         }
         PPDesc* hp = ctx->h_pps.p + sg.pp_first;
         uint64_t* hc = ctx->h_code_off.p + sg.pp_first;

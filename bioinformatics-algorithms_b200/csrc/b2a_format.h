@@ -96,13 +96,18 @@ B2A_HD int delta_bits_wide(int match, int mismatch, int gap) {
 // the delta width K and the bias that keeps every stored H of the (junk-extended) matrix in
 // [0, 32767] (needed both for the s16 arithmetic and for the ring-exact word encoding).
 struct Short16Plan { int K, R, bias; };
-constexpr int SHORT16_MAX_R = 8;          // rows per lane -> patterns up to 256 bases
+constexpr int SHORT16_MAX_R = 16;         // rows per lane -> patterns up to 512 bases
+// rows per lane for an m-row pattern: every value up to 8, then 10, 12, 16 (fewer kernel instances; the extra rows are junk rows)
+B2A_HD int short16_R(uint32_t m) {
+    const int r = (int)((m + 31u) / 32u);
+    return r <= 8 ? r : (r <= 10 ? 10 : (r <= 12 ? 12 : 16));
+}
 B2A_HD bool short16_plan(int mode, uint32_t m, uint32_t n, int match, int mismatch, int gap, Short16Plan& pl) {
     if (m == 0 || n == 0 || m > 32u * SHORT16_MAX_R || n > 30000u) return false;     // (the int16 range test below is the real limit on n)
     pl.K = delta_bits(match, mismatch, gap);
     if (pl.K == 0) return false;
     if (match > 127 || match < -128 || mismatch > 127 || mismatch < -128) return false;   // PRMT score tables are int8
-    pl.R = (int)((m + 31u) / 32u);
+    pl.R = short16_R(m);
     const long rows = 32L * pl.R;
     const long smax = match > mismatch ? match : mismatch, smin = match < mismatch ? match : mismatch;
     const long margin = (long)(-gap) + (smin < 0 ? -smin : 0) + 1;
@@ -178,8 +183,8 @@ B2A_HD void decode_step(const Chunk& ch, int half, int gap, int rem, int& H, int
 }
 
 // (row i, chunk c) -> chunk index, and the lane L that owns the row.  No runtime divisions: the wide32
-// family has R = 4 (shifts); short16 has a single band and R <= 8, where x / R == (x * rmagic) >> 16
-// exactly for x < 256 (rmagic = 65536 / R rounded up; checked exhaustively in tests).
+// family has R = 4 (shifts); short16 has a single band and R <= 16, where x / R == (x * rmagic) >> 16
+// exactly for x < 512 (rmagic = 65536 / R rounded up; checked exhaustively in tests).
 template <class FM>
 B2A_HD uint32_t row_slot(const PairView& v, uint32_t i, uint32_t& L) {     // band*R + r, and the owning lane
     const uint32_t x = i - 1u;

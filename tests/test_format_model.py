@@ -93,7 +93,9 @@ def test_plan_picks_expected_widths():
     plan = (C.c_int * 3)()
     assert lib.hm_plan(0, 150, 1000, 1, -1, -1, plan) and (plan[0], plan[1]) == (2, 5)
     assert lib.hm_plan(0, 150, 1000, 5, -4, -16, plan) and plan[0] == 8
-    assert not lib.hm_plan(0, 300, 1000, 1, -1, -1, plan)    # > 256 rows
+    assert lib.hm_plan(0, 300, 1000, 1, -1, -1, plan) and plan[1] == 10      # 257..320 rows: 10 rows per lane
+    assert lib.hm_plan(0, 400, 1000, 1, -1, -1, plan) and plan[1] == 16
+    assert not lib.hm_plan(0, 513, 1000, 1, -1, -1, plan)    # > 512 rows: int32 family
     assert not lib.hm_plan(1, 150, 100000, 1, -1, -1, plan)  # too many columns
 
 
@@ -222,3 +224,15 @@ def test_walker_with_hw4_tie_order_matches_hw4_oracle():
     finally:
         lib.hm_set_opt(3)
     assert differs > 0
+
+
+def test_walkers_match_oracle_long_patterns():
+    """rows-per-lane 10, 12, 16 (patterns of 257..512 bases): record layout + walkers against the oracle on the CPU"""
+    lib = hostmodel()
+    rng = random.Random(4830)
+    for m, n in ((257, 300), (300, 420), (384, 200), (400, 500), (512, 130)):
+        t1, t2 = rnd(rng, n), rnd(rng, n)
+        p1 = (mutate(rng, t1) + rnd(rng, m))[:m]
+        p2 = (mutate(rng, t2) + rnd(rng, m))[:m]
+        for mode in (ob.GLOBAL, ob.LOCAL):
+            assert check(lib, mode, p1, t1, p2, t2, (1, -1, -1))

@@ -222,7 +222,7 @@ def test_wide_long_patterns_vs_oracle(eng):
     for s in ((1, -1, -1), (2, -3, -4), (5, -4, -16)):
         for mode in (pkg.GLOBAL, pkg.LOCAL):
             res, _ = check_batch(eng, mode, ps, ts, s)
-            assert all(int(x) == 2 for x, p in zip(res["path"], ps) if len(p) > 256)
+            assert all(int(x) == 2 for x, p in zip(res["path"], ps) if len(p) > 512)
 
 
 def test_wide_general_alphabet_and_odd_scores_vs_oracle(eng):
@@ -242,7 +242,7 @@ def test_mixed_batch_short_and_wide(eng):
     rng = random.Random(33)
     ps, ts = [], []
     for k in range(50):
-        m = rng.choice([20, 150, 150, 256, 257, 600])
+        m = rng.choice([20, 150, 150, 256, 257, 600, 513])
         n = rng.choice([20, 1000, 333])
         t = rnd(rng, n)
         ps.append((mutate(rng, t) + rnd(rng, m))[:m]); ts.append(t)
@@ -468,6 +468,22 @@ def test_hw3_cli_byte_exact(eng, tmp_path):
         for binary, name in ((ob.REF_HW3, "ref.phy"), (pkg.HW3_BIN, "mine.phy")):
             subprocess.check_call([binary, "-i", "big.fa", "-o", name, "-s", "5:-4:-16:-4"], cwd=tmp_path)
         assert (tmp_path / "ref.phy").read_bytes() == (tmp_path / "mine.phy").read_bytes()
+
+
+def test_short16_patterns_up_to_512_rows(eng):
+    """rows-per-lane 10, 12, 16 (patterns of 257..512 bases stay on the s16x2 path); 513 goes to the int32 family"""
+    rng = random.Random(82)
+    ps, ts = [], []
+    for m, n in ((257, 300), (300, 1000), (300, 1000), (320, 321), (321, 700), (384, 500), (385, 900), (500, 2000), (512, 512), (512, 40), (290, 1)):
+        t = rnd(rng, n)
+        k = rng.randrange(0, max(1, n - m)) if n > m else 0
+        ps.append((mutate(rng, t[k:k + m]) + rnd(rng, m))[:m]); ts.append(t)
+    ps.append((b"ACGTA" * 110)[:512]); ts.append((b"ACGTACG" * 120)[:800])           # tie stress
+    for s in ((1, -1, -1), (2, -3, -4)):
+        for mode in (pkg.GLOBAL, pkg.LOCAL):
+            check_batch(eng, mode, ps, ts, s, expect_path=1)
+    res, _ = check_batch(eng, pkg.GLOBAL, ps + [rnd(rng, 513)], ts + [rnd(rng, 600)], (1, -1, -1))
+    assert int(res["path"][-1]) == 2
 
 
 def test_short16_long_texts_through_the_ring(eng):
