@@ -550,3 +550,24 @@ def test_abi_error_paths(eng):
     assert fresh.lib.b2a_batch_download(fresh.ctx, P(res)) == -5
     fresh.close()
     check_batch(eng, pkg.GLOBAL, [b"ACGT"], [b"ACGA"], (1, -1, -1))                 # the context still works after all that
+
+
+def test_cli_all_pairs_report(eng, tmp_path):
+    """HW2_ALL_PAIRS (extension): one line per pair with what struct AlignmentResult holds, equal to the oracle's,
+    while the regular output file stays byte-identical to the reference's."""
+    rng = random.Random(91)
+    ps, ts = [], []
+    for _ in range(300):
+        m, n = rng.choice([(20, 20), (150, 1000), (5, 7), (300, 400), (600, 500), (40, 3)])
+        t = rnd(rng, n)
+        ps.append((mutate(rng, t) + rnd(rng, m))[:m]); ts.append(t)
+    ob.write_fasta(str(tmp_path / "p.fa"), ps, b"p"); ob.write_fasta(str(tmp_path / "t.fa"), ts, b"t")
+    for flag, mode in (("-g", pkg.GLOBAL), ("-l", pkg.LOCAL)):
+        env = dict(os.environ, HW2_ALL_PAIRS=str(tmp_path / "all.tsv"))
+        subprocess.check_call([pkg.HW2_BIN, flag, "-p", "p.fa", "-t", "t.fa", "-o", "o.txt", "-s", "1", "-1", "-1"], cwd=tmp_path, env=env)
+        assert (tmp_path / "o.txt").read_bytes() == ob.render_file(mode, ps, ts, 1, -1, -1)
+        lines = (tmp_path / "all.tsv").read_text().split("\n")
+        assert len(lines) == len(ps) + 1 and lines[-1] == ""
+        for k, line in enumerate(lines[:-1]):
+            a = ob.align(mode, ps[k], ts[k], 1, -1, -1)
+            assert line.split("\t") == [str(k), str(a.score), str(a.overlap), a.cigar, a.mdz], (k, line)
