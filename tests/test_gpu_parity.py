@@ -571,3 +571,28 @@ def test_cli_all_pairs_report(eng, tmp_path):
         for k, line in enumerate(lines[:-1]):
             a = ob.align(mode, ps[k], ts[k], 1, -1, -1)
             assert line.split("\t") == [str(k), str(a.score), str(a.overlap), a.cigar, a.mdz], (k, line)
+
+
+def test_cli_flag_corner_cases_match_reference(eng, tmp_path):
+    """SURVEY Appendix A.1: neither -g nor -l -> empty output file, rc 0; both -> global; -s with garbage -> atoi gives 0;
+    unknown tokens ignored; later duplicates win.  Compared with the unmodified binary when it travelled."""
+    if not ob.have_ref():
+        pytest.skip("oracle/_ref/hw2 not present")
+    ps, ts = [b"ACGTACGTTT", b"TTGACCA"], [b"ACGTTCGTTA", b"TTGGACCA"]
+    ob.write_fasta(str(tmp_path / "p.fa"), ps, b"p"); ob.write_fasta(str(tmp_path / "t.fa"), ts, b"t")
+    base = ["-p", "p.fa", "-t", "t.fa", "-o", "o.txt"]
+    cases = [base + ["-s", "1", "-1", "-1"],                                   # neither flag
+             ["-g", "-l"] + base + ["-s", "1", "-1", "-1"],                      # both flags
+             ["-l"] + base + ["-s", "x", "-1", "y"],                             # atoi garbage
+             ["-g", "--frobnicate", "7"] + base + ["-s", "1", "-1", "-1"],       # unknown tokens
+             ["-l", "-s", "5", "-4", "-16"] + base + ["-s", "1", "-1", "-1"],    # duplicate -s: the later one wins
+             ["-g"] + base + ["-s", "1", "-1"]]                                  # -s without three values: scores stay 0
+    for args in cases:
+        outs = []
+        for binary in (ob.REF_HW2, pkg.HW2_BIN):
+            if (tmp_path / "o.txt").exists():
+                (tmp_path / "o.txt").unlink()
+            p = subprocess.run([binary] + args, cwd=tmp_path, capture_output=True, text=True)
+            body = (tmp_path / "o.txt").read_bytes() if (tmp_path / "o.txt").exists() else None
+            outs.append((p.returncode, p.stderr.replace(binary, "hw2"), body))
+        assert outs[0] == outs[1], (args, outs)
