@@ -763,27 +763,52 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
             const uint64_t key = (m64 << 32) | n64;
             if (key != plan_key) { plan_key = key; plan_ok = !score_only && short16_plan(prm->mode, m, n, prm->match, prm->mismatch, prm->gap, pl); }
             if (!plan_ok) { ctx->wide_pairs.push_back((uint32_t)q); ++sg.n_wide; continue; }
-            if (have_last && key == last_key) { pps[pl.R].push_back(PPDesc{last_idx, (uint32_t)q, m, n}); have_last = false; continue; }
+            if (have_last && key == last_key) { pps[pl.R].push_back(PPDesc{last_idx, (uint32_t)q, pp_pack(m, m), pp_pack(n, n)}); have_last = false; continue; }
             if (have_last) {                                             // the previous pair found no neighbour: park it
                 auto it = pending.find(last_key);
                 const uint32_t lm = (uint32_t)(last_key >> 32), ln = (uint32_t)last_key;
-                if (it != pending.end()) { pps[short16_R(lm)].push_back(PPDesc{it->second, last_idx, lm, ln}); pending.erase(it); }
+                if (it != pending.end()) { pps[short16_R(lm)].push_back(PPDesc{it->second, last_idx, pp_pack(lm, lm), pp_pack(ln, ln)}); pending.erase(it); }
                 else pending[last_key] = last_idx;
                 have_last = false;
             }
             auto it = pending.find(key);
-            if (it != pending.end()) { pps[pl.R].push_back(PPDesc{it->second, (uint32_t)q, m, n}); pending.erase(it); }
+            if (it != pending.end()) { pps[pl.R].push_back(PPDesc{it->second, (uint32_t)q, pp_pack(m, m), pp_pack(n, n)}); pending.erase(it); }
             else { have_last = true; last_key = key; last_idx = (uint32_t)q; }
         }
         if (have_last) {
             auto it = pending.find(last_key);
             const uint32_t lm = (uint32_t)(last_key >> 32), ln = (uint32_t)last_key;
-            if (it != pending.end()) { pps[short16_R(lm)].push_back(PPDesc{it->second, last_idx, lm, ln}); pending.erase(it); }
+            if (it != pending.end()) { pps[short16_R(lm)].push_back(PPDesc{it->second, last_idx, pp_pack(lm, lm), pp_pack(ln, ln)}); pending.erase(it); }
             else pending[last_key] = last_idx;
         }
-        for (auto& kv : pending) {                                       // unpaired leftovers: both halves carry the same pair
-            const uint32_t lm = (uint32_t)(kv.first >> 32), ln = (uint32_t)kv.first;
-            pps[short16_R(lm)].push_back(PPDesc{kv.second, kv.second, lm, ln});
+        // Leftovers (one per distinct shape): zip pairs of DIFFERENT shapes, neighbours in (rows per lane, n, m) order so that little
+        // is padded.  Safe for NW always (the score is read at the true end cell); for SW the junk columns of the shorter text must
+        // stay strictly below the real maximum, which needs gap < 0 and mismatch < 0.  What still has no partner runs as a singleton
+        // (both halves carry the same pair).
+        {
+            struct Left { int R; uint32_t n, m, idx; };
+            std::vector<Left> left;
+            left.reserve(pending.size());
+            for (auto& kv : pending) { const uint32_t lm = (uint32_t)(kv.first >> 32), ln = (uint32_t)kv.first; left.push_back(Left{short16_R(lm), ln, lm, kv.second}); }
+            std::sort(left.begin(), left.end(), [](const Left& x, const Left& y) {
+                return x.R != y.R ? x.R < y.R : (x.n != y.n ? x.n < y.n : (x.m != y.m ? x.m < y.m : x.idx < y.idx)); });
+            static const bool no_mix = std::getenv("B2A_NO_MIX") != nullptr;           // A/B switch for scripts/ragged_exp.py
+            const bool mix_ok = !no_mix && (!local || (prm->gap < 0 && prm->mismatch < 0));
+            for (size_t q = 0; q < left.size(); ++q) {
+                const Left& x = left[q];
+                if (mix_ok && q + 1 < left.size() && left[q + 1].R == x.R) {
+                    const Left& y = left[q + 1];
+                    Short16Plan both{0, 0, 0};
+                    if (short16_plan(prm->mode, std::max(x.m, y.m), std::max(x.n, y.n), prm->match, prm->mismatch, prm->gap, both) && both.R == x.R) {
+                        const bool xfirst = x.idx < y.idx;               // low half = lower pair index (deterministic records)
+                        const Left& lo = xfirst ? x : y; const Left& hi = xfirst ? y : x;
+                        pps[x.R].push_back(PPDesc{lo.idx, hi.idx, pp_pack(lo.m, hi.m), pp_pack(lo.n, hi.n)});
+                        ++q;
+                        continue;
+                    }
+                }
+                pps[x.R].push_back(PPDesc{x.idx, x.idx, pp_pack(x.m, x.m), pp_pack(x.n, x.n)});
+            }
         }
         PPDesc* hp = ctx->h_pps.p + sg.pp_first;
         uint64_t* hc = ctx->h_code_off.p + sg.pp_first;
@@ -793,8 +818,8 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
             ClassRange cr{R, (uint32_t)npp, (uint32_t)pps[R].size(), 0};
             for (const PPDesc& d : pps[R]) {
                 hp[npp] = d; hc[npp] = chunks; ++npp;
-                chunks += (uint64_t)R * num_chunks(d.n, CS) * 32u;
-                cr.max_n = std::max(cr.max_n, d.n);
+                chunks += (uint64_t)R * num_chunks(pp_max(d.n), CS) * 32u;
+                cr.max_n = std::max(cr.max_n, pp_max(d.n));
             }
             rb = std::max<uint64_t>(rb, (uint64_t)(cr.first + cr.count) * R * 32u);
             sg.classes.push_back(cr);

@@ -40,8 +40,13 @@ namespace b2a {
 
 struct alignas(16) Chunk { uint32_t w0, w1, w2, anchor; };
 
-// pair-pair descriptor (short16): pairs a and b (b == a for an unpaired singleton) of shape m x n
+// pair-pair descriptor (short16): pairs a and b (b == a for an unpaired singleton).  m = m_a | m_b << 16, n = n_a | n_b << 16:
+// the two pairs may differ in shape.  The warp sweeps max(m) x max(n); cells right of / below a half's own (m, n) are junk that
+// never feeds its real cells (the recurrence only looks left and up), and only the epilogue and the walker use the true shapes.
 struct PPDesc { uint32_t a, b, m, n; };
+B2A_HD uint32_t pp_dim(uint32_t packed, int half) { return half ? packed >> 16 : packed & 0xFFFFu; }
+B2A_HD uint32_t pp_max(uint32_t packed) { const uint32_t lo = packed & 0xFFFFu, hi = packed >> 16; return lo > hi ? lo : hi; }
+B2A_HD uint32_t pp_pack(uint32_t lo, uint32_t hi) { return lo | (hi << 16); }
 
 // one record per pair; mirrors b2a_result in include/b2align.h (static_assert in b2a_api.cu)
 struct PairResult {

@@ -96,14 +96,15 @@ short16_fill_kernel(const FillArgs A)
     uint2* ring = s_ring[warp];
 
     const PPDesc d = A.pps[pp];
-    const uint32_t m = d.m, n = d.n;
+    const uint32_t ma = pp_dim(d.m, 0), mb = pp_dim(d.m, 1), na = pp_dim(d.n, 0), nb = pp_dim(d.n, 1);
+    const uint32_t m = pp_max(d.m), n = pp_max(d.n);                  // the sweep covers both pairs; the shorter one gets junk cells
     const uint8_t* pa = A.pat + A.pat_off[d.a];
     const uint8_t* pb = A.pat + A.pat_off[d.b];
     const uint8_t* ta = A.txt + A.txt_off[d.a];
     const uint8_t* tb = A.txt + A.txt_off[d.b];
 
     uint32_t staged = 0;                                  // text indices [0, staged) have been staged (multiple of 32)
-    uint32_t nxa = (uint32_t)lane < n ? ta[lane] : 0u, nxb = (uint32_t)lane < n ? tb[lane] : 0u;   // bytes of the next block, one block ahead
+    uint32_t nxa = (uint32_t)lane < na ? ta[lane] : 0u, nxb = (uint32_t)lane < nb ? tb[lane] : 0u;   // bytes of the next block, one block ahead
     auto stage_block = [&]() {
         const uint32_t slot = (staged + (uint32_t)lane) & 127u;
         const uint2 e = make_uint2(s_tbl4[nxa], s_tbl4[nxb]);
@@ -112,7 +113,7 @@ short16_fill_kernel(const FillArgs A)
         __syncwarp();
         staged += 32u;
         const uint32_t x = staged + (uint32_t)lane;
-        nxa = x < n ? ta[x] : 0u; nxb = x < n ? tb[x] : 0u;
+        nxa = x < na ? ta[x] : 0u; nxb = x < nb ? tb[x] : 0u;
     };
 
     // PRMT selectors of this lane's rows: byte0 = tableA[codeA], byte1 = its sign, byte2 = tableB[codeB], byte3 = its sign
@@ -122,11 +123,12 @@ short16_fill_kernel(const FillArgs A)
     for (int r = 0; r < R; ++r) {
         const uint32_t i0 = (uint32_t)lane * R + r;     // 0-based row
         uint32_t ca = 0, cb = 0;
-        if (i0 < m) {
-            const uint8_t xa = pa[i0], xb = pb[i0];
+        if (i0 < ma) { const uint8_t xa = pa[i0];
 #pragma unroll
-            for (int c = 1; c < 4; ++c) { if (xa == sym[c]) ca = c; if (xb == sym[c]) cb = c; }
-        }
+            for (int c = 1; c < 4; ++c) if (xa == sym[c]) ca = c; }
+        if (i0 < mb) { const uint8_t xb = pb[i0];
+#pragma unroll
+            for (int c = 1; c < 4; ++c) if (xb == sym[c]) cb = c; }
         sel[r] = ca | ((8u | ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
         // LOCAL: H of the column-0 border (0, hw2.cpp:196-197).  NW: S of the frozen border H(i, 0) = i*gap (hw2.cpp:125-130) as
         // seen from this lane's column before step 0, j = -1 - lane: Z - (lane + 1)|gap|; it grows by |gap| per frozen step
@@ -249,12 +251,13 @@ short16_fill_kernel(const FillArgs A)
         __syncwarp();                                            // the chunk stores above are visible to the whole warp
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
+            const uint32_t mh = half ? mb : ma, nh = half ? nb : na;     // this pair's own shape
             int mloc = 0; uint32_t iloc = 0xFFFFFFFFu;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int v = (int)((best[r] >> (16 * half)) & 0xFFFFu);
                 const uint32_t i = (uint32_t)lane * R + r + 1u;
-                if (i <= m && v > mloc) { mloc = v; iloc = i; }
+                if (i <= mh && v > mloc) { mloc = v; iloc = i; }
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
@@ -277,7 +280,7 @@ short16_fill_kernel(const FillArgs A)
                     const uint64_t X = ((uint64_t)((ch.x >> sh) & 0xFFFFu) << 32) | ((uint64_t)((ch.y >> sh) & 0xFFFFu) << 16) | ((ch.z >> sh) & 0xFFFFu);
                     for (int rem = CS - 1; rem >= 0; --rem) {
                         const uint32_t q = c * CS + (uint32_t)rem;
-                        if (Hq == mloc && q - Lb - 1u < n) cand = min(cand, q);   // columns 1..n only (frozen steps outside repeat border values)
+                        if (Hq == mloc && q - Lb - 1u < nh) cand = min(cand, q);   // columns 1..n only (frozen steps outside repeat border values)
                         Hq -= (int)((uint32_t)(X >> (K * (CS - 1 - rem))) & Geo<K>::MASK) + A.gap;
                     }
                 }

@@ -115,7 +115,8 @@ short16_traceback_kernel(const TbArgs A)
     const uint8_t* __restrict__ P = A.pat + A.pat_off[pair];
     const uint8_t* __restrict__ T = A.txt + A.txt_off[pair];
     const int gap = A.gap, match = A.match, mismatch = A.mismatch;
-    S16View<K> v{A.codes + A.code_off[pp], num_chunks(d.n, FM::CS), (uint32_t)A.R, (uint32_t)short16_rmagic(A.R), 32u * (uint32_t)A.R,
+    const uint32_t mh = pp_dim(d.m, half), nh = pp_dim(d.n, half);   // this pair's own shape; the record is laid out for max(n)
+    S16View<K> v{A.codes + A.code_off[pp], num_chunks(pp_max(d.n), FM::CS), (uint32_t)A.R, (uint32_t)short16_rmagic(A.R), 32u * (uint32_t)A.R,
                  half ? 0x7632u : 0x5410u, half ? 0x4432u : 0x4410u, gap};
     uint32_t* out = A.ops ? A.ops + A.ops_off[pair] : nullptr;
 
@@ -144,7 +145,7 @@ short16_traceback_kernel(const TbArgs A)
         i = res.end_i; j = res.end_j;
         if (e.x == 0) { i = 0; j = 0; }                   // hw2.cpp:202-203: best cell stays (0,0), empty alignment
     } else {
-        i = d.m; j = d.n;
+        i = mh; j = nh;
         res.end_i = i; res.end_j = j;
         int H, D;
         v.cell(i, j, H, D);
@@ -207,7 +208,7 @@ short16_traceback_kernel(const TbArgs A)
     }
     if (fill && out) out[wpos] = word;
     res.start_i = i; res.start_j = j; res.n_ops = nops;
-    res.overlap = hw4 ? (int)(nops - (d.m + d.n - nops) + mism) : best;      // gap columns = n_ops - M columns, M columns = m + n - n_ops
+    res.overlap = hw4 ? (int)(nops - (mh + nh - nops) + mism) : best;      // gap columns = n_ops - M columns, M columns = m + n - n_ops
     A.results[pair] = res;
 }
 
