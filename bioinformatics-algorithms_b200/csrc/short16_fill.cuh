@@ -249,9 +249,10 @@ short16_fill_kernel(const FillArgs A)
         // backwards from their anchors by the lanes in parallel.  ~2 % of the fill; the traceback kernel (one thread
         // per pair) used to spend more than its whole walk on this search.
         __syncwarp();                                            // the chunk stores above are visible to the whole warp
+        const PPDesc de = A.pps[pp];                              // re-read: keeping the per-half shapes live through the sweep cost 4 %
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const uint32_t mh = half ? mb : ma, nh = half ? nb : na;     // this pair's own shape
+            const uint32_t mh = pp_dim(de.m, half), nh = pp_dim(de.n, half);     // this pair's own shape
             int mloc = 0; uint32_t iloc = 0xFFFFFFFFu;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -288,7 +289,7 @@ short16_fill_kernel(const FillArgs A)
                 for (int o = 16; o; o >>= 1) cand = min(cand, __shfl_xor_sync(0xFFFFFFFFu, cand, o));
                 bj = cand - Lb;
             }
-            if (lane == 0) A.endcell[half ? d.b : d.a] = make_int4(mloc, (int)bi, (int)bj, 0);
+            if (lane == 0) A.endcell[half ? de.b : de.a] = make_int4(mloc, (int)bi, (int)bj, 0);
         }
     }
 }
