@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb2align.so")
+LIB_PATH = os.environ.get("B2A_LIB") or os.path.join(HERE, "libb2align.so")      # B2A_LIB: experiment builds (scripts/)
 HW2_BIN = os.path.join(HERE, "bin", "hw2")
 HW3_BIN = os.path.join(HERE, "bin", "hw3")
 HW4_BIN = os.path.join(HERE, "bin", "hw4")
@@ -30,7 +30,7 @@ RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<u4"), ("end_j", "<u4"), (
                          ("start_j", "<u4"), ("overlap", "<i4"), ("n_ops", "<u4"), ("path", "<u4")])
 
 EXPORTS = ["b2a_device_count", "b2a_create", "b2a_destroy", "b2a_last_error", "b2a_host_alloc", "b2a_host_free",
-           "b2a_align_batch", "b2a_affine_score_batch", "b2a_affine_align_batch", "b2a_affine_fetch_ops", "b2a_affine_star_scores", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
+           "b2a_host_register", "b2a_host_unregister", "b2a_align_batch", "b2a_align_batch_multi", "b2a_select_run", "b2a_affine_score_batch", "b2a_affine_align_batch", "b2a_affine_fetch_ops", "b2a_affine_star_scores", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
            "b2a_batch_download", "b2a_batch_times", "b2a_set_option", "b2a_batch_stats", "b2a_render_cigar", "b2a_render_mdz", "b2a_select_best",
            "b2a_upgma_newick", "b2a_center_star_phylip",
            "b2a_microbench_int16x2", "b2a_debug_copy_record"]
@@ -65,6 +65,10 @@ def load_library():
         lib.b2a_host_free.argtypes = [C.c_void_p]
         P = C.c_void_p
         lib.b2a_align_batch.argtypes = [P, C.POINTER(Params), P, P, P, P, C.c_uint64, P]
+        lib.b2a_align_batch_multi.argtypes = [P, C.POINTER(Params), C.c_uint32, P, P, P, P, C.c_uint64, P]
+        lib.b2a_select_run.argtypes = [P, C.c_uint32]
+        lib.b2a_host_register.argtypes = [P, C.c_size_t]
+        lib.b2a_host_unregister.argtypes = [P]
         lib.b2a_batch_upload.argtypes = [P, C.POINTER(Params), P, P, P, P, C.c_uint64]
         lib.b2a_batch_run.argtypes = [P, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         lib.b2a_batch_download.argtypes = [P, P]
@@ -126,6 +130,16 @@ def pinned_empty(n, dtype):
     buf = (C.c_uint8 * nbytes).from_address(ptr)
     buf._owner = _Owner(ptr)
     return np.frombuffer(buf, dtype=dt, count=int(n))
+
+
+def host_register(arr):
+    """Pin an existing numpy buffer (e.g. over POSIX shared memory) for asynchronous device copies."""
+    if load_library().b2a_host_register(arr.ctypes.data, arr.nbytes) != 0:
+        raise B2AError("b2a_host_register failed")
+
+
+def host_unregister(arr):
+    load_library().b2a_host_unregister(arr.ctypes.data)
 
 
 def unpack_ops(words, off, k, n_ops):
@@ -207,6 +221,20 @@ class Engine:
         self._check(self.lib.b2a_align_batch(self.ctx, C.byref(prm), pat.ctypes.data, pat_off.ctypes.data,
                                              txt.ctypes.data, txt_off.ctypes.data, n, results.ctypes.data), "b2a_align_batch")
         return results
+
+    def align_packed_multi(self, modes, pat, pat_off, txt, txt_off, match, mismatch, gap, want_ops=False, results=None):
+        """Several runs (modes) over ONE upload of the pairs (b2a_align_batch_multi): returns one result array per mode."""
+        n = len(pat_off) - 1
+        if results is None:
+            results = [np.empty(n, dtype=RESULT_DTYPE) for _ in modes]
+        prms = (Params * len(modes))(*[Params(m, match, mismatch, gap, WANT_OPS if want_ops else 0) for m in modes])
+        ptrs = (C.c_void_p * len(modes))(*[r.ctypes.data for r in results])
+        self._check(self.lib.b2a_align_batch_multi(self.ctx, prms, len(modes), pat.ctypes.data, pat_off.ctypes.data,
+                                                   txt.ctypes.data, txt_off.ctypes.data, n, ptrs), "b2a_align_batch_multi")
+        return results
+
+    def select_run(self, run):
+        self._check(self.lib.b2a_select_run(self.ctx, int(run)), "b2a_select_run")
 
     def align_batch(self, mode, patterns, texts, match, mismatch, gap, want_ops=True, tie_hw4=False):
         """lists of bytes -> (results recarray, list of op byte-strings in traceback order or None)."""

@@ -72,7 +72,6 @@ struct Segment {
     uint64_t chunks = 0, rowbest_words = 0;       // record size of the segment
     uint64_t n_wide = 0;                          // pairs of the segment planned for wide32
     std::vector<ClassRange> classes;
-    int lane = 0;
     bool flagged = false;                         // > 4 pattern symbols: the whole segment goes to wide32
 };
 
@@ -116,7 +115,18 @@ struct WideState {
     }
 };
 
+// What differs between the runs of one batch (b2a_align_batch_multi: same pairs, same scoring, another mode): the outputs.
+// Inputs, segments and the pair-pair plan are shared.
+struct RunBuf {
+    int32_t mode = B2A_MODE_GLOBAL;
+    DevBuf<PairResult> d_results;
+    DevBuf<uint32_t> d_ops;
+    DevBuf<int4> d_endcell;                       // local mode: end cell per pair, written by the short16 fill epilogue
+    void release() { d_results.release(); d_ops.release(); d_endcell.release(); }
+};
+
 constexpr int MAX_LANES = 2;
+constexpr int MAX_RUNS = B2A_MAX_RUNS;
 constexpr uint64_t SEG_MIN_PAIRS = 2048;          // a segment is never closed below this many pairs
 
 } // namespace
@@ -143,7 +153,10 @@ struct b2a_ctx {
     // batch state
     bool have_batch = false, ran = false;
     bool affine_ops = false;                      // the last call was b2a_affine_align_batch: d_ops / d_nops hold its op lists
-    b2a_params prm{};
+    b2a_params prm{};                             // scoring + flags of the batch; prm.mode = mode of run 0
+    RunBuf run[MAX_RUNS];
+    uint32_t n_runs = 1, sel_run = 0;             // sel_run: the run b2a_fetch_ops / b2a_copy_ops / b2a_batch_download read
+    uint64_t n_launched = 0;                      // (segment, run) launches so far: they alternate over the lanes
     uint64_t n_pairs = 0;
     int K = 0;
     int tb_opt = 0;                               // walker tuning bits (B2A_TB_OPT overrides, for experiments)
@@ -156,10 +169,8 @@ struct b2a_ctx {
     DevBuf<uint8_t> d_pat, d_txt;
     DevBuf<uint64_t> d_pat_off, d_txt_off, d_code_off, d_ops_off;
     DevBuf<PPDesc> d_pps;
-    DevBuf<uint32_t> d_ops, d_nops;
+    DevBuf<uint32_t> d_nops;                      // affine only
     DevBuf<AlphaInfo> d_alpha;                    // one per segment + one for the whole batch (wide32)
-    DevBuf<PairResult> d_results;
-    DevBuf<int4> d_endcell;                       // local mode: end cell per pair, written by the short16 fill epilogue
     HostBuf<PPDesc> h_pps;
     HostBuf<uint64_t> h_code_off, h_ops_off;
     HostBuf<AlphaInfo> h_alpha;
@@ -245,22 +256,22 @@ cudaError_t launch_fill(int K, int R, bool local, const FillArgs& a, cudaStream_
     }
     return cudaErrorInvalidValue;
 }
+// The per-thread walk lives on L1 hits (measured: any shared-memory carve-out costs 2-4x): ask for all of it.  Function attributes
+// are per DEVICE, so every context sets them after its cudaSetDevice (b2a_create), not once per process.
+void set_kernel_attributes() {
+    cudaFuncSetAttribute(short16_traceback_kernel<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(short16_traceback_kernel<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(short16_traceback_kernel<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(short16_traceback_kernel<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(short16_traceback_kernel<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(short16_traceback_kernel<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaGetLastError();
+}
 cudaError_t launch_tb(int K, bool local, const TbArgs& a, cudaStream_t st) {
     const unsigned threads = TB_THREADS, grid = (2u * a.n_pp + threads - 1) / threads;
-    const unsigned pad = 0;
-    static const bool once = []() {            // the walk lives on L1 hits (measured: any shared-memory carve-out costs 2-4x): ask for all of it
-        cudaFuncSetAttribute(short16_traceback_kernel<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-        cudaFuncSetAttribute(short16_traceback_kernel<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-        cudaFuncSetAttribute(short16_traceback_kernel<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-        cudaFuncSetAttribute(short16_traceback_kernel<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-        cudaFuncSetAttribute(short16_traceback_kernel<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-        cudaFuncSetAttribute(short16_traceback_kernel<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-        return true;
-    }();
-    (void)once;
     switch (K * 2 + (local ? 1 : 0)) {
-        case 4:  short16_traceback_kernel<2, false><<<grid, threads, pad, st>>>(a); break;
-        case 5:  short16_traceback_kernel<2, true><<<grid, threads, pad, st>>>(a); break;
+        case 4:  short16_traceback_kernel<2, false><<<grid, threads, 0, st>>>(a); break;
+        case 5:  short16_traceback_kernel<2, true><<<grid, threads, 0, st>>>(a); break;
         case 8:  short16_traceback_kernel<4, false><<<grid, threads, 0, st>>>(a); break;
         case 9:  short16_traceback_kernel<4, true><<<grid, threads, 0, st>>>(a); break;
         case 16: short16_traceback_kernel<8, false><<<grid, threads, 0, st>>>(a); break;
@@ -357,7 +368,7 @@ int wide_plan(b2a_ctx* ctx, const uint64_t* pat_off, const uint64_t* txt_off, bo
     return B2A_OK;
 }
 
-int wide_fill(b2a_ctx* ctx, cudaStream_t st, uint64_t* launches)
+int wide_fill(b2a_ctx* ctx, int r, cudaStream_t st, uint64_t* launches)
 {
     WideState& W = ctx->wide;
     if (W.tasks.empty()) return B2A_OK;
@@ -374,26 +385,12 @@ int wide_fill(b2a_ctx* ctx, cudaStream_t st, uint64_t* launches)
     a.alpha = ctx->d_alpha.p + (ctx->alpha_slots - 1);
     const unsigned need = (unsigned)((W.tasks.size() + WIDE_WARPS - 1) / WIDE_WARPS);
     const unsigned grid = std::min<unsigned>(need, (unsigned)ctx->sm_count * 8u);
-    static const bool dbg = std::getenv("B2A_WIDE_DEBUG") != nullptr;
-    unsigned long long* d_dbg = nullptr;
-    if (dbg) { CU(cudaMalloc((void**)&d_dbg, W.tasks.size() * 64)); CU(cudaMemsetAsync(d_dbg, 0, W.tasks.size() * 64, st)); a.debug = d_dbg; }
-    CU(launch_wide_fill(W.K, prm.mode == B2A_MODE_LOCAL, W.store, W.alpha4, a, grid, st));
+    CU(launch_wide_fill(W.K, ctx->run[r].mode == B2A_MODE_LOCAL, W.store, W.alpha4, a, grid, st));
     ++*launches;
-    if (dbg) {
-        std::vector<unsigned long long> h(W.tasks.size() * 8);
-        CU(cudaMemcpyAsync(h.data(), d_dbg, h.size() * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        cudaFree(d_dbg);
-        const unsigned long long t0 = h[0];
-        for (size_t k = 0; k < W.tasks.size(); k += std::max<size_t>(1, W.tasks.size() / 40))
-            std::fprintf(stderr, "[wide dbg] band %5u: blk0 waited %8.2f us | ring +%5.2f steps +%5.2f stores +%5.2f | blk1 wait +%5.2f compute +%5.2f | done %9.2f\n",
-                         W.tasks[k].band, (h[8 * k + 1] - t0) * 1e-3, (h[8 * k + 2] - h[8 * k + 1]) * 1e-3, (h[8 * k + 3] - h[8 * k + 2]) * 1e-3,
-                         (h[8 * k + 4] - h[8 * k + 3]) * 1e-3, (h[8 * k + 5] - h[8 * k + 4]) * 1e-3, (h[8 * k + 6] - h[8 * k + 5]) * 1e-3, (h[8 * k + 7] - t0) * 1e-3);
-    }
     return B2A_OK;
 }
 
-int wide_traceback(b2a_ctx* ctx, cudaStream_t st, uint64_t* launches, bool score_only)
+int wide_traceback(b2a_ctx* ctx, int r, cudaStream_t st, uint64_t* launches, bool score_only)
 {
     WideState& W = ctx->wide;
     if (W.pairs.empty()) return B2A_OK;
@@ -401,12 +398,12 @@ int wide_traceback(b2a_ctx* ctx, cudaStream_t st, uint64_t* launches, bool score
     WideTbArgs a{};
     a.pat = ctx->d_pat.p; a.txt = ctx->d_txt.p; a.pairs = W.d_pairs.p; a.n_wide = (uint32_t)W.pairs.size();
     a.codes = W.d_codes.p; a.rowbest = W.d_rowbest.p; a.final_score = W.d_final.p;
-    a.results = ctx->d_results.p;
-    a.ops = (prm.flags & B2A_WANT_OPS) && !score_only ? ctx->d_ops.p : nullptr;
+    a.results = ctx->run[r].d_results.p;
+    a.ops = (prm.flags & B2A_WANT_OPS) && !score_only ? ctx->run[r].d_ops.p : nullptr;
     a.ops_off = ctx->d_ops_off.p;
     a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.score_only = score_only ? 1 : 0;
     a.opt = (ctx->tb_opt & ~4) | ((prm.flags & B2A_TIE_HW4) ? 4 : 0);
-    CU(launch_wide_tb(W.K, prm.mode == B2A_MODE_LOCAL, a, st));
+    CU(launch_wide_tb(W.K, ctx->run[r].mode == B2A_MODE_LOCAL, a, st));
     ++*launches;
     return B2A_OK;
 }
@@ -414,43 +411,48 @@ int wide_traceback(b2a_ctx* ctx, cudaStream_t st, uint64_t* launches, bool score
 // ---------------------------------------------------------------------------------------------
 // short16 family: segments
 // ---------------------------------------------------------------------------------------------
-cudaEvent_t* seg_events(b2a_ctx* ctx, size_t si) {          // 4 events per segment, created on demand
-    while (ctx->ev_pool.size() < 4 * (si + 1)) {
+// 4 events per (segment, run), created on demand: inputs ready (run 0's slot only), fill start, fill end, traceback end
+cudaEvent_t* seg_events(b2a_ctx* ctx, size_t si, int r = 0) {
+    const size_t slot = si * MAX_RUNS + (size_t)r;
+    while (ctx->ev_pool.size() < 4 * (slot + 1)) {
         cudaEvent_t e = nullptr;
         if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
         ctx->ev_pool.push_back(e);
     }
-    return ctx->ev_pool.data() + 4 * si;
+    return ctx->ev_pool.data() + 4 * slot;
 }
 
-// fill + traceback kernels of one segment on its lane
-int launch_segment(b2a_ctx* ctx, size_t si, uint64_t* launches)
+// fill + traceback kernels of one segment for run r, on the next lane
+int launch_segment(b2a_ctx* ctx, size_t si, int r, uint64_t* launches)
 {
     Segment& sg = ctx->segs[si];
     if (sg.classes.empty() || sg.flagged) return B2A_OK;
     const b2a_params& prm = ctx->prm;
-    const bool local = prm.mode == B2A_MODE_LOCAL, want_ops = (prm.flags & B2A_WANT_OPS) != 0;
-    Lane& ln = ctx->lanes[sg.lane];
+    RunBuf& rb = ctx->run[r];
+    const int mode = rb.mode;
+    const bool local = mode == B2A_MODE_LOCAL, want_ops = (prm.flags & B2A_WANT_OPS) != 0;
+    Lane& ln = ctx->lanes[ctx->n_launched++ % (uint64_t)ctx->n_lanes];
     cudaStream_t st = ctx->s_fill;
-    cudaEvent_t* ev = seg_events(ctx, si);
-    if (!ev) return fail(ctx, B2A_ERR_CUDA, "cudaEventCreate failed");
+    cudaEvent_t* ev = seg_events(ctx, si, r);
+    cudaEvent_t* ev_in = seg_events(ctx, si, 0);
+    if (!ev || !ev_in) return fail(ctx, B2A_ERR_CUDA, "cudaEventCreate failed");
     if (sg.chunks > ln.codes.cap || sg.rowbest_words > ln.rowbest.cap) {
         CU(cudaStreamSynchronize(ctx->s_fill)); CU(cudaStreamSynchronize(ctx->s_tb));   // the lane's record is about to be reallocated
         CU(ln.codes.reserve(sg.chunks));
         if (local) CU(ln.rowbest.reserve(sg.rowbest_words));
     }
-    CU(cudaStreamWaitEvent(st, ev[0], 0));                   // inputs + plan of this segment are on the device
+    CU(cudaStreamWaitEvent(st, ev_in[0], 0));                // inputs + plan of this segment are on the device
     CU(cudaStreamWaitEvent(st, ln.tb_done, 0));              // the previous user of this lane's record has been walked
     CU(cudaEventRecord(ev[1], st));
     const AlphaInfo* alpha = ctx->d_alpha.p + si;
     for (const ClassRange& c : sg.classes) {
         Short16Plan pl{0, 0, 0};
-        short16_plan(prm.mode, (uint32_t)c.R * 32u, c.max_n, prm.match, prm.mismatch, prm.gap, pl);   // bias for the class' largest shape
+        short16_plan(mode, (uint32_t)c.R * 32u, c.max_n, prm.match, prm.mismatch, prm.gap, pl);   // bias for the class' largest shape
         FillArgs a{};
         a.pat = ctx->d_pat.p; a.txt = ctx->d_txt.p; a.pat_off = ctx->d_pat_off.p; a.txt_off = ctx->d_txt_off.p;
         a.pps = ctx->d_pps.p + sg.pp_first + c.first; a.code_off = ctx->d_code_off.p + sg.pp_first + c.first; a.codes = ln.codes.p;
         a.rowbest = local ? ln.rowbest.p + (size_t)c.first * c.R * 32 : nullptr;
-        a.endcell = ctx->d_endcell.p;
+        a.endcell = rb.d_endcell.p;
         a.n_pp = c.count;
         a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.bias = pl.bias;
         a.radix = 1u << ctx->K;
@@ -463,13 +465,13 @@ int launch_segment(b2a_ctx* ctx, size_t si, uint64_t* launches)
     CU(cudaStreamWaitEvent(st, ev[2], 0));
     for (const ClassRange& c : sg.classes) {
         Short16Plan pl{0, 0, 0};
-        short16_plan(prm.mode, (uint32_t)c.R * 32u, c.max_n, prm.match, prm.mismatch, prm.gap, pl);
+        short16_plan(mode, (uint32_t)c.R * 32u, c.max_n, prm.match, prm.mismatch, prm.gap, pl);
         TbArgs a{};
         a.pat = ctx->d_pat.p; a.txt = ctx->d_txt.p; a.pat_off = ctx->d_pat_off.p; a.txt_off = ctx->d_txt_off.p;
         a.pps = ctx->d_pps.p + sg.pp_first + c.first; a.code_off = ctx->d_code_off.p + sg.pp_first + c.first; a.codes = ln.codes.p;
         a.rowbest = local ? ln.rowbest.p + (size_t)c.first * c.R * 32 : nullptr;
-        a.endcell = ctx->d_endcell.p;
-        a.results = ctx->d_results.p; a.ops = want_ops ? ctx->d_ops.p : nullptr; a.ops_off = ctx->d_ops_off.p;
+        a.endcell = rb.d_endcell.p;
+        a.results = rb.d_results.p; a.ops = want_ops ? rb.d_ops.p : nullptr; a.ops_off = ctx->d_ops_off.p;
         a.n_pp = c.count; a.R = c.R;
         a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.bias = pl.bias;
         a.opt = ctx->tb_opt;
@@ -526,7 +528,7 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
     CU(W.d_progress.reserve(1));
     if (trace) {
         ctx->h_ops_off.p[n] = opsw;
-        CU(ctx->d_ops.reserve(opsw)); CU(ctx->d_ops_off.reserve(n + 1)); CU(ctx->d_nops.reserve(n));
+        CU(ctx->run[0].d_ops.reserve(opsw)); CU(ctx->d_ops_off.reserve(n + 1)); CU(ctx->d_nops.reserve(n));
         CU(cudaMemcpyAsync(ctx->d_ops_off.p, ctx->h_ops_off.p, (n + 1) * 8, cudaMemcpyHostToDevice, st));
         if (n) CU(cudaMemsetAsync(ctx->d_nops.p, 0, n * 4, st));
     }
@@ -602,7 +604,7 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
                          else affine32_score_kernel<false, false, AFFINE_R_SCORE><<<grid, WIDE_WARPS * 32, 0, st>>>(a); }
             CU(cudaGetLastError()); ++launches;
             if (trace) {
-                AffineTbArgs ta{W.d_pairs.p, (uint32_t)W.pairs.size(), reinterpret_cast<const uint4*>(W.d_codes.p), ctx->d_nops.p, ctx->d_ops.p, ctx->d_ops_off.p};
+                AffineTbArgs ta{W.d_pairs.p, (uint32_t)W.pairs.size(), reinterpret_cast<const uint4*>(W.d_codes.p), ctx->d_nops.p, ctx->run[0].d_ops.p, ctx->d_ops_off.p};
                 affine32_traceback_kernel<<<(unsigned)((W.pairs.size() + WIDE_TB_WARPS - 1) / WIDE_TB_WARPS), WIDE_TB_WARPS * 32, 0, st>>>(ta);
                 CU(cudaGetLastError()); ++launches;
                 ctx->fill_bytes += W.chunks * sizeof(Chunk);
@@ -634,7 +636,7 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
                 // one gap run along a border (hw3.cpp:42-53): all 'D' (column 0) or all 'I' (row 0); written from the host
                 const uint32_t len = sp.m + sp.n, op = sp.n == 0 ? OP_D : OP_I;
                 std::vector<uint32_t> w(((uint64_t)len + 15) / 16 + 1, op * 0x55555555u);
-                if (len) CU(cudaMemcpy(ctx->d_ops.p + ctx->h_ops_off.p[k], w.data(), (((uint64_t)len + 15) / 16) * 4, cudaMemcpyHostToDevice));
+                if (len) CU(cudaMemcpy(ctx->run[0].d_ops.p + ctx->h_ops_off.p[k], w.data(), (((uint64_t)len + 15) / 16) * 4, cudaMemcpyHostToDevice));
                 nops[k] = len;
             }
             if (n_ops_out) n_ops_out[k] = nops[k];
@@ -656,21 +658,32 @@ bool is_pinned(const void* p) {
 // Cuts the batch into segments, queues the copies, plans, and (pipelined == true) launches every
 // segment as soon as it is planned and returns the result records.  With pipelined == false the
 // batch ends up resident and planned; b2a_batch_run launches it.
-int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const uint64_t* pat_off,
-                  const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs, bool pipelined, b2a_result* results)
+int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const uint8_t* pat, const uint64_t* pat_off,
+                  const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs, bool pipelined, b2a_result* const* results)
 {
     if (!ctx) return B2A_ERR_ARG;
-    if (!prm || !pat_off || !txt_off || (prm->mode != B2A_MODE_GLOBAL && prm->mode != B2A_MODE_LOCAL))
-        return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: null argument or bad mode");
+    if (!prms || !pat_off || !txt_off || n_runs < 1 || n_runs > (uint32_t)MAX_RUNS)
+        return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: null argument or bad run count");
+    const b2a_params* prm = &prms[0];
+    bool any_local = false;
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        const b2a_params& q = prms[r];
+        if (q.mode != B2A_MODE_GLOBAL && q.mode != B2A_MODE_LOCAL) return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: bad mode");
+        if ((q.flags & B2A_TIE_HW4) && q.mode != B2A_MODE_GLOBAL) return fail(ctx, B2A_ERR_ARG, "B2A_TIE_HW4 applies to the global mode only");
+        if (q.match != prm->match || q.mismatch != prm->mismatch || q.gap != prm->gap || ((q.flags ^ prm->flags) & ~B2A_TIE_HW4))
+            return fail(ctx, B2A_ERR_ARG, "b2a_align_batch_multi: the runs of one batch share scoring and flags (they differ in mode)");
+        if (pipelined && n_pairs && (!results || !results[r])) return fail(ctx, B2A_ERR_ARG, "b2a_align_batch: null results");
+        any_local |= q.mode == B2A_MODE_LOCAL;
+    }
     if (n_pairs > 0x7FFFFFF0ull) return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: too many pairs");
-    if (pipelined && !results && n_pairs) return fail(ctx, B2A_ERR_ARG, "b2a_align_batch: null results");
-    if ((prm->flags & B2A_TIE_HW4) && prm->mode != B2A_MODE_GLOBAL) return fail(ctx, B2A_ERR_ARG, "B2A_TIE_HW4 applies to the global mode only");
     CU(cudaSetDevice(ctx->device));
     // a previous batch may still own the pinned plan arrays / device buffers
     CU(cudaStreamSynchronize(ctx->s_copy)); CU(cudaStreamSynchronize(ctx->s_down));
     CU(cudaStreamSynchronize(ctx->s_fill)); CU(cudaStreamSynchronize(ctx->s_tb));
     ctx->have_batch = false; ctx->ran = false; ctx->affine_ops = false;
     ctx->prm = *prm; ctx->n_pairs = n_pairs;
+    ctx->n_runs = n_runs; ctx->sel_run = 0; ctx->n_launched = 0;
+    for (uint32_t r = 0; r < n_runs; ++r) ctx->run[r].mode = prms[r].mode;
     ctx->segs.clear(); ctx->wide_pairs.clear();
     ctx->cells = ctx->fill_bytes = ctx->launches = ctx->h2d = ctx->d2h = 0;
     ctx->n_pp_total = 0;
@@ -679,8 +692,14 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
     // Appendix A.8: (m+n)*max|score| must stay inside int32 (beyond that the reference itself is undefined)
     const int64_t smag = std::max<int64_t>({std::llabs((long long)prm->match), std::llabs((long long)prm->mismatch),
                                             std::llabs((long long)prm->gap)});
-    const bool local = prm->mode == B2A_MODE_LOCAL, want_ops = (prm->flags & B2A_WANT_OPS) != 0;
+    const bool want_ops = (prm->flags & B2A_WANT_OPS) != 0;
     const bool score_only = (prm->flags & B2A_SCORE_ONLY) != 0;
+    // one plan serves every run: a pair is a short16 pair iff the s16x2 record holds it in every run's mode (NW is the stricter one)
+    auto plan_all = [&](uint32_t m, uint32_t n, Short16Plan& pl) {
+        for (uint32_t r = 0; r < n_runs; ++r)
+            if (!short16_plan(prms[r].mode, m, n, prm->match, prm->mismatch, prm->gap, pl)) return false;
+        return true;
+    };
     ctx->K = delta_bits(prm->match, prm->mismatch, prm->gap);
     const int CS = ctx->K ? chunk_steps(ctx->K) : 24;
 
@@ -691,12 +710,17 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
     CU(ctx->d_pat_off.reserve(n_pairs + 1)); CU(ctx->d_txt_off.reserve(n_pairs + 1));
     CU(ctx->d_pps.reserve(n_pairs)); CU(ctx->d_code_off.reserve(n_pairs));
     CU(ctx->h_pps.reserve(n_pairs)); CU(ctx->h_code_off.reserve(n_pairs)); CU(ctx->h_ops_off.reserve(n_pairs + 1));
-    CU(ctx->d_results.reserve(n_pairs));
-    if (local) CU(ctx->d_endcell.reserve(n_pairs));
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        RunBuf& rb = ctx->run[r];
+        CU(rb.d_results.reserve(n_pairs));
+        if (rb.mode == B2A_MODE_LOCAL) CU(rb.d_endcell.reserve(n_pairs));
+        if (want_ops) CU(rb.d_ops.reserve(ops_bound));
+    }
     CU(ctx->d_alpha.reserve(ctx->alpha_slots)); CU(ctx->h_alpha.reserve(ctx->alpha_slots));
-    if (want_ops) { CU(ctx->d_ops.reserve(ops_bound)); CU(ctx->d_ops_off.reserve(n_pairs + 1)); }
+    if (want_ops) CU(ctx->d_ops_off.reserve(n_pairs + 1));
     CU(cudaMemsetAsync(ctx->d_alpha.p, 0, ctx->alpha_slots * sizeof(AlphaInfo), ctx->s_copy));
-    const bool async_down = pipelined && results && is_pinned(results);
+    bool async_down = pipelined && results;
+    for (uint32_t r = 0; r < n_runs && async_down; ++r) async_down = is_pinned(results[r]);
     uint64_t launches = 0;
     using clk = std::chrono::steady_clock;
     const clk::time_point t_begin = clk::now();
@@ -728,7 +752,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
             const uint64_t key = (m64 << 32) | n64;
             if (key != plan_key) {
                 plan_key = key;
-                plan_ok = !score_only && short16_plan(prm->mode, (uint32_t)m64, (uint32_t)n64, prm->match, prm->mismatch, prm->gap, pl);
+                plan_ok = !score_only && plan_all((uint32_t)m64, (uint32_t)n64, pl);
                 pair_bytes = plan_ok ? (uint64_t)pl.R * num_chunks((uint32_t)n64, CS) * 32u * sizeof(Chunk) / 2 : 0;
             }
             seg_bytes += pair_bytes;
@@ -739,7 +763,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
         const size_t si = ctx->segs.size();
         ctx->segs.emplace_back();
         Segment& sg = ctx->segs.back();
-        sg.first = first; sg.count = k - first; sg.lane = (int)(si % (size_t)ctx->n_lanes);
+        sg.first = first; sg.count = k - first;
         sg.pp_first = ctx->n_pp_total;
         if (si + 2 > ctx->alpha_slots) return fail(ctx, B2A_ERR_STATE, "internal: segment count exceeds its bound");
 
@@ -761,7 +785,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
             const uint64_t m64 = pat_off[q + 1] - pat_off[q], n64 = txt_off[q + 1] - txt_off[q];
             const uint32_t m = (uint32_t)m64, n = (uint32_t)n64;
             const uint64_t key = (m64 << 32) | n64;
-            if (key != plan_key) { plan_key = key; plan_ok = !score_only && short16_plan(prm->mode, m, n, prm->match, prm->mismatch, prm->gap, pl); }
+            if (key != plan_key) { plan_key = key; plan_ok = !score_only && plan_all(m, n, pl); }
             if (!plan_ok) { ctx->wide_pairs.push_back((uint32_t)q); ++sg.n_wide; continue; }
             if (have_last && key == last_key) { pps[pl.R].push_back(PPDesc{last_idx, (uint32_t)q, pp_pack(m, m), pp_pack(n, n)}); have_last = false; continue; }
             if (have_last) {                                             // the previous pair found no neighbour: park it
@@ -793,13 +817,13 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
             std::sort(left.begin(), left.end(), [](const Left& x, const Left& y) {
                 return x.R != y.R ? x.R < y.R : (x.n != y.n ? x.n < y.n : (x.m != y.m ? x.m < y.m : x.idx < y.idx)); });
             static const bool no_mix = std::getenv("B2A_NO_MIX") != nullptr;           // A/B switch for scripts/ragged_exp.py
-            const bool mix_ok = !no_mix && (!local || (prm->gap < 0 && prm->mismatch < 0));
+            const bool mix_ok = !no_mix && (!any_local || (prm->gap < 0 && prm->mismatch < 0));
             for (size_t q = 0; q < left.size(); ++q) {
                 const Left& x = left[q];
                 if (mix_ok && q + 1 < left.size() && left[q + 1].R == x.R) {
                     const Left& y = left[q + 1];
                     Short16Plan both{0, 0, 0};
-                    if (short16_plan(prm->mode, std::max(x.m, y.m), std::max(x.n, y.n), prm->match, prm->mismatch, prm->gap, both) && both.R == x.R) {
+                    if (plan_all(std::max(x.m, y.m), std::max(x.n, y.n), both) && both.R == x.R) {
                         const bool xfirst = x.idx < y.idx;               // low half = lower pair index (deterministic records)
                         const Left& lo = xfirst ? x : y; const Left& hi = xfirst ? y : x;
                         pps[x.R].push_back(PPDesc{lo.idx, hi.idx, pp_pack(lo.m, hi.m), pp_pack(lo.n, hi.n)});
@@ -824,7 +848,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
             rb = std::max<uint64_t>(rb, (uint64_t)(cr.first + cr.count) * R * 32u);
             sg.classes.push_back(cr);
         }
-        sg.n_pp = npp; sg.chunks = chunks; sg.rowbest_words = local ? rb : 0;
+        sg.n_pp = npp; sg.chunks = chunks; sg.rowbest_words = any_local ? rb : 0;
         ctx->n_pp_total += npp;
         ctx->fill_bytes += chunks * sizeof(Chunk);
         if (npp) {
@@ -856,12 +880,15 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
         if (ctx->trace) tr_host.push_back(ms_since(t_begin));
 
         if (pipelined) {
-            int rc = launch_segment(ctx, si, &launches);
-            if (rc != B2A_OK) return rc;
-            if (async_down && !sg.classes.empty()) {
-                CU(cudaStreamWaitEvent(ctx->s_down, ev[3], 0));
-                CU(cudaMemcpyAsync(results + first, ctx->d_results.p + first, sg.count * sizeof(b2a_result), cudaMemcpyDeviceToHost, ctx->s_down));
-                ctx->d2h += sg.count * sizeof(b2a_result);
+            for (uint32_t r = 0; r < n_runs; ++r) {              // every run's kernels follow the ONE upload of the segment
+                int rc = launch_segment(ctx, si, (int)r, &launches);
+                if (rc != B2A_OK) return rc;
+                if (async_down && !sg.classes.empty()) {
+                    cudaEvent_t* evr = seg_events(ctx, si, (int)r);
+                    CU(cudaStreamWaitEvent(ctx->s_down, evr[3], 0));
+                    CU(cudaMemcpyAsync(results[r] + first, ctx->run[r].d_results.p + first, sg.count * sizeof(b2a_result), cudaMemcpyDeviceToHost, ctx->s_down));
+                    ctx->d2h += sg.count * sizeof(b2a_result);
+                }
             }
         }
         if (ctx->trace) tr_host.push_back(ms_since(t_begin));
@@ -902,11 +929,12 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
 
     if (!pipelined) {
         // resident mode: size the lanes' records now so that b2a_batch_run never allocates
+        uint64_t nl = 0;                                          // b2a_batch_run hands the lanes out in launch order
         for (const Segment& sg : ctx->segs) {
-            if (sg.flagged) continue;
-            Lane& ln = ctx->lanes[sg.lane];
+            if (sg.flagged || sg.classes.empty()) continue;
+            Lane& ln = ctx->lanes[nl++ % (uint64_t)ctx->n_lanes];
             CU(ln.codes.reserve(sg.chunks));
-            if (local) CU(ln.rowbest.reserve(sg.rowbest_words));
+            if (any_local) CU(ln.rowbest.reserve(sg.rowbest_words));
         }
         CU(cudaStreamSynchronize(s0));
         ctx->launches = launches;
@@ -915,23 +943,24 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const
     }
 
     // ---- pipelined mode: the wide32 phase (if any) runs behind the segments, then the records come back ----
-    if (!ctx->wide_pairs.empty()) {
-        int rc = wide_fill(ctx, s0, &launches);
+    for (uint32_t r = 0; r < n_runs && !ctx->wide_pairs.empty(); ++r) {     // one record, the runs take turns in stream order
+        int rc = wide_fill(ctx, (int)r, s0, &launches);
         if (rc != B2A_OK) return rc;
-        rc = wide_traceback(ctx, s0, &launches, score_only);
+        rc = wide_traceback(ctx, (int)r, s0, &launches, score_only);
         if (rc != B2A_OK) return rc;
     }
     CU(cudaStreamSynchronize(s0));
     if (n_pairs && (!async_down || !ctx->wide_pairs.empty())) {
-        CU(cudaMemcpyAsync(results, ctx->d_results.p, n_pairs * sizeof(b2a_result), cudaMemcpyDeviceToHost, ctx->s_down));
-        ctx->d2h = n_pairs * sizeof(b2a_result);
+        for (uint32_t r = 0; r < n_runs; ++r)
+            CU(cudaMemcpyAsync(results[r], ctx->run[r].d_results.p, n_pairs * sizeof(b2a_result), cudaMemcpyDeviceToHost, ctx->s_down));
+        ctx->d2h = n_runs * n_pairs * sizeof(b2a_result);
     }
     CU(cudaStreamSynchronize(ctx->s_down));
     if (ctx->trace) {
         std::fprintf(stderr, "[b2a trace] %llu pairs, %zu segments, host total %.2f ms\n", (unsigned long long)n_pairs, ctx->segs.size(), ms_since(t_begin));
         for (size_t si = 0; si < ctx->segs.size(); ++si) {
             const Segment& sg = ctx->segs[si];
-            cudaEvent_t* ev = ctx->ev_pool.data() + 4 * si;
+            cudaEvent_t* ev = seg_events(ctx, si, 0);
             float g[4] = {0, 0, 0, 0};
             for (int e = 0; e < 4; ++e) if (e == 0 || !(sg.classes.empty() || sg.flagged)) cudaEventElapsedTime(&g[e], ctx->ev_begin, ev[e]);
             std::fprintf(stderr, "[b2a trace] seg %2zu pairs %7llu | host: scanned %6.2f planned %6.2f launched %6.2f | device: inputs %6.2f fill %6.2f..%6.2f tb ..%6.2f\n",
@@ -966,6 +995,7 @@ b2a_ctx* b2a_create(int device) {
         delete ctx; cudaGetLastError(); return nullptr;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    set_kernel_attributes();
     if (const char* e = std::getenv("B2A_TB_OPT")) ctx->tb_opt = std::atoi(e);
     if (const char* e = std::getenv("B2A_TRACE")) ctx->trace = std::atoi(e) != 0;
     if (const char* e = std::getenv("B2A_LANES")) ctx->n_lanes = std::max(1, std::min(MAX_LANES, std::atoi(e)));
@@ -1000,7 +1030,8 @@ void b2a_destroy(b2a_ctx* ctx) {
     if (ctx->s_tb) cudaStreamDestroy(ctx->s_tb);
     ctx->d_pat.release(); ctx->d_txt.release(); ctx->d_pat_off.release(); ctx->d_txt_off.release();
     ctx->d_code_off.release(); ctx->d_ops_off.release(); ctx->d_pps.release();
-    ctx->d_ops.release(); ctx->d_alpha.release(); ctx->d_results.release(); ctx->d_endcell.release(); ctx->d_nops.release();
+    ctx->d_alpha.release(); ctx->d_nops.release();
+    for (auto& rb : ctx->run) rb.release();
     ctx->h_pps.release(); ctx->h_code_off.release(); ctx->h_ops_off.release(); ctx->h_alpha.release();
     ctx->wide.release();
     for (auto& e : ctx->ev_pool) if (e) cudaEventDestroy(e);
@@ -1023,7 +1054,7 @@ void b2a_host_free(void* p) { if (p) cudaFreeHost(p); }
 int b2a_batch_upload(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const uint64_t* pat_off,
                      const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs)
 {
-    return batch_prepare(ctx, prm, pat, pat_off, txt, txt_off, n_pairs, false, nullptr);
+    return batch_prepare(ctx, prm, 1, pat, pat_off, txt, txt_off, n_pairs, false, nullptr);
 }
 
 int b2a_batch_run(b2a_ctx* ctx, float* fill_ms, float* traceback_ms)
@@ -1035,25 +1066,26 @@ int b2a_batch_run(b2a_ctx* ctx, float* fill_ms, float* traceback_ms)
     const bool score_only = (prm.flags & B2A_SCORE_ONLY) != 0;
     uint64_t launches = 0;
     cudaStream_t s0 = ctx->s_fill;
+    ctx->n_launched = 0;
     CU(cudaEventRecord(ctx->ev_begin, s0));
     for (size_t si = 0; si < ctx->segs.size(); ++si) {
-        int rc = launch_segment(ctx, si, &launches);
+        int rc = launch_segment(ctx, si, 0, &launches);
         if (rc != B2A_OK) return rc;
     }
     { int rc = join_tracebacks(ctx); if (rc != B2A_OK) return rc; }
     cudaEvent_t* wev = seg_events(ctx, ctx->segs.size());          // spare slot: wide32 phase
     if (!wev) return fail(ctx, B2A_ERR_CUDA, "cudaEventCreate failed");
     CU(cudaEventRecord(wev[1], s0));
-    if (!ctx->wide_pairs.empty()) { int rc = wide_fill(ctx, s0, &launches); if (rc != B2A_OK) return rc; }
+    if (!ctx->wide_pairs.empty()) { int rc = wide_fill(ctx, 0, s0, &launches); if (rc != B2A_OK) return rc; }
     CU(cudaEventRecord(wev[2], s0));
-    if (!ctx->wide_pairs.empty()) { int rc = wide_traceback(ctx, s0, &launches, score_only); if (rc != B2A_OK) return rc; }
+    if (!ctx->wide_pairs.empty()) { int rc = wide_traceback(ctx, 0, s0, &launches, score_only); if (rc != B2A_OK) return rc; }
     CU(cudaEventRecord(wev[3], s0));
     CU(cudaEventRecord(ctx->ev_end, s0));
     CU(cudaStreamSynchronize(s0));
     float f = 0, t = 0, tot = 0, x = 0;
     for (size_t si = 0; si <= ctx->segs.size(); ++si) {
         if (si < ctx->segs.size() && (ctx->segs[si].classes.empty() || ctx->segs[si].flagged)) continue;
-        cudaEvent_t* ev = ctx->ev_pool.data() + 4 * si;
+        cudaEvent_t* ev = seg_events(ctx, si, 0);
         CU(cudaEventElapsedTime(&x, ev[1], ev[2])); f += x;
         CU(cudaEventElapsedTime(&x, ev[2], ev[3])); t += x;
     }
@@ -1082,7 +1114,7 @@ int b2a_batch_download(b2a_ctx* ctx, b2a_result* results)
     if (!results && ctx->n_pairs) return fail(ctx, B2A_ERR_ARG, "b2a_batch_download: null results");
     CU(cudaSetDevice(ctx->device));
     if (ctx->n_pairs) {
-        CU(cudaMemcpyAsync(results, ctx->d_results.p, ctx->n_pairs * sizeof(b2a_result), cudaMemcpyDeviceToHost, ctx->s_down));
+        CU(cudaMemcpyAsync(results, ctx->run[ctx->sel_run].d_results.p, ctx->n_pairs * sizeof(b2a_result), cudaMemcpyDeviceToHost, ctx->s_down));
         CU(cudaStreamSynchronize(ctx->s_down));
         ctx->d2h += ctx->n_pairs * sizeof(b2a_result);
     }
@@ -1092,7 +1124,34 @@ int b2a_batch_download(b2a_ctx* ctx, b2a_result* results)
 int b2a_align_batch(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pat, const uint64_t* pat_off,
                     const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs, b2a_result* results)
 {
-    return batch_prepare(ctx, prm, pat, pat_off, txt, txt_off, n_pairs, true, results);
+    return batch_prepare(ctx, prm, 1, pat, pat_off, txt, txt_off, n_pairs, true, &results);
+}
+
+int b2a_align_batch_multi(b2a_ctx* ctx, const b2a_params* prm, uint32_t n_runs, const uint8_t* pat, const uint64_t* pat_off,
+                          const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs, b2a_result* const* results)
+{
+    return batch_prepare(ctx, prm, n_runs, pat, pat_off, txt, txt_off, n_pairs, true, results);
+}
+
+int b2a_select_run(b2a_ctx* ctx, uint32_t run)
+{
+    if (!ctx) return B2A_ERR_ARG;
+    if (run >= ctx->n_runs) return fail(ctx, B2A_ERR_ARG, "b2a_select_run: the last batch had fewer runs");
+    ctx->sel_run = run;
+    return B2A_OK;
+}
+
+int b2a_host_register(void* p, size_t bytes)
+{
+    if (!p || !bytes) return B2A_ERR_ARG;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return B2A_ERR_CUDA; }
+    return B2A_OK;
+}
+int b2a_host_unregister(void* p)
+{
+    if (!p) return B2A_ERR_ARG;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return B2A_ERR_CUDA; }
+    return B2A_OK;
 }
 
 int b2a_affine_score_batch(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
@@ -1146,7 +1205,7 @@ int64_t b2a_affine_fetch_ops(b2a_ctx* ctx, uint64_t pair, char* ops, uint64_t op
     if (n_ops > ops_cap) return fail(ctx, B2A_ERR_ARG, "b2a_affine_fetch_ops: buffer too small");
     const uint64_t nw = ((uint64_t)n_ops + 15) / 16;
     std::vector<uint32_t> w(nw);
-    if (nw) CU(cudaMemcpy(w.data(), ctx->d_ops.p + ctx->h_ops_off.p[pair], nw * 4, cudaMemcpyDeviceToHost));
+    if (nw) CU(cudaMemcpy(w.data(), ctx->run[0].d_ops.p + ctx->h_ops_off.p[pair], nw * 4, cudaMemcpyDeviceToHost));
     ctx->d2h += 4 + nw * 4;
     static const char L[4] = {'M', 'D', 'I', '?'};
     for (uint32_t t = 0; t < n_ops; ++t) ops[t] = L[(w[t >> 4] >> (2 * (t & 15))) & 3u];
@@ -1178,15 +1237,14 @@ int b2a_affine_star_scores(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_
     int rc = affine_run(ctx, match, mismatch, gap_open, gap_extend, seqs, n_seqs ? seq_off[n_seqs] : 0, nullptr, 0, true, specs, sc.data(), false, nullptr);
     if (rc != B2A_OK) return rc;
     if (pair_scores) std::copy(sc.begin(), sc.end(), pair_scores);
-    if (sum_scores) {                                                        // hw3.cpp:238-239 (partial sums of this pair range)
-        for (uint32_t i = 0; i < n_seqs; ++i) sum_scores[i] = 0;
-        for (size_t k = 0; k < ij.size(); ++k) { sum_scores[ij[k].first] += sc[k]; sum_scores[ij[k].second] += sc[k]; }
-    }
-    if (center) {                                                            // hw3.cpp:243-251: first strict maximum
+    std::vector<int32_t> sums(n_seqs, 0);                                    // hw3.cpp:238-239 (partial sums of this pair range)
+    for (size_t k = 0; k < ij.size(); ++k) { sums[ij[k].first] += sc[k]; sums[ij[k].second] += sc[k]; }
+    if (sum_scores) std::copy(sums.begin(), sums.end(), sum_scores);
+    if (center) {                                                            // hw3.cpp:243-251: first strict maximum -- of COMPLETE sums only
         *center = -1;
-        if (sum_scores && n_seqs) {
+        if (n_seqs && pair_first == 0 && count == total) {
             int64_t c = 0;
-            for (uint32_t i = 1; i < n_seqs; ++i) if (sum_scores[i] > sum_scores[c]) c = i;
+            for (uint32_t i = 1; i < n_seqs; ++i) if (sums[i] > sums[c]) c = i;
             *center = c;
         }
     }
@@ -1225,11 +1283,12 @@ int64_t b2a_fetch_ops(b2a_ctx* ctx, uint64_t pair, char* ops, uint64_t ops_cap)
     if (pair >= ctx->n_pairs) return fail(ctx, B2A_ERR_ARG, "b2a_fetch_ops: pair index out of range");
     CU(cudaSetDevice(ctx->device));
     PairResult r;
-    CU(cudaMemcpy(&r, ctx->d_results.p + pair, sizeof(r), cudaMemcpyDeviceToHost));
+    const RunBuf& rb = ctx->run[ctx->sel_run];
+    CU(cudaMemcpy(&r, rb.d_results.p + pair, sizeof(r), cudaMemcpyDeviceToHost));
     if (r.n_ops > ops_cap) return fail(ctx, B2A_ERR_ARG, "b2a_fetch_ops: buffer too small");
     const uint64_t nw = ((uint64_t)r.n_ops + 15) / 16;
     std::vector<uint32_t> w(nw);
-    if (nw) CU(cudaMemcpy(w.data(), ctx->d_ops.p + ctx->h_ops_off.p[pair], nw * 4, cudaMemcpyDeviceToHost));
+    if (nw) CU(cudaMemcpy(w.data(), rb.d_ops.p + ctx->h_ops_off.p[pair], nw * 4, cudaMemcpyDeviceToHost));
     ctx->d2h += sizeof(r) + nw * 4;
     static const char L[4] = {'M', 'D', 'I', '?'};
     for (uint32_t t = 0; t < r.n_ops; ++t) ops[t] = L[(w[t >> 4] >> (2 * (t & 15))) & 3u];
@@ -1245,7 +1304,7 @@ int64_t b2a_copy_ops(b2a_ctx* ctx, uint32_t* ops_words, uint64_t cap_words, uint
     if (cap_words < ctx->total_ops_words) return fail(ctx, B2A_ERR_ARG, "b2a_copy_ops: buffer too small");
     CU(cudaSetDevice(ctx->device));
     if (ctx->total_ops_words) {
-        CU(cudaMemcpyAsync(ops_words, ctx->d_ops.p, ctx->total_ops_words * 4, cudaMemcpyDeviceToHost, ctx->s_down));
+        CU(cudaMemcpyAsync(ops_words, ctx->run[ctx->sel_run].d_ops.p, ctx->total_ops_words * 4, cudaMemcpyDeviceToHost, ctx->s_down));
         CU(cudaStreamSynchronize(ctx->s_down));
         ctx->d2h += ctx->total_ops_words * 4;
     }
@@ -1257,12 +1316,15 @@ int64_t b2a_debug_copy_record(b2a_ctx* ctx, void* chunks, uint64_t chunk_cap, vo
     if (!ctx) return B2A_ERR_ARG;
     if (!ctx->ran || ctx->segs.empty() || ctx->segs[0].classes.empty() || ctx->segs[0].flagged)
         return fail(ctx, B2A_ERR_STATE, "b2a_debug_copy_record: no short16 record");
+    // the first segment's record still sits in lane 0 only if no later (segment, run) launch reused that lane
+    if (ctx->n_launched > (uint64_t)ctx->n_lanes)
+        return fail(ctx, B2A_ERR_STATE, "b2a_debug_copy_record: the first segment's record has been overwritten (batch has more launches than lanes)");
     CU(cudaSetDevice(ctx->device));
-    const Segment& sg = ctx->segs[0];                       // the first segment's record still sits in its lane
-    const Lane& ln = ctx->lanes[sg.lane];
+    const Segment& sg = ctx->segs[0];
+    const Lane& ln = ctx->lanes[0];
     const uint64_t bytes = sg.chunks * sizeof(Chunk);
     if (chunks) CU(cudaMemcpy(chunks, ln.codes.p, std::min<uint64_t>(bytes, chunk_cap), cudaMemcpyDeviceToHost));
-    if (rowbest && ctx->prm.mode == B2A_MODE_LOCAL)
+    if (rowbest && ctx->run[0].mode == B2A_MODE_LOCAL)
         CU(cudaMemcpy(rowbest, ln.rowbest.p, std::min<uint64_t>(sg.rowbest_words * 4, rowbest_cap), cudaMemcpyDeviceToHost));
     return (int64_t)bytes;
 }

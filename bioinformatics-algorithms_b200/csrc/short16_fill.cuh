@@ -104,16 +104,19 @@ short16_fill_kernel(const FillArgs A)
     const uint8_t* tb = A.txt + A.txt_off[d.b];
 
     uint32_t staged = 0;                                  // text indices [0, staged) have been staged (multiple of 32)
-    uint32_t nxa = (uint32_t)lane < na ? ta[lane] : 0u, nxb = (uint32_t)lane < nb ? tb[lane] : 0u;   // bytes of the next block, one block ahead
+    // bytes of the next block, one block ahead; 0x100 = beyond this pair's own text (mixed-shape pair-pairs): scores as a mismatch against
+    // every pattern symbol, whatever bytes the alphabet holds (a NUL pad would MATCH a NUL pattern symbol)
+    uint32_t nxa = (uint32_t)lane < na ? ta[lane] : 0x100u, nxb = (uint32_t)lane < nb ? tb[lane] : 0x100u;
+    const uint32_t mmw = ((uint32_t)(A.mismatch - (LOCAL ? 0 : 2 * A.gap)) & 0xFFu) * 0x01010101u;
     auto stage_block = [&]() {
         const uint32_t slot = (staged + (uint32_t)lane) & 127u;
-        const uint2 e = make_uint2(s_tbl4[nxa], s_tbl4[nxb]);
+        const uint2 e = make_uint2((nxa & 0x100u) ? mmw : s_tbl4[nxa], (nxb & 0x100u) ? mmw : s_tbl4[nxb]);
         __syncwarp();
         ring[slot] = e; ring[slot + 128u] = e;
         __syncwarp();
         staged += 32u;
         const uint32_t x = staged + (uint32_t)lane;
-        nxa = x < na ? ta[x] : 0u; nxb = x < nb ? tb[x] : 0u;
+        nxa = x < na ? ta[x] : 0x100u; nxb = x < nb ? tb[x] : 0x100u;
     };
 
     // PRMT selectors of this lane's rows: byte0 = tableA[codeA], byte1 = its sign, byte2 = tableB[codeB], byte3 = its sign

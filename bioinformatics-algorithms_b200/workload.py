@@ -80,6 +80,27 @@ def config5(n_seqs=16, length=100_000, seed=483, divergence=0.10):
     return [mutate(rng, anc, divergence * 0.8, divergence * 0.1, divergence * 0.1) for _ in range(n_seqs)]
 
 
+def config5_shipped():
+    """The reference's own 16 x 100 kb input (Multiple_Sequence_Alignment/input16100000.fasta, committed gzip'ed under
+    tests/golden/): [(name, bytes)] read with hw3's rules (header = text after '>', all whitespace stripped, hw3.cpp:137-167)."""
+    import gzip, os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "input16100000.fasta.gz")
+    out, name, cur = [], None, []
+    for line in gzip.open(path, "rb").read().split(b"\n"):
+        line = b"".join(line.split())
+        if not line:
+            continue
+        if line.startswith(b">"):
+            if name is not None:
+                out.append((name, b"".join(cur)))
+            name, cur = line[1:].decode("latin-1"), []
+        else:
+            cur.append(line)
+    if name is not None:
+        out.append((name, b"".join(cur)))
+    return out
+
+
 def split(data, off):
     """packed -> list of bytes"""
     return [data[int(off[k]):int(off[k + 1])].tobytes() for k in range(len(off) - 1)]

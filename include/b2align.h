@@ -86,6 +86,10 @@ const char* b2a_last_error(const b2a_ctx* ctx);     /* text of the last failure 
 /* Pinned host memory for batch inputs/outputs (optional; pageable memory works, staged). */
 void*       b2a_host_alloc(size_t bytes);
 void        b2a_host_free(void* p);
+/* Pin memory the caller already owns (e.g. a POSIX shared-memory segment several one-GPU processes write their result records
+ * into: the "host gather" of a pair-sharded batch is then the device->host copies themselves).  Call after b2a_create. */
+int         b2a_host_register(void* p, size_t bytes);
+int         b2a_host_unregister(void* p);
 
 /* ---- the batch call: replaces the loop hw2.cpp:328-338 ------------------------------------ */
 /* Pair k aligns pattern bytes pat[pat_off[k] .. pat_off[k+1]) against text bytes
@@ -96,6 +100,17 @@ int b2a_align_batch(b2a_ctx* ctx, const b2a_params* prm,
                     const uint8_t* pat, const uint64_t* pat_off,
                     const uint8_t* txt, const uint64_t* txt_off,
                     uint64_t n_pairs, b2a_result* results);
+
+/* Several runs over ONE upload of the same pairs: run r aligns them under prm[r].  The runs share scoring and flags and differ in
+ * mode -- hw2's -g and -l over one batch (BASELINE config 2 asks for both).  Per segment the sequences cross PCIe once and the
+ * kernels of every run follow, so the copy is hidden behind n_runs times the work.  results[r] receives the n_pairs records of run r.
+ * b2a_select_run chooses which run b2a_fetch_ops / b2a_copy_ops / b2a_batch_download read afterwards (run 0 after the call). */
+#define B2A_MAX_RUNS 2
+int b2a_align_batch_multi(b2a_ctx* ctx, const b2a_params* prm, uint32_t n_runs,
+                          const uint8_t* pat, const uint64_t* pat_off,
+                          const uint8_t* txt, const uint64_t* txt_off,
+                          uint64_t n_pairs, b2a_result* const* results);
+int b2a_select_run(b2a_ctx* ctx, uint32_t run);
 
 /* After a batch run with B2A_WANT_OPS: traceback ops of one pair as ASCII 'M'/'D'/'I', in
  * TRACEBACK order (alignment end -> start, exactly the reference's `tracebacks` vector,
@@ -141,8 +156,9 @@ int64_t b2a_affine_fetch_ops(b2a_ctx* ctx, uint64_t pair, char* ops, uint64_t op
 /* The loop hw3.cpp:231-251 itself over one sequence set: pairs (i, j), i < j, in the reference's
  * row-major order; this call serves pairs [pair_first, pair_first + pair_count) of that order (so the
  * n(n-1)/2 pairs can be sharded over GPUs), writes their scores, the star sums sum_scores[n_seqs]
- * restricted to the range (add the ranges' sums, hw3.cpp:238-239) and, when the range is everything,
- * the centre index hw3.cpp:243-251 (first strict maximum).  Any output pointer may be NULL. */
+ * restricted to the range (add the ranges' sums, hw3.cpp:238-239) and the centre index hw3.cpp:243-251
+ * (first strict maximum) when the range covers every pair, -1 otherwise (partial sums do not determine it).
+ * Any output pointer may be NULL; the centre does not depend on sum_scores being requested. */
 int b2a_affine_star_scores(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
                            const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_seqs,
                            uint32_t pair_first, uint32_t pair_count, int32_t* pair_scores, int32_t* sum_scores, int64_t* center);

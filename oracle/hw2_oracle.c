@@ -134,6 +134,83 @@ int orc_align(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t
                      : orc_local(p, m, t, n, match, mismatch, gap, res, ops);
 }
 
+/* Row-checkpointed restatement of orc_global / orc_local for pairs whose (m+1) x (n+1) matrices do not fit in memory
+ * (config 4: the reference itself needs 49 GB for 100 kb x 100 kb).  Pass 1 is the fill loop hw2.cpp:138-156 / :205-231 on two
+ * rows, keeping every ck-th row (and, local, the first row-major maximum, hw2.cpp:225-229).  Pass 2 re-fills one block of <= ck
+ * rows from the checkpoint above it, bottom-up and only up to the path's current column, re-derives the direction letter of every
+ * VISITED cell with the reference's own comparisons on the re-filled values (hw2.cpp:145-153: d, then l if left > diag, then u if
+ * up > max; hw2.cpp:214-222: 0, d, u, l by equality) and walks exactly as hw2.cpp:158-181 / :239-257 do.  Same outputs as orc_align
+ * (tests/test_oracle.py checks that on random, tandem-repeat and odd-scoring cases with tiny ck). */
+int orc_align_ckpt(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t n,
+                   int match, int mismatch, int gap, uint32_t ck, orc_result* res, uint8_t* ops)
+{
+    if (ck == 0) ck = 1024;
+    const size_t W = (size_t)n + 1;
+    const uint32_t nck = m / ck + 1;                       /* checkpoint b holds DP row b*ck */
+    int32_t* cp = (int32_t*)malloc(sizeof(int32_t) * W * nck);
+    int32_t* row = (int32_t*)malloc(sizeof(int32_t) * W);
+    int32_t* blk = (int32_t*)malloc(sizeof(int32_t) * W * ((size_t)ck + 1));
+    if (!cp || !row || !blk) { free(cp); free(row); free(blk); return -1; }
+    int score = 0; uint32_t bi = 0, bj = 0;
+    for (uint32_t j = 0; j <= n; ++j) row[j] = mode == 0 ? (int32_t)((int64_t)j * gap) : 0;
+    memcpy(cp, row, sizeof(int32_t) * W);
+    for (uint32_t i = 1; i <= m; ++i) {
+        int32_t diagv = row[0];
+        row[0] = mode == 0 ? (int32_t)((int64_t)i * gap) : 0;
+        for (uint32_t j = 1; j <= n; ++j) {
+            int d = diagv + (p[i - 1] == t[j - 1] ? match : mismatch);
+            int u = row[j] + gap, l = row[j - 1] + gap;
+            int v;
+            if (mode == 0) { v = d; if (l > v) v = l; if (u > v) v = u; }
+            else { int ul = u > l ? u : l; v = d > ul ? d : ul; if (v < 0) v = 0; if (v > score) { score = v; bi = i; bj = j; } }
+            diagv = row[j]; row[j] = v;
+        }
+        if (i % ck == 0) memcpy(cp + (size_t)(i / ck) * W, row, sizeof(int32_t) * W);
+    }
+    uint32_t ti = mode == 0 ? m : bi, tj = mode == 0 ? n : bj, k = 0;
+    int cur = 0, best = 0, stop = 0;
+    res->score = mode == 0 ? row[n] : score;
+    res->end_i = ti; res->end_j = tj;
+    while (!stop && ti > 0 && tj > 0) {
+        const uint32_t b = (ti - 1) / ck, r0 = b * ck;     /* block rows r0+1 .. ti, columns 0 .. tj */
+        const size_t BW = (size_t)tj + 1;
+        memcpy(blk, cp + (size_t)b * W, sizeof(int32_t) * BW);
+        for (uint32_t i = r0 + 1; i <= ti; ++i) {
+            int32_t* prev = blk + (size_t)(i - 1 - r0) * BW; int32_t* curr = blk + (size_t)(i - r0) * BW;
+            curr[0] = mode == 0 ? (int32_t)((int64_t)i * gap) : 0;
+            for (uint32_t j = 1; j <= tj; ++j) {
+                int d = prev[j - 1] + (p[i - 1] == t[j - 1] ? match : mismatch);
+                int u = prev[j] + gap, l = curr[j - 1] + gap;
+                int v;
+                if (mode == 0) { v = d; if (l > v) v = l; if (u > v) v = u; }
+                else { int ul = u > l ? u : l; v = d > ul ? d : ul; if (v < 0) v = 0; }
+                curr[j] = v;
+            }
+        }
+        while (ti > r0 && tj > 0) {
+            const int32_t* prev = blk + (size_t)(ti - 1 - r0) * BW; const int32_t* curr = blk + (size_t)(ti - r0) * BW;
+            const int diag = prev[tj - 1] + (p[ti - 1] == t[tj - 1] ? match : mismatch);
+            const int up = prev[tj] + gap, left = curr[tj - 1] + gap, v = curr[tj];
+            char d;
+            if (mode == 0) { int x = diag; d = 'd'; if (left > x) { x = left; d = 'l'; } if (up > x) d = 'u'; }      /* hw2.cpp:145-153 */
+            else { if (v == 0) { stop = 1; break; } d = v == diag ? 'd' : (v == up ? 'u' : 'l'); }                        /* hw2.cpp:239, :214-222 */
+            if (d == 'd') {
+                ops[k++] = 'M';
+                if (p[ti - 1] == t[tj - 1] && p[ti - 1] != '-') { if (++cur > best) best = cur; } else cur = 0;
+                --ti; --tj;
+            } else if (d == 'u') { ops[k++] = 'D'; cur = 0; --ti; }
+            else { ops[k++] = 'I'; cur = 0; --tj; }
+        }
+    }
+    if (mode == 0) {                                        /* borders: column 0 holds 'u', row 0 holds 'l' (hw2.cpp:128, :134) */
+        while (ti > 0) { ops[k++] = 'D'; --ti; }
+        while (tj > 0) { ops[k++] = 'I'; --tj; }
+    }
+    res->start_i = ti; res->start_j = tj; res->overlap = best; res->n_ops = k;
+    free(cp); free(row); free(blk);
+    return 0;
+}
+
 /* Linear-memory score(+end cell) only, for sizes where the full matrices do
  * not fit: same recurrences (hw2.cpp:138-156 / :205-231), two rows. */
 int orc_score_only(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t n,

@@ -34,6 +34,7 @@ def lib():
             subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
         _lib = C.CDLL(so)
         _lib.orc_align.restype = C.c_int
+        _lib.orc_align_ckpt.restype = C.c_int
         _lib.orc_score_only.restype = C.c_int
         _lib.orc_cigar.restype = C.c_size_t
         _lib.orc_mdz.restype = C.c_size_t
@@ -71,6 +72,29 @@ def align(mode, pattern: bytes, text: bytes, match: int, mismatch: int, gap: int
     a.cigar = buf.raw[:w].decode("latin-1")
     w = L.orc_mdz(a.ops, C.c_uint32(res.n_ops), pattern, text, C.c_uint32(res.start_i), C.c_uint32(res.start_j),
                   buf, C.c_size_t(cap))
+    a.mdz = buf.raw[:w].decode("latin-1")
+    return a
+
+
+def align_ckpt(mode, pattern: bytes, text: bytes, match: int, mismatch: int, gap: int, ck: int = 1024) -> Alignment:
+    """orc_align_ckpt: the same outputs as align() in O(ck * n + (m / ck) * n) memory (config 4 size)."""
+    L = lib()
+    m, n = len(pattern), len(text)
+    res = OrcResult()
+    ops = C.create_string_buffer(m + n + 1)
+    rc = L.orc_align_ckpt(C.c_int(mode), pattern, C.c_uint32(m), text, C.c_uint32(n), C.c_int(match), C.c_int(mismatch), C.c_int(gap),
+                          C.c_uint32(ck), C.byref(res), ops)
+    if rc != 0:
+        raise RuntimeError(f"orc_align_ckpt rc={rc}")
+    a = Alignment()
+    a.score, a.end_i, a.end_j = res.score, res.end_i, res.end_j
+    a.start_i, a.start_j, a.overlap = res.start_i, res.start_j, res.overlap
+    a.ops = ops.raw[:res.n_ops]
+    cap = 16 * (m + n) + 64
+    buf = C.create_string_buffer(cap)
+    w = L.orc_cigar(a.ops, C.c_uint32(res.n_ops), buf, C.c_size_t(cap))
+    a.cigar = buf.raw[:w].decode("latin-1")
+    w = L.orc_mdz(a.ops, C.c_uint32(res.n_ops), pattern, text, C.c_uint32(res.start_i), C.c_uint32(res.start_j), buf, C.c_size_t(cap))
     a.mdz = buf.raw[:w].decode("latin-1")
     return a
 

@@ -414,9 +414,67 @@ def test_config2_full_size_one_million_pairs(eng):
                 else:
                     j -= 1; sc -= 1
             assert (i, j, sc) == (int(res["start_i"][k]), int(res["start_j"][k]), int(res["score"][k]))
-        for k in range(0, n_pairs, 99991):
+        # 2 100 pairs spread over the whole batch against the oracle: record fields AND the op list, byte for byte
+        for k in range(0, n_pairs, 477):
             a = ob.align(mode, P[k].tobytes(), T[k].tobytes(), 1, -1, -1)
-            assert (int(res["score"][k]), int(res["overlap"][k]), pkg.unpack_ops(words, off, k, res["n_ops"][k])) == (a.score, a.overlap, a.ops)
+            got = (int(res["score"][k]), int(res["end_i"][k]), int(res["end_j"][k]), int(res["start_i"][k]), int(res["start_j"][k]),
+                   int(res["overlap"][k]), pkg.unpack_ops(words, off, k, res["n_ops"][k]))
+            assert got == (a.score, a.end_i, a.end_j, a.start_i, a.start_j, a.overlap, a.ops), (mode, k)
+
+
+def test_multi_run_one_upload_equals_single_runs(eng):
+    """b2a_align_batch_multi (-g and -l over ONE upload, BASELINE config 2/3's shape) returns the records and op lists of the
+    two single-mode calls, on a ragged batch that also holds wide32 pairs and tandem-repeat ties."""
+    rng = random.Random(77)
+    pat, po, txt, to = workload.config2(6000, seed=99, tie_fraction=0.1)
+    ps, ts = workload.split(pat, po), workload.split(txt, to)
+    for _ in range(300):                                           # ragged shapes, some beyond the s16x2 record (wide32)
+        t = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 700)))
+        ps.append(bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 200)))); ts.append(t)
+    ps += [bytes(rng.choice(b"ACGT") for _ in range(700)), b"ACGTN" * 30]; ts += [bytes(rng.choice(b"ACGT") for _ in range(900)), b"ACGNT" * 40]
+    pat, po = pkg.pack(ps); txt, to = pkg.pack(ts)
+    n = len(ps)
+    single = {}
+    for mode in (pkg.GLOBAL, pkg.LOCAL):
+        res = eng.align_packed(mode, pat, po, txt, to, 1, -1, -1, want_ops=True).copy()
+        words, off = eng.copy_ops(n)
+        single[mode] = (res, [pkg.unpack_ops(words, off, k, res["n_ops"][k]) for k in range(n)])
+    for order in ([pkg.GLOBAL, pkg.LOCAL], [pkg.LOCAL, pkg.GLOBAL]):
+        multi = eng.align_packed_multi(order, pat, po, txt, to, 1, -1, -1, want_ops=True)
+        for r, mode in enumerate(order):
+            assert np.array_equal(multi[r], single[mode][0]), (order, mode)
+            eng.select_run(r)
+            words, off = eng.copy_ops(n)
+            for k in range(0, n, 7):
+                assert pkg.unpack_ops(words, off, k, multi[r]["n_ops"][k]) == single[mode][1][k], (order, mode, k)
+            k = n - 1
+            assert eng.fetch_ops(k, multi[r]["n_ops"][k]) == single[mode][1][k]
+    with pytest.raises(pkg.B2AError):
+        eng.select_run(1) if eng.align_packed(pkg.GLOBAL, pat, po, txt, to, 1, -1, -1) is None else eng.select_run(1)
+    # spot-check the oracle too
+    for mode in (pkg.GLOBAL, pkg.LOCAL):
+        for k in list(range(0, n, 501)) + [n - 2, n - 1]:
+            a = ob.align(mode, ps[k], ts[k], 1, -1, -1)
+            assert (int(single[mode][0]["score"][k]), single[mode][1][k]) == (a.score, a.ops)
+
+
+def test_multi_gpu_cli_equals_one_gpu_file(eng, tmp_path):
+    """B2A_ALL_GPUS=1 bin/hw2 (one host thread + context per device, results in one host array, winner's ops fetched from the
+    device that owns the pair) writes the file the 1-GPU run writes.  Needs > 1 GPU."""
+    lib = pkg.load_library()
+    if lib.b2a_device_count() < 2:
+        pytest.skip("one GPU visible")
+    pat, po, txt, to = workload.config2(30000, seed=11, tie_fraction=0.05)
+    workload.write_fasta(str(tmp_path / "p.fa"), pat, po, b"p")
+    workload.write_fasta(str(tmp_path / "t.fa"), txt, to, b"t")
+    for flag in ("-g", "-l"):
+        outs = []
+        for env_extra in ({"CUDA_VISIBLE_DEVICES": "0"}, {"B2A_ALL_GPUS": "1"}):
+            env = dict(os.environ); env.pop("CUDA_VISIBLE_DEVICES", None); env.update(env_extra)
+            out = tmp_path / ("out_%s_%d.txt" % (flag[1], len(outs)))
+            subprocess.check_call([pkg.HW2_BIN, flag, "-p", "p.fa", "-t", "t.fa", "-o", str(out), "-s", "1", "-1", "-1"], cwd=tmp_path, env=env)
+            outs.append(out.read_bytes())
+        assert outs[0] == outs[1] and len(outs[0]) > 1000
 
 
 # ---------------- hw3 traceback (SURVEY 8 f1): affine alignment with ops ----------------

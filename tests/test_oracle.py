@@ -48,6 +48,47 @@ def test_score_only_matches_full():
             assert ob.score_only(mode, p, t, *s) == (a.score, a.end_i, a.end_j)
 
 
+def test_checkpointed_traceback_equals_full_matrix_oracle():
+    """orc_align_ckpt (the config-4-sized oracle) == orc_align: every field and the op list, with block heights down to 1 row."""
+    import random
+    rng = random.Random(4)
+    cases = []
+    for _ in range(150):
+        alpha = rng.choice([b"ACGT", b"AC", b"A", b"ACGTN"])
+        m, n = rng.randint(1, 70), rng.randint(1, 90)
+        p = bytes(rng.choice(alpha) for _ in range(m)); t = bytes(rng.choice(alpha) for _ in range(n))
+        if rng.random() < 0.4:                                    # tandem repeats: ties everywhere
+            u = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 5)))
+            p = (u * 40)[:m]; t = (u * 40)[:n]
+        cases.append((p, t))
+    for s in ((1, -1, -1), (2, -3, -4), (5, -4, -16), (0, 0, 0), (3, 1, -2)):
+        for p, t in cases[::3] if s != (1, -1, -1) else cases:
+            for mode in (0, 1):
+                a = ob.align(mode, p, t, *s)
+                for ck in (1, 3, 16, 1024):
+                    b = ob.align_ckpt(mode, p, t, *s, ck=ck)
+                    assert (a.score, a.end_i, a.end_j, a.start_i, a.start_j, a.overlap, a.ops) == \
+                           (b.score, b.end_i, b.end_j, b.start_i, b.start_j, b.overlap, b.ops), (mode, s, ck, p, t)
+
+
+@pytest.mark.parametrize("mode,name,header", [(1, "c4_local.txt.gz", "Highest local alignment score:"), (0, "c4_global.txt.gz", "Longest overlap:")])
+def test_checkpointed_oracle_reproduces_reference_file_at_config4_size(mode, name, header):
+    """Pins the config-4-sized oracle: its score, CIGAR and MD:Z for the seed-482 100 kb x 100 kb pair equal, byte for byte, the file
+    the UNMODIFIED reference binary wrote for that pair (tests/golden/make_golden_c4.py, ~50 GB of RAM and 3 min per mode)."""
+    import gzip
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+    if not os.path.exists(path):
+        pytest.skip("golden not generated")
+    from __graft_entry__ import load_package
+    load_package()
+    from bioinformatics_algorithms_b200 import workload
+    p, t = workload.config4(100_000, seed=482)
+    p, t = p.tobytes(), t.tobytes()
+    a = ob.align_ckpt(mode, p, t, 1, -1, -1)
+    mine = "%s\npattern=%s\nreference=%s\nScore =%d\nCIGAR =%s\nMD:Z=%s\n" % (header, p.decode(), t.decode(), a.score, a.cigar, a.mdz)
+    assert mine.encode() == gzip.open(path, "rb").read()
+
+
 def test_empty_local_alignment():
     a = ob.align(ob.LOCAL, b"acgt", b"ACGT", 1, -1, -1)
     assert (a.score, a.cigar, a.mdz, a.n_ops if hasattr(a, "n_ops") else len(a.ops)) == (0, "", "0", 0)
