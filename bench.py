@@ -15,8 +15,8 @@ one pass of the hot path over the batch in both modes.
   strong     = BASELINE.json configs[2]: the ONE seed-481 P-pair batch pair-sharded over the N ranks
                (rank r takes pairs [r P/N, (r+1) P/N)), device-resident and end to end.  The end-to-end
                figure includes the HOST GATHER and the winner selection (hw2.cpp:340-357): every rank's
-               result records land by DMA in its slice of one shared host array, a barrier, then rank 0
-               runs b2a_select_best over all P records of both modes -- all inside the timed region.
+               result records land by DMA in its slice of one shared host array, every rank selects over
+               its slice, a barrier, rank 0 merges the N candidates -- all inside the timed region.
   roofline   = integer-ALU roofline: algorithmic int16 lane-ops (5 per NW cell, 6 per SW cell)
                against 2 x the VIADDMNMX.S16x2 issue rate microbenchmarked on this GPU in this run.
                frac = frac_step uses fill + traceback kernel time (SURVEY.md 8d metric 1), frac_fill the
@@ -307,7 +307,9 @@ def bench_c2(args):
     workload_name = (f"config2: {n_pairs} pairs/GPU, 150 bp x 1 kb DNA, seed 481+rank, -s {' '.join(map(str, SCORING))}, "
                      "global+local, score+traceback")
 
-    pat_np, po_np, txt_np, to_np = workload.config2(n_pairs, seed=481 + rank)
+    pat_np, po_np, txt_np, to_np = workload.config2(n_pairs, seed=481 + rank, n_rate=args.n_rate)
+    if args.n_rate:
+        workload_name += f", {args.n_rate:g} of the pattern bases replaced by 'N' (robustness variant, not the BASELINE config)"
     if world > 1 and rank == 0:                                  # rank 0's batch IS the seed-481 batch of the strong arm
         np.save(shm_path("pat.npy"), pat_np); np.save(shm_path("txt.npy"), txt_np)
     pat, txt, po, to = (pinned_copy(pkg, a) for a in (pat_np, txt_np, po_np, to_np))
@@ -357,11 +359,13 @@ def bench_c2(args):
         sto = pinned_copy(pkg, np.arange(count + 1, dtype=np.uint64) * np.uint64(N_TXT))
         del sp, stx
         # one host array for all ranks' records (POSIX shared memory, pinned by every rank): the gather IS the D2H copies
-        rec_path = shm_path("records")
+        rec_path, cand_path = shm_path("records"), shm_path("cand")
         if rank == 0:
             np.lib.format.open_memmap(rec_path, mode="w+", dtype=pkg.RESULT_DTYPE, shape=(2, n_pairs)).flush()
+            np.lib.format.open_memmap(cand_path, mode="w+", dtype=np.int64, shape=(world, 2, 2)).flush()
         dev.barrier()
         shared = np.lib.format.open_memmap(rec_path, mode="r+")
+        cand = np.lib.format.open_memmap(cand_path, mode="r+")              # per rank and mode: (key, global pair index) of the slice's winner
         dma_into_shared = True
         try:
             pkg.host_register(shared)
@@ -380,9 +384,21 @@ def bench_c2(args):
             if not dma_into_shared:
                 for k in range(2):
                     shared[k, first:first + count] = mine[k]
-            dev.barrier()                                        # every rank's records are in the one host array
+            # hw2.cpp:340-357: first strict maximum.  Every rank scans its own slice (in parallel); the ranks own ascending index
+            # ranges, so the batch winner is the first strict maximum of the N slice winners taken in rank order.
+            for k, mode in enumerate(modes):
+                b = pkg.select_best(mode, mine[k])
+                key = int(mine[k]["overlap" if mode == pkg.GLOBAL else "score"][b]) if b >= 0 else -1000000
+                cand[rank, k] = (key, first + b if b >= 0 else -1)
+            dev.barrier()                                        # every rank's records are in the one host array, every candidate is posted
             if rank == 0:
-                s_winners = [pkg.select_best(mode, shared[k]) for k, mode in enumerate(modes)]   # hw2.cpp:340-357 over all P pairs
+                s_winners = []
+                for k in range(2):
+                    best_key, best_idx = -1000000, -1
+                    for r in range(world):
+                        if int(cand[r, k, 1]) >= 0 and int(cand[r, k, 0]) > best_key:
+                            best_key, best_idx = int(cand[r, k, 0]), int(cand[r, k, 1])
+                    s_winners.append(best_idx)
 
         for _ in range(max(1, min(args.warmup, 2))):
             strong_step()
@@ -398,13 +414,14 @@ def bench_c2(args):
         if rank == 0:
             assert merged == s_winners, (merged, s_winners)
             assert s_winners == winners, "strong and weak arms pick different winners for the seed-481 batch"
+            assert s_winners == [pkg.select_best(mode, shared[k]) for k, mode in enumerate(modes)], "serial scan of the gathered records disagrees"
         eng.close()
         if dma_into_shared:
             pkg.host_unregister(shared)
-        del mine, shared
+        del mine, shared, cand
         dev.barrier()
         if rank == 0:
-            for tag in ("pat.npy", "txt.npy", "records"):
+            for tag in ("pat.npy", "txt.npy", "records", "cand"):
                 try:
                     os.unlink(shm_path(tag))
                 except OSError:
@@ -413,9 +430,10 @@ def bench_c2(args):
         strong = {"value": scells / s_dev_s / 1e9, "e2e": scells / s_e2e_s / 1e9, "ms_per_step": s_dev_s * 1e3 / args.steps,
                   "e2e_ms_per_step": s_e2e_s * 1e3 / args.steps, "pairs_total": n_pairs, "pairs_per_gpu": count, "winners": s_winners,
                   "h2d_bytes_per_step_per_gpu": sst["h2d_bytes"], "d2h_bytes_per_step_per_gpu": sst["d2h_bytes"],
-                  "gather": ("every rank's D2H lands in its slice of one POSIX-shm host array pinned with b2a_host_register; barrier; "
-                             "rank 0 runs b2a_select_best over all records of both modes -- inside the timed region")
-                            if dma_into_shared else "private pinned array -> memcpy into the shared host array; barrier; rank 0 selects"}
+                  "gather": ("every rank's D2H lands in its slice of one POSIX-shm host array pinned with b2a_host_register; every rank runs "
+                             "b2a_select_best over its slice and posts (key, index); barrier; rank 0 takes the first strict maximum of the N "
+                             "candidates in rank order -- all inside the timed region (checked afterwards against one serial scan of all records)")
+                            if dma_into_shared else "private pinned array -> memcpy into the shared host array; per-rank select; barrier; rank 0 merges"}
 
     line = None
     if rank == 0:
@@ -634,6 +652,7 @@ def main():
     ap.add_argument("--len", type=int, default=100_000, help="c4: sequence length")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident-seg-pairs", type=int, default=0, help="experiment: pairs per segment of the device-resident arm")
+    ap.add_argument("--n-rate", type=float, default=0.0, help="c2 variant: fraction of pattern bases turned into 'N' (pairs holding one leave the 4-symbol s16x2 path)")
     ap.add_argument("--scoring", default="1,-1,-1", help="c2: match,mismatch,gap (SURVEY 8d also names 2,-3,-4: 4-bit deltas, twice the record)")
     args = ap.parse_args()
 

@@ -72,7 +72,6 @@ struct Segment {
     uint64_t chunks = 0, rowbest_words = 0;       // record size of the segment
     uint64_t n_wide = 0;                          // pairs of the segment planned for wide32
     std::vector<ClassRange> classes;
-    bool flagged = false;                         // > 4 pattern symbols: the whole segment goes to wide32
 };
 
 struct Lane {                                     // one DP record, reused by every n_lanes-th segment
@@ -95,6 +94,11 @@ struct WideState {
     DevBuf<uint64_t> d_bound;                     // tagged boundary entries (wide32.cuh)
     DevBuf<int32_t> d_final;
     DevBuf<uint32_t> d_rowbest, d_progress;       // d_progress[0] is the ticket counter
+    // pairs whose full record would exceed the budget: score pass with checkpoint rows, then band groups re-filled bottom-up (wide_ckpt_run)
+    struct CkptSpec { uint32_t pair, m, n; uint64_t pat_off, txt_off; };
+    std::vector<CkptSpec> ckpt_pairs;
+    DevBuf<int32_t> d_ck;
+    DevBuf<CkptWalk> d_walk;
     // epoch tag of the next launch; the boundary buffer is cleared when it was reallocated or the 12-bit epoch wraps
     cudaError_t next_epoch(uint64_t need_words, cudaStream_t st, uint32_t* tag) {
         const size_t cap_before = d_bound.cap;
@@ -111,7 +115,7 @@ struct WideState {
     }
     void release() {
         d_pairs.release(); d_tasks.release(); d_codes.release(); d_bound.release(); d_final.release();
-        d_rowbest.release(); d_progress.release();
+        d_rowbest.release(); d_progress.release(); d_ck.release(); d_walk.release();
     }
 };
 
@@ -160,6 +164,8 @@ struct b2a_ctx {
     uint64_t n_pairs = 0;
     int K = 0;
     int tb_opt = 0;                               // walker tuning bits (B2A_TB_OPT overrides, for experiments)
+    uint64_t wide_ckpt_bytes = 48ull << 30;       // a wide32 pair whose traceback record would be larger is walked from checkpoints instead
+    uint64_t wide_ckpt_group_bytes = 1ull << 30;  // ... re-filling groups of bands whose record fits this
     std::vector<Segment> segs;
     std::vector<uint32_t> wide_pairs;             // pairs served by the wide32 family
     uint64_t total_ops_words = 0, n_pp_total = 0;
@@ -171,6 +177,9 @@ struct b2a_ctx {
     DevBuf<PPDesc> d_pps;
     DevBuf<uint32_t> d_nops;                      // affine only
     DevBuf<AlphaInfo> d_alpha;                    // one per segment + one for the whole batch (wide32)
+    DevBuf<uint32_t> d_hist;                      // 256 pattern-byte counts per segment
+    DevBuf<uint8_t> d_dirty;                      // per pair-pair: a pattern byte outside the segment's 4 table symbols -> wide32 serves its pairs
+    HostBuf<uint8_t> h_dirty;
     HostBuf<PPDesc> h_pps;
     HostBuf<uint64_t> h_code_off, h_ops_off;
     HostBuf<AlphaInfo> h_alpha;
@@ -182,40 +191,70 @@ namespace {
 
 int fail(b2a_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
 int cuda_fail(b2a_ctx* c, cudaError_t e, const char* where) {
+    cudaGetLastError();                                   // a failed call (cudaMalloc: out of memory) leaves its code for the NEXT cudaGetLastError
     return fail(c, e == cudaErrorMemoryAllocation ? B2A_ERR_NOMEM : B2A_ERR_CUDA,
                 std::string(where) + ": " + cudaGetErrorString(e));
 }
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); } while (0)
 
-// 256-bit presence mask of the bytes in [p, p+n), OR-ed into info->mask
-__global__ void alphabet_kernel(const uint8_t* __restrict__ p, uint64_t n, AlphaInfo* __restrict__ info) {
-    __shared__ uint32_t s[8];
-    if (threadIdx.x < 8) s[threadIdx.x] = 0;
+// Histogram of the pattern bytes of a segment: hist[256] += counts of the bytes in [p, p+n)
+__global__ void alphabet_kernel(const uint8_t* __restrict__ p, uint64_t n, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s[256];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s[k] = 0;
     __syncthreads();
-    uint32_t loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint8_t b = p[i];
-        loc[b >> 5] |= 1u << (b & 31);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        uint32_t v = loc[k];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        if ((threadIdx.x & 31) == 0 && v) atomicOr(&s[k], v);
+        const uint32_t b = p[i];
+        // the lanes of a warp mostly hold the same few symbols: one atomic per distinct symbol and warp
+        const uint32_t peers = __match_any_sync(__activemask(), b);
+        if ((uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31u)) atomicAdd(&s[b], (uint32_t)__popc(peers));
     }
     __syncthreads();
-    if (threadIdx.x < 8 && s[threadIdx.x]) atomicOr(&info->mask[threadIdx.x], s[threadIdx.x]);
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) if (s[k]) atomicAdd(&hist[k], s[k]);
 }
-// mask -> the (<= 4) symbols the PRMT score tables are built for
-__global__ void alphabet_finish_kernel(AlphaInfo* __restrict__ info) {
+// histogram -> presence mask + the (<= 4) MOST FREQUENT symbols, which the PRMT score tables are built for.  too_many = the segment
+// holds other pattern bytes as well (an 'N' in a read): the pair-pairs that contain one are flagged by dirty_kernel and served by wide32.
+__global__ void alphabet_finish_kernel(AlphaInfo* __restrict__ info, const uint32_t* __restrict__ hist) {
     if (threadIdx.x != 0) return;
-    int ns = 0, many = 0;
+    uint32_t cnt[4] = {0, 0, 0, 0};
     uint8_t sym[4] = {0, 0, 0, 0};
-    for (int b = 0; b < 256; ++b)
-        if (info->mask[b >> 5] & (1u << (b & 31))) { if (ns == 4) { many = 1; break; } sym[ns++] = (uint8_t)b; }
+    int present = 0;
+    for (int w = 0; w < 8; ++w) info->mask[w] = 0;
+    for (int b = 0; b < 256; ++b) {
+        const uint32_t h = hist[b];
+        if (!h) continue;
+        ++present;
+        info->mask[b >> 5] |= 1u << (b & 31);
+        for (int c = 0; c < 4; ++c)
+            if (h > cnt[c]) {                                  // insert into the top-4 (ties: lower byte value first)
+                for (int k = 3; k > c; --k) { cnt[k] = cnt[k - 1]; sym[k] = sym[k - 1]; }
+                cnt[c] = h; sym[c] = (uint8_t)b;
+                break;
+            }
+    }
     for (int c = 0; c < 4; ++c) info->sym[c] = sym[c];
-    info->nsym = ns; info->too_many = many;
+    info->nsym = present < 4 ? present : 4;
+    info->too_many = present > 4;
+}
+// dirty[pp] = 1 iff a pattern of pair-pair pp holds a byte outside the segment's four table symbols (runs only when there is one)
+__global__ void dirty_kernel(const uint8_t* __restrict__ pat, const uint64_t* __restrict__ pat_off, const PPDesc* __restrict__ pps, uint32_t n_pp,
+                             const AlphaInfo* __restrict__ info, uint8_t* __restrict__ dirty) {
+    if (!info->too_many) return;                               // uniform: nothing to flag (the flags were cleared by the host)
+    const uint32_t pp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pp >= n_pp) return;
+    const int nsym = info->nsym;
+    const uint8_t s0 = info->sym[0], s1 = info->sym[1], s2 = info->sym[2], s3 = info->sym[3];
+    const PPDesc d = pps[pp];
+    bool bad = false;
+    for (int half = 0; half < 2 && !bad; ++half) {
+        if (half && d.b == d.a) break;
+        const uint8_t* p = pat + pat_off[half ? d.b : d.a];
+        const uint32_t m = pp_dim(d.m, half);
+        for (uint32_t i = 0; i < m; ++i) {
+            const uint8_t x = p[i];
+            if (!((nsym > 0 && x == s0) || (nsym > 1 && x == s1) || (nsym > 2 && x == s2) || (nsym > 3 && x == s3))) { bad = true; break; }
+        }
+    }
+    dirty[pp] = bad ? 1 : 0;
 }
 void alpha_from_mask(AlphaInfo& a) {
     a.nsym = 0; a.too_many = 0;
@@ -294,8 +333,9 @@ cudaError_t launch_wide_fill_a(bool alpha4, const WideArgs& a, unsigned grid, cu
 }
 template <int K>
 cudaError_t launch_wide_fill_k(bool local, bool store, bool alpha4, const WideArgs& a, unsigned grid, cudaStream_t st) {
-    if (local) return store ? launch_wide_fill_a<K, true, true>(alpha4, a, grid, st) : launch_wide_fill_a<K, true, false>(alpha4, a, grid, st);
-    return store ? launch_wide_fill_a<K, false, true>(alpha4, a, grid, st) : launch_wide_fill_a<K, false, false>(alpha4, a, grid, st);
+    if (store) return local ? launch_wide_fill_a<K, true, true>(alpha4, a, grid, st) : launch_wide_fill_a<K, false, true>(alpha4, a, grid, st);
+    if (K != 2) return cudaErrorInvalidValue;                 // score-only kernels exist for K = 2 only
+    return local ? launch_wide_fill_a<2, true, false>(alpha4, a, grid, st) : launch_wide_fill_a<2, false, false>(alpha4, a, grid, st);
 }
 cudaError_t launch_wide_fill(int K, bool local, bool store, bool alpha4, const WideArgs& a, unsigned grid, cudaStream_t st) {
     switch (K) {
@@ -329,7 +369,7 @@ int wide_plan(b2a_ctx* ctx, const uint64_t* pat_off, const uint64_t* txt_off, bo
 {
     WideState& W = ctx->wide;
     const b2a_params& prm = ctx->prm;
-    W.pairs.clear(); W.tasks.clear();
+    W.pairs.clear(); W.tasks.clear(); W.ckpt_pairs.clear();
     W.chunks = W.bound_words = W.rowbest_words = 0;
     W.K = delta_bits_wide(prm.match, prm.mismatch, prm.gap);
     W.store = store;
@@ -342,12 +382,17 @@ int wide_plan(b2a_ctx* ctx, const uint64_t* pat_off, const uint64_t* txt_off, bo
         p.m = (uint32_t)(pat_off[k + 1] - pat_off[k]); p.n = (uint32_t)(txt_off[k + 1] - txt_off[k]);
         p.pair = k;
         p.nbands = (p.m && p.n) ? (p.m + 32u * WIDE_R - 1u) / (32u * WIDE_R) : 0u;
+        p.top_off = WIDE_NO_TOP;
+        if (p.nbands >= (1u << 20)) return fail(ctx, B2A_ERR_RANGE, "wide32: pattern too long (band index must fit 20 bits)");
+        if (store && (uint64_t)p.nbands * WIDE_R * num_chunks(p.n, CS, wide_skew(W.K)) * 32u * sizeof(Chunk) > ctx->wide_ckpt_bytes) {
+            W.ckpt_pairs.push_back(WideState::CkptSpec{k, p.m, p.n, p.pat_off, p.txt_off});   // too large to keep: served one by one from checkpoints
+            continue;
+        }
         p.code_off = W.chunks;
-        if (store) W.chunks += (uint64_t)p.nbands * WIDE_R * num_chunks(p.n, CS) * 32u;
+        if (store) W.chunks += (uint64_t)p.nbands * WIDE_R * num_chunks(p.n, CS, wide_skew(W.K)) * 32u;
         p.bound_stride = ((p.n + 64u) + 31u) & ~31u;
         p.bound_off = W.bound_words; if (p.nbands > 1u) W.bound_words += 2ull * p.bound_stride;   // single-band pairs exchange nothing
         p.rowbest_off = W.rowbest_words; W.rowbest_words += (uint64_t)p.nbands * 32u * WIDE_R;
-        if (p.nbands >= (1u << 20)) return fail(ctx, B2A_ERR_RANGE, "wide32: pattern too long (band index must fit 20 bits)");
         max_bands = std::max(max_bands, p.nbands);
         W.pairs.push_back(p);
     }
@@ -380,12 +425,13 @@ int wide_fill(b2a_ctx* ctx, int r, cudaStream_t st, uint64_t* launches)
     a.n_tasks = (uint32_t)W.tasks.size(); a.ticket = W.d_progress.p;
     a.codes = W.d_codes.p; a.bound = W.d_bound.p; a.rowbest = W.d_rowbest.p;
     a.final_score = W.d_final.p;
+    a.ck = nullptr;
     a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap;
     a.radix = W.K < 32 ? (1u << W.K) : 0u;
     a.alpha = ctx->d_alpha.p + (ctx->alpha_slots - 1);
     const unsigned need = (unsigned)((W.tasks.size() + WIDE_WARPS - 1) / WIDE_WARPS);
     const unsigned grid = std::min<unsigned>(need, (unsigned)ctx->sm_count * 8u);
-    CU(launch_wide_fill(W.K, ctx->run[r].mode == B2A_MODE_LOCAL, W.store, W.alpha4, a, grid, st));
+    CU(launch_wide_fill(W.store ? W.K : 2, ctx->run[r].mode == B2A_MODE_LOCAL, W.store, W.alpha4, a, grid, st));   // score-only: no record, one instance
     ++*launches;
     return B2A_OK;
 }
@@ -408,6 +454,132 @@ int wide_traceback(b2a_ctx* ctx, int r, cudaStream_t st, uint64_t* launches, boo
     return B2A_OK;
 }
 
+template <int K>
+cudaError_t launch_ckpt_walk_k(bool local, const CkptWalkArgs& a, cudaStream_t st) {
+    if (local) wide32_ckpt_walk_kernel<K, true><<<1, 32, 0, st>>>(a);
+    else wide32_ckpt_walk_kernel<K, false><<<1, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_ckpt_walk(int K, bool local, const CkptWalkArgs& a, cudaStream_t st) {
+    switch (K) {
+        case 2:  return launch_ckpt_walk_k<2>(local, a, st);
+        case 4:  return launch_ckpt_walk_k<4>(local, a, st);
+        case 8:  return launch_ckpt_walk_k<8>(local, a, st);
+        case 16: return launch_ckpt_walk_k<16>(local, a, st);
+        case 32: return launch_ckpt_walk_k<32>(local, a, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// Pairs whose traceback record does not fit (ctx->wide_ckpt_bytes; 0.5 byte per cell, so a 1 Mb x 1 Mb pair would need 500 GB -- the
+// reference's own full matrices, hw2.cpp:119-120, are what NOT to imitate).  Checkpointed recomputation, one pair at a time:
+//   pass 1  score-only fill of the whole pair (the tiled kernel) that keeps the bottom row of every G-th band (4 bytes per column and
+//           kept row) and, local mode, the per-row maxima -> score, and the row of the first row-major maximum (hw2.cpp:225-229);
+//   pass 2  from the end cell upwards: the group of <= G bands that holds the path's current row is filled again WITH its record, from
+//           the checkpoint row above it and only up to the path's current column, and the warp walker continues through it with the
+//           reference's own comparisons (hw2.cpp:145-153 / :214-222) until it leaves the group at the top.
+// Memory: kept rows (m / 128 G x n x 4 B) + one group record (128 G x n x 0.5 B).  Work: one score pass + at most one more fill.
+int wide_ckpt_run(b2a_ctx* ctx, int r, cudaStream_t st, uint64_t* launches)
+{
+    WideState& W = ctx->wide;
+    if (W.ckpt_pairs.empty()) return B2A_OK;
+    const b2a_params& prm = ctx->prm;
+    RunBuf& rb = ctx->run[r];
+    const bool local = rb.mode == B2A_MODE_LOCAL, want_ops = (prm.flags & B2A_WANT_OPS) != 0;
+    const int K = W.K, CS = 2 * (32 / K), skew = wide_skew(K);
+    const uint32_t band_rows = 32u * WIDE_R;
+    CU(W.d_pairs.reserve(1)); CU(W.d_final.reserve(1)); CU(W.d_progress.reserve(1)); CU(W.d_walk.reserve(1));
+    for (const WideState::CkptSpec& sp : W.ckpt_pairs) {
+        const uint32_t k = sp.pair, m = sp.m, n = sp.n;
+        const uint32_t nbands = (m + band_rows - 1u) / band_rows;
+        const uint64_t band_bytes = (uint64_t)WIDE_R * num_chunks(n, CS, skew) * 32u * sizeof(Chunk);
+        const uint32_t G = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nbands, ctx->wide_ckpt_group_bytes / std::max<uint64_t>(band_bytes, 1)));
+        const uint32_t ck_stride = (n + 1u + 31u) & ~31u, n_ck = (nbands - 1u) / G;     // kept: the bottom rows of bands G-1, 2G-1, ... that have a band below
+        const uint32_t bound_stride = ((n + 64u) + 31u) & ~31u;
+        CU(W.d_ck.reserve(std::max<uint64_t>(1, (uint64_t)n_ck * ck_stride)));
+        CU(W.d_rowbest.reserve(std::max<uint64_t>((uint64_t)nbands * band_rows, 1)));
+        CU(W.d_tasks.reserve(nbands));
+        CU(W.d_codes.reserve((uint64_t)G * band_bytes / sizeof(Chunk)));
+        std::vector<WideTask> tasks(nbands);
+        for (uint32_t b = 0; b < nbands; ++b) tasks[b] = WideTask{0u, b};
+        CU(cudaMemcpyAsync(W.d_tasks.p, tasks.data(), nbands * sizeof(WideTask), cudaMemcpyHostToDevice, st));
+        ctx->h2d += nbands * sizeof(WideTask);
+
+        auto fill = [&](const WidePair& p, bool store) -> int {
+            CU(cudaMemcpyAsync(W.d_pairs.p, &p, sizeof(p), cudaMemcpyHostToDevice, st));
+            CU(cudaMemsetAsync(W.d_progress.p, 0, 4, st));
+            WideArgs a{};
+            CU(W.next_epoch(2ull * bound_stride, st, &a.epoch_tag));
+            a.pat = ctx->d_pat.p; a.txt = ctx->d_txt.p; a.pairs = W.d_pairs.p; a.tasks = W.d_tasks.p;
+            a.n_tasks = p.nbands; a.ticket = W.d_progress.p;
+            a.codes = W.d_codes.p; a.bound = W.d_bound.p; a.rowbest = W.d_rowbest.p; a.final_score = W.d_final.p; a.ck = W.d_ck.p;
+            a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap;
+            a.radix = K < 32 ? (1u << K) : 0u;
+            a.alpha = ctx->d_alpha.p + (ctx->alpha_slots - 1);
+            const unsigned need = (unsigned)((p.nbands + WIDE_WARPS - 1) / WIDE_WARPS);
+            CU(launch_wide_fill(store ? K : 2, local, store, W.alpha4, a, std::min<unsigned>(need, (unsigned)ctx->sm_count * 8u), st));
+            ++*launches;
+            CU(cudaStreamSynchronize(st));                        // &p and the next sub-problem's plan depend on this launch
+            return B2A_OK;
+        };
+
+        // ---- pass 1: scores + kept rows ----
+        WidePair whole{};
+        whole.pat_off = sp.pat_off; whole.txt_off = sp.txt_off; whole.m = m; whole.n = n; whole.pair = k; whole.nbands = nbands;
+        whole.bound_stride = bound_stride; whole.top_off = WIDE_NO_TOP; whole.ck_every = n_ck ? G : 0u; whole.ck_stride = ck_stride;
+        { int rc = fill(whole, false); if (rc != B2A_OK) return rc; }
+        CkptWalk wst{};
+        wst.i = m; wst.j = n;
+        if (local) {
+            CU(cudaMemcpyAsync(W.d_walk.p, &wst, sizeof(wst), cudaMemcpyHostToDevice, st));
+            wide32_first_best_row_kernel<<<1, 32, 0, st>>>(W.d_rowbest.p, m, W.d_walk.p);
+            CU(cudaGetLastError()); ++*launches;
+            CU(cudaMemcpyAsync(&wst, W.d_walk.p, sizeof(wst), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            wst.j = n;                                            // the column of the maximum is found in the first re-filled group
+        } else {
+            int32_t sc = 0;
+            CU(cudaMemcpyAsync(&sc, W.d_final.p, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            wst.score = sc; wst.end_i = m; wst.end_j = n;
+        }
+        // ---- pass 2: band groups, bottom-up ----
+        bool first = true;
+        if (local && wst.score == 0) {                            // hw2.cpp:202-203: no positive cell, empty alignment
+            PairResult res{0, 0, 0, 0, 0, 0, 0, 2};
+            CU(cudaMemcpyAsync(rb.d_results.p + k, &res, sizeof(res), cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+            continue;
+        }
+        while (!wst.done) {
+            const uint32_t g = (wst.i - 1u) / (G * band_rows), r0 = g * G * band_rows;
+            WidePair sub{};
+            sub.pat_off = sp.pat_off + r0; sub.txt_off = sp.txt_off; sub.m = wst.i - r0; sub.n = wst.j; sub.pair = k;
+            sub.nbands = (sub.m + band_rows - 1u) / band_rows;
+            sub.bound_stride = bound_stride; sub.row_base = r0;
+            sub.top_off = g ? (uint64_t)(g - 1u) * ck_stride : WIDE_NO_TOP;
+            { int rc = fill(sub, true); if (rc != B2A_OK) return rc; }
+            CU(cudaMemcpyAsync(W.d_walk.p, &wst, sizeof(wst), cudaMemcpyHostToDevice, st));
+            CkptWalkArgs wa{};
+            wa.pat = ctx->d_pat.p; wa.txt = ctx->d_txt.p; wa.pair = W.d_pairs.p; wa.codes = W.d_codes.p; wa.rowbest = W.d_rowbest.p; wa.ck = W.d_ck.p;
+            wa.st = W.d_walk.p; wa.result = rb.d_results.p + k;
+            wa.ops = want_ops ? rb.d_ops.p + ctx->h_ops_off.p[k] : nullptr;
+            wa.m_total = m; wa.n_total = n;
+            wa.match = prm.match; wa.mismatch = prm.mismatch; wa.gap = prm.gap;
+            wa.opt = (prm.flags & B2A_TIE_HW4) ? 4 : 0;
+            wa.first = (local && first) ? 1 : 0;
+            CU(launch_ckpt_walk(K, local, wa, st));
+            ++*launches;
+            CU(cudaMemcpyAsync(&wst, W.d_walk.p, sizeof(wst), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            first = false;
+            if (!wst.done && (wst.i == 0 || wst.j == 0)) return fail(ctx, B2A_ERR_STATE, "internal: checkpointed walk left the matrix without finishing");
+        }
+        ctx->fill_bytes += (uint64_t)n_ck * ck_stride * 4;
+    }
+    return B2A_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // short16 family: segments
 // ---------------------------------------------------------------------------------------------
@@ -426,7 +598,7 @@ cudaEvent_t* seg_events(b2a_ctx* ctx, size_t si, int r = 0) {
 int launch_segment(b2a_ctx* ctx, size_t si, int r, uint64_t* launches)
 {
     Segment& sg = ctx->segs[si];
-    if (sg.classes.empty() || sg.flagged) return B2A_OK;
+    if (sg.classes.empty()) return B2A_OK;
     const b2a_params& prm = ctx->prm;
     RunBuf& rb = ctx->run[r];
     const int mode = rb.mode;
@@ -457,6 +629,7 @@ int launch_segment(b2a_ctx* ctx, size_t si, int r, uint64_t* launches)
         a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.bias = pl.bias;
         a.radix = 1u << ctx->K;
         a.alpha = alpha;
+        a.dirty = ctx->d_dirty.p + sg.pp_first + c.first;
         CU(launch_fill(ctx->K, c.R, local, a, st));
         ++*launches;
     }
@@ -477,6 +650,7 @@ int launch_segment(b2a_ctx* ctx, size_t si, int r, uint64_t* launches)
         a.opt = ctx->tb_opt;
         a.tie_hw4 = (prm.flags & B2A_TIE_HW4) ? 1 : 0;
         a.alpha = alpha;
+        a.dirty = ctx->d_dirty.p + sg.pp_first + c.first;
         CU(launch_tb(ctx->K, local, a, st));
         ++*launches;
     }
@@ -524,7 +698,7 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
     cudaStream_t st = ctx->s_fill;
     CU(ctx->d_pat.reserve(pat_bytes + 16));
     if (!same_buffer) CU(ctx->d_txt.reserve(txt_bytes + 16));
-    CU(ctx->d_alpha.reserve(2)); CU(ctx->h_alpha.reserve(2));
+    CU(ctx->d_alpha.reserve(2)); CU(ctx->h_alpha.reserve(2)); CU(ctx->d_hist.reserve(256));
     CU(W.d_progress.reserve(1));
     if (trace) {
         ctx->h_ops_off.p[n] = opsw;
@@ -536,13 +710,14 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
     if (!same_buffer && txt_bytes) CU(cudaMemcpyAsync(ctx->d_txt.p, txt, txt_bytes, cudaMemcpyHostToDevice, st));
     ctx->h2d += pat_bytes + (same_buffer ? 0 : txt_bytes);
     CU(cudaMemsetAsync(ctx->d_alpha.p, 0, sizeof(AlphaInfo), st));
+    CU(cudaMemsetAsync(ctx->d_hist.p, 0, 256 * sizeof(uint32_t), st));
     uint64_t launches = 0;
     if (pat_bytes) {
         const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count * 4u, (pat_bytes + 4095) / 4096);
-        alphabet_kernel<<<grid, 256, 0, st>>>(ctx->d_pat.p, pat_bytes, ctx->d_alpha.p);
+        alphabet_kernel<<<grid, 256, 0, st>>>(ctx->d_pat.p, pat_bytes, ctx->d_hist.p);
         CU(cudaGetLastError()); ++launches;
     }
-    alphabet_finish_kernel<<<1, 32, 0, st>>>(ctx->d_alpha.p);
+    alphabet_finish_kernel<<<1, 32, 0, st>>>(ctx->d_alpha.p, ctx->d_hist.p);
     CU(cudaGetLastError()); ++launches;
     CU(cudaMemcpyAsync(ctx->h_alpha.p, ctx->d_alpha.p, sizeof(AlphaInfo), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -562,6 +737,7 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
             const AffSpec& sp = specs[k];
             if (sp.m == 0 || sp.n == 0) continue;           // borders only: answered on the host below
             WidePair p{};
+            p.top_off = WIDE_NO_TOP;
             p.pat_off = sp.pat_off; p.txt_off = sp.txt_off; p.m = sp.m; p.n = sp.n; p.pair = (uint32_t)k;
             const uint32_t band_rows = 32u * (uint32_t)(trace ? WIDE_R : AFFINE_R_SCORE);
             p.nbands = (sp.m + band_rows - 1u) / band_rows;
@@ -717,8 +893,11 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
         if (want_ops) CU(rb.d_ops.reserve(ops_bound));
     }
     CU(ctx->d_alpha.reserve(ctx->alpha_slots)); CU(ctx->h_alpha.reserve(ctx->alpha_slots));
+    CU(ctx->d_hist.reserve(ctx->alpha_slots * 256)); CU(ctx->d_dirty.reserve(n_pairs)); CU(ctx->h_dirty.reserve(n_pairs));
     if (want_ops) CU(ctx->d_ops_off.reserve(n_pairs + 1));
     CU(cudaMemsetAsync(ctx->d_alpha.p, 0, ctx->alpha_slots * sizeof(AlphaInfo), ctx->s_copy));
+    CU(cudaMemsetAsync(ctx->d_hist.p, 0, ctx->alpha_slots * 256 * sizeof(uint32_t), ctx->s_copy));
+    if (n_pairs) CU(cudaMemsetAsync(ctx->d_dirty.p, 0, n_pairs, ctx->s_copy));
     bool async_down = pipelined && results;
     for (uint32_t r = 0; r < n_runs && async_down; ++r) async_down = is_pinned(results[r]);
     uint64_t launches = 0;
@@ -870,13 +1049,19 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
         CU(cudaStreamWaitEvent(ctx->s_fill, ev[0], 0));
         if (pb1 > pb0) {
             const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count * 4u, (pb1 - pb0 + 4095) / 4096);
-            alphabet_kernel<<<grid, 256, 0, ctx->s_fill>>>(ctx->d_pat.p + pb0, pb1 - pb0, ctx->d_alpha.p + si);
+            alphabet_kernel<<<grid, 256, 0, ctx->s_fill>>>(ctx->d_pat.p + pb0, pb1 - pb0, ctx->d_hist.p + si * 256);
             CU(cudaGetLastError());
             ++launches;
         }
-        alphabet_finish_kernel<<<1, 32, 0, ctx->s_fill>>>(ctx->d_alpha.p + si);
+        alphabet_finish_kernel<<<1, 32, 0, ctx->s_fill>>>(ctx->d_alpha.p + si, ctx->d_hist.p + si * 256);
         CU(cudaGetLastError());
         ++launches;
+        if (npp) {                                                       // exits at once unless the segment holds a fifth pattern symbol
+            dirty_kernel<<<(unsigned)((npp + 255) / 256), 256, 0, ctx->s_fill>>>(ctx->d_pat.p, ctx->d_pat_off.p, ctx->d_pps.p + sg.pp_first, (uint32_t)npp,
+                                                                                  ctx->d_alpha.p + si, ctx->d_dirty.p + sg.pp_first);
+            CU(cudaGetLastError());
+            ++launches;
+        }
         if (ctx->trace) tr_host.push_back(ms_since(t_begin));
 
         if (pipelined) {
@@ -904,21 +1089,25 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
     CU(cudaMemcpyAsync(ctx->h_alpha.p, ctx->d_alpha.p, ctx->alpha_slots * sizeof(AlphaInfo), cudaMemcpyDeviceToHost, s0));
     CU(cudaStreamSynchronize(s0));
     AlphaInfo batch_alpha{};
-    bool any_flagged = false;
+    bool any_dirty = false;
     for (size_t si = 0; si < ctx->segs.size(); ++si) {
         const AlphaInfo& a = ctx->h_alpha.p[si];
         for (int w = 0; w < 8; ++w) batch_alpha.mask[w] |= a.mask[w];
-        Segment& sg = ctx->segs[si];
-        if (a.too_many && !sg.classes.empty()) {
-            sg.flagged = true; any_flagged = true;
-            for (uint64_t q = 0; q < sg.n_pp; ++q) {
-                const PPDesc& d = ctx->h_pps.p[sg.pp_first + q];
+        any_dirty |= a.too_many && ctx->segs[si].n_pp;
+    }
+    if (any_dirty) {
+        // some segment holds a fifth pattern symbol: the pair-pairs dirty_kernel flagged were skipped by the s16x2 kernels; wide32 serves their pairs
+        CU(cudaMemcpyAsync(ctx->h_dirty.p, ctx->d_dirty.p, ctx->n_pp_total, cudaMemcpyDeviceToHost, s0));
+        CU(cudaStreamSynchronize(s0));
+        ctx->d2h += ctx->n_pp_total;
+        const size_t before = ctx->wide_pairs.size();
+        for (uint64_t q = 0; q < ctx->n_pp_total; ++q)
+            if (ctx->h_dirty.p[q]) {
+                const PPDesc& d = ctx->h_pps.p[q];
                 ctx->wide_pairs.push_back(d.a); if (d.b != d.a) ctx->wide_pairs.push_back(d.b);
             }
-            ctx->fill_bytes -= sg.chunks * sizeof(Chunk);
-        }
+        if (ctx->wide_pairs.size() != before) std::sort(ctx->wide_pairs.begin(), ctx->wide_pairs.end());
     }
-    if (any_flagged) std::sort(ctx->wide_pairs.begin(), ctx->wide_pairs.end());
     alpha_from_mask(batch_alpha);
     ctx->h_alpha.p[ctx->alpha_slots - 1] = batch_alpha;
     if (!ctx->wide_pairs.empty()) {
@@ -931,7 +1120,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
         // resident mode: size the lanes' records now so that b2a_batch_run never allocates
         uint64_t nl = 0;                                          // b2a_batch_run hands the lanes out in launch order
         for (const Segment& sg : ctx->segs) {
-            if (sg.flagged || sg.classes.empty()) continue;
+            if (sg.classes.empty()) continue;
             Lane& ln = ctx->lanes[nl++ % (uint64_t)ctx->n_lanes];
             CU(ln.codes.reserve(sg.chunks));
             if (any_local) CU(ln.rowbest.reserve(sg.rowbest_words));
@@ -948,6 +1137,8 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
         if (rc != B2A_OK) return rc;
         rc = wide_traceback(ctx, (int)r, s0, &launches, score_only);
         if (rc != B2A_OK) return rc;
+        rc = wide_ckpt_run(ctx, (int)r, s0, &launches);
+        if (rc != B2A_OK) return rc;
     }
     CU(cudaStreamSynchronize(s0));
     if (n_pairs && (!async_down || !ctx->wide_pairs.empty())) {
@@ -962,7 +1153,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
             const Segment& sg = ctx->segs[si];
             cudaEvent_t* ev = seg_events(ctx, si, 0);
             float g[4] = {0, 0, 0, 0};
-            for (int e = 0; e < 4; ++e) if (e == 0 || !(sg.classes.empty() || sg.flagged)) cudaEventElapsedTime(&g[e], ctx->ev_begin, ev[e]);
+            for (int e = 0; e < 4; ++e) if (e == 0 || !sg.classes.empty()) cudaEventElapsedTime(&g[e], ctx->ev_begin, ev[e]);
             std::fprintf(stderr, "[b2a trace] seg %2zu pairs %7llu | host: scanned %6.2f planned %6.2f launched %6.2f | device: inputs %6.2f fill %6.2f..%6.2f tb ..%6.2f\n",
                          si, (unsigned long long)sg.count, tr_host[3 * si], tr_host[3 * si + 1], tr_host[3 * si + 2], g[0], g[1], g[2], g[3]);
         }
@@ -1030,7 +1221,7 @@ void b2a_destroy(b2a_ctx* ctx) {
     if (ctx->s_tb) cudaStreamDestroy(ctx->s_tb);
     ctx->d_pat.release(); ctx->d_txt.release(); ctx->d_pat_off.release(); ctx->d_txt_off.release();
     ctx->d_code_off.release(); ctx->d_ops_off.release(); ctx->d_pps.release();
-    ctx->d_alpha.release(); ctx->d_nops.release();
+    ctx->d_alpha.release(); ctx->d_nops.release(); ctx->d_hist.release(); ctx->d_dirty.release(); ctx->h_dirty.release();
     for (auto& rb : ctx->run) rb.release();
     ctx->h_pps.release(); ctx->h_code_off.release(); ctx->h_ops_off.release(); ctx->h_alpha.release();
     ctx->wide.release();
@@ -1079,12 +1270,13 @@ int b2a_batch_run(b2a_ctx* ctx, float* fill_ms, float* traceback_ms)
     if (!ctx->wide_pairs.empty()) { int rc = wide_fill(ctx, 0, s0, &launches); if (rc != B2A_OK) return rc; }
     CU(cudaEventRecord(wev[2], s0));
     if (!ctx->wide_pairs.empty()) { int rc = wide_traceback(ctx, 0, s0, &launches, score_only); if (rc != B2A_OK) return rc; }
+    if (!ctx->wide_pairs.empty()) { int rc = wide_ckpt_run(ctx, 0, s0, &launches); if (rc != B2A_OK) return rc; }
     CU(cudaEventRecord(wev[3], s0));
     CU(cudaEventRecord(ctx->ev_end, s0));
     CU(cudaStreamSynchronize(s0));
     float f = 0, t = 0, tot = 0, x = 0;
     for (size_t si = 0; si <= ctx->segs.size(); ++si) {
-        if (si < ctx->segs.size() && (ctx->segs[si].classes.empty() || ctx->segs[si].flagged)) continue;
+        if (si < ctx->segs.size() && ctx->segs[si].classes.empty()) continue;
         cudaEvent_t* ev = seg_events(ctx, si, 0);
         CU(cudaEventElapsedTime(&x, ev[1], ev[2])); f += x;
         CU(cudaEventElapsedTime(&x, ev[2], ev[3])); t += x;
@@ -1260,6 +1452,8 @@ int b2a_set_option(b2a_ctx* ctx, int option, int64_t value)
         case B2A_OPT_SEG_FIRST:  if (value < 1) break; ctx->seg_first_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, (uint64_t)value); return B2A_OK;
         case B2A_OPT_SEG_BYTES:  if (value < 1) break; ctx->seg_budget_bytes = (uint64_t)value; return B2A_OK;
         case B2A_OPT_TB:         ctx->tb_opt = (int)value; return B2A_OK;
+        case B2A_OPT_CKPT_BYTES: if (value < 0) break; ctx->wide_ckpt_bytes = (uint64_t)value; return B2A_OK;
+        case B2A_OPT_CKPT_GROUP: if (value < 1) break; ctx->wide_ckpt_group_bytes = (uint64_t)value; return B2A_OK;
     }
     return fail(ctx, B2A_ERR_ARG, "b2a_set_option: unknown option or bad value");
 }
@@ -1314,7 +1508,7 @@ int64_t b2a_copy_ops(b2a_ctx* ctx, uint32_t* ops_words, uint64_t cap_words, uint
 int64_t b2a_debug_copy_record(b2a_ctx* ctx, void* chunks, uint64_t chunk_cap, void* rowbest, uint64_t rowbest_cap)
 {
     if (!ctx) return B2A_ERR_ARG;
-    if (!ctx->ran || ctx->segs.empty() || ctx->segs[0].classes.empty() || ctx->segs[0].flagged)
+    if (!ctx->ran || ctx->segs.empty() || ctx->segs[0].classes.empty())
         return fail(ctx, B2A_ERR_STATE, "b2a_debug_copy_record: no short16 record");
     // the first segment's record still sits in lane 0 only if no later (segment, run) launch reused that lane
     if (ctx->n_launched > (uint64_t)ctx->n_lanes)

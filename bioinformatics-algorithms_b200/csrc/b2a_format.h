@@ -12,9 +12,12 @@
 //   reference by construction.
 //
 // Geometry (both kernel families): a BAND is 32 lanes x R rows; lane L owns rows
-//   i = band*32R + L*R + r + 1, r = 0..R-1.  At wavefront step q lane L is at column j = q - L
+//   i = band*32R + L*R + r + 1, r = 0..R-1.  At (lane-)step q lane L is at column j = q - L*SKEW
 //   (active iff 1 <= j <= n, otherwise its H registers are frozen, which makes D = -gap, still in
-//   range).  A word holds F = WBITS/K steps, a 16-byte chunk holds NWORDS words + the anchor
+//   range).  SKEW = 1: the lanes follow each other one column apart (one shuffle per column).  SKEW = 4
+//   (wide32, K <= 8): a lane computes R x 4 cells per macro-step from four independent shuffles, so the
+//   next lane is four columns behind (a register tile instead of a single column: 4-5x the cells per
+//   dependent shuffle, which is what a single long pair -- one warp per band -- is bound by).  A word holds F = WBITS/K steps, a 16-byte chunk holds NWORDS words + the anchor
 //   (= H after the chunk's last step) and covers CS = NWORDS*F steps.
 //   wide32 : chunk index of (band, r, c, L) = ((band*R + r)*NC + c)*32 + L  -> a warp stores 512 contiguous bytes;
 //            the chunks of one row are 32 apart.
@@ -55,21 +58,29 @@ struct PairResult {
 
 enum : uint32_t { OP_M = 0, OP_D = 1, OP_I = 2 };
 
-template <int K_, int WBITS_, int NWORDS_> struct Fmt {
+template <int K_, int WBITS_, int NWORDS_, int SKEW_ = 1> struct Fmt {
     static_assert(K_ == 2 || K_ == 4 || K_ == 8 || K_ == 16 || K_ == 32, "delta width");
     static_assert(WBITS_ % K_ == 0 && (WBITS_ == 16 || WBITS_ == 32), "word width");
-    static constexpr int K = K_, WBITS = WBITS_, NWORDS = NWORDS_;
+    static_assert(SKEW_ == 1 || (WBITS_ / K_) % SKEW_ == 0, "a macro-step never straddles a delta word");
+    static constexpr int K = K_, WBITS = WBITS_, NWORDS = NWORDS_, SKEW = SKEW_;
     static constexpr int F = WBITS_ / K_;       // steps per word
     static constexpr int CS = NWORDS_ * F;      // steps per 16-byte chunk
     static constexpr uint32_t MASK = K_ == 32 ? 0xFFFFFFFFu : ((1u << (K_ & 31)) - 1u);
 };
+// Lane skew of the wide32 RECORD.  4 was built and measured (profiles/r02_wide32_tile.md): the 4-column register tile raises the
+// throughput of many concurrent pairs by 9 % but makes ONE long pair slower (13.1 vs 10.0 ms at 100 kb): the bottom row of a band
+// exists 31 lane-to-lane hand-offs after its top row whatever the tile width, and a 4-column macro-step takes 3.5x as long as a
+// single step.  So kernels that write a record keep skew 1; the score-only kernels (no record, many pairs) use the tile.
+constexpr int wide_skew(int /*K*/) { return 1; }
+constexpr int WIDE_TILE_SCORE_ONLY = 4;
 template <int K> using Short16 = Fmt<K, 16, 3>;
-template <int K> using Wide32 = Fmt<K, 32, 2>;
-template <int K> using Geo = Short16<K>;        // historical name used by the short16 kernels
+template <int K> using Wide32 = Fmt<K, 32, 2, wide_skew(K)>;
+template <int K> using Geo = Short16<K>;        // the short16 kernels' name for their geometry
 
 constexpr int WIDE_R = 4;                        // rows per lane in the wide32 family (band = 128 rows)
 
-B2A_HD uint32_t num_chunks(uint32_t n, int CS) { return (n + 32u + (uint32_t)CS - 1u) / (uint32_t)CS; }
+// chunks per DP row: lane 31 reaches column n at step n + 31*skew
+B2A_HD uint32_t num_chunks(uint32_t n, int CS, int skew = 1) { return (n + 31u * (uint32_t)skew + (uint32_t)CS) / (uint32_t)CS; }
 
 // number of distinct D values of a scoring scheme; 0 if the delta-range lemma does not apply
 B2A_HD long delta_span(int match, int mismatch, int gap) {
@@ -155,6 +166,8 @@ struct PairView {
     int match, mismatch, gap, bias;
     int opt;                   // walker bits: 1 = batch runs of 'l' moves, 2 = L2-prefetch rows ahead, 4 = hw4 tie order d > u > l
     int rmagic;                // short16: ceil(65536 / R)
+    const int32_t* top = nullptr;   // checkpointed sub-problems (wide32): exact H of the row above row 1, top[j] for columns 0..n; null = the
+                                    // real border row 0 (H = bias + j*gap global / 0 local)
 };
 
 template <class FM> B2A_HD uint32_t word_of(const Chunk& ch, int wi, int half) {
@@ -240,14 +253,22 @@ struct RowCursor {
     uint64_t X;         // field string of the current chunk
     uint64_t cidx;      // index of the current chunk (chunks of a row are 32 apart); 0 on the border row
     int H, off, c;      // off = bit offset of the current field
-    int dborder;        // D of the virtual row 0 (0 global, -gap local), unused otherwise
+    int dborder;        // D of the virtual row 0 (0 global, -gap local; from the checkpoint row of a sub-problem), unused otherwise
     bool border;
     B2A_HD void seek(const PairView& v, const Loader& ld, uint32_t i, uint32_t j) {
-        if (i == 0) { border = true; H = LOCAL ? 0 : v.bias + (int)j * v.gap; X = 0; off = 0; c = 0; cidx = 0; dborder = LOCAL ? -v.gap : 0; return; }
+        if (i == 0) {
+            border = true; X = 0; off = 0; cidx = 0;
+            if (v.top) {                                             // row 0 of a checkpointed sub-problem: stored values (top[0..n]), not the border formula
+                c = (int)j;                                          // (c doubles as the column on this row)
+                H = v.top[j];
+                dborder = j ? H - v.top[j - 1] - v.gap : 0;
+            } else { c = 0; H = LOCAL ? 0 : v.bias + (int)j * v.gap; dborder = LOCAL ? -v.gap : 0; }
+            return;
+        }
         border = false; dborder = 0;
         uint32_t L;
         const uint64_t base = chunk_index<FM>(v, i, 0, L);
-        const uint32_t q = j + L;
+        const uint32_t q = j + L * (uint32_t)FM::SKEW;
         c = (int)(q / (uint32_t)FM::CS);
         const int rem = (int)(q - (uint32_t)c * (uint32_t)FM::CS);
         cidx = base + (uint64_t)c * chunk_stride<FM>(v);
@@ -263,6 +284,10 @@ struct RowCursor {
     }
     // move to column j-1 (caller guarantees j >= 1)
     B2A_HD void left(const PairView& v, const Loader& ld) {
+        if (border && v.top) {                                       // step along the checkpoint row
+            if (c > 0) { --c; H = v.top[c]; dborder = c ? H - v.top[c - 1] - v.gap : 0; }
+            return;
+        }
         H -= D() + v.gap;
         off += FM::K;
         if (off == BITS) {
@@ -282,7 +307,7 @@ B2A_HD void prefetch_row(const PairView& v, const Loader& ld, uint32_t i, uint32
     if (i == 0) return;
     uint32_t L;
     const uint64_t base = chunk_index<FM>(v, i, 0, L);
-    ld.prefetch(base + (uint64_t)((j + L) / (uint32_t)FM::CS) * chunk_stride<FM>(v));
+    ld.prefetch(base + (uint64_t)((j + L * (uint32_t)FM::SKEW) / (uint32_t)FM::CS) * chunk_stride<FM>(v));
 }
 
 // ---- Needleman-Wunsch traceback, hw2.cpp:158-181 on reconstructed H; directions per hw2.cpp:145-153 ----
@@ -352,6 +377,7 @@ B2A_HD void find_local_end(const PairView& v, Loader ld, int& M, uint32_t& bi, u
     if (M == 0) { bi = 0; return; }                                 // hw2.cpp:202-203: best cell stays (0,0)
     uint32_t L;
     const uint64_t rowbase = chunk_index<FM>(v, bi, 0, L);
+    L *= (uint32_t)FM::SKEW;                                        // from here on: the row's step offset (q = j + L)
     int run = 0;                                                    // H(bi, 0) = 0
     uint32_t q = L + 1u;
     while (q <= L + v.n && bj == 0) {

@@ -21,59 +21,12 @@
 #include <vector>
 
 #include "b2align.h"
+#include "fasta_hw2.h"
 
 namespace {
 
-struct FastaBatch {                      // sequences only, concatenated, with offsets (count + 1)
-    std::vector<uint8_t> bytes;
-    std::vector<uint64_t> off{0};
-    size_t count() const { return off.size() - 1; }
-    std::string seq(size_t k) const { return std::string(bytes.begin() + off[k], bytes.begin() + off[k + 1]); }
-};
-
-// hw2.cpp:25-57 semantics: trailing CR/whitespace stripped per line, blank lines skipped, '>' lines
-// flush the current record only if it is non-empty, everything else is appended verbatim.
-// The file is read in one piece and scanned with memchr (a 1 GB text file parses in ~0.4 s; getline took 1.2 s).
-bool load_fasta(const std::string& path, FastaBatch& out)
-{
-    std::FILE* f = std::fopen(path.c_str(), "rb");
-    if (!f) return false;
-    std::vector<char> buf;
-    if (std::fseek(f, 0, SEEK_END) == 0) {
-        const long sz = std::ftell(f);
-        std::rewind(f);
-        if (sz > 0) buf.resize((size_t)sz);
-    }
-    size_t got = buf.empty() ? 0 : std::fread(buf.data(), 1, buf.size(), f);
-    if (got == buf.size()) {                                 // pipes / growing files: keep reading
-        char tmp[1 << 16];
-        size_t k;
-        while ((k = std::fread(tmp, 1, sizeof tmp, f)) > 0) { buf.insert(buf.end(), tmp, tmp + k); got += k; }
-    }
-    std::fclose(f);
-    buf.resize(got);
-    out.bytes.reserve(out.bytes.size() + got);
-    bool open_record = false;                                // bytes appended since the last flush
-    const char* p = buf.data();
-    const char* const end = p + got;
-    while (p < end) {
-        const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
-        const char* stop = nl ? nl : end;
-        const char* e = stop;
-        while (e > p && (e[-1] == '\r' || std::isspace((unsigned char)e[-1]))) --e;
-        if (e > p) {
-            if (*p == '>') {
-                if (open_record) { out.off.push_back(out.bytes.size()); open_record = false; }
-            } else {
-                out.bytes.insert(out.bytes.end(), p, e);
-                open_record = true;
-            }
-        }
-        p = nl ? nl + 1 : end;
-    }
-    if (open_record) out.off.push_back(out.bytes.size());
-    return true;
-}
+using b2a_cli::FastaBatch;
+using b2a_cli::load_fasta;
 
 struct Shard {
     uint64_t first = 0, count = 0;
@@ -151,12 +104,13 @@ int main(int argc, char** argv)
                 b2a_ctx* ctx = b2a_create(d);
                 ctxs[d] = ctx;
                 if (!ctx) { s.rc = B2A_ERR_CUDA; s.err = "cannot create a context on device " + std::to_string(d); return; }
+                if (d == 0) stamp("context created");
                 // rebase the shard's offsets so the device only receives its own bytes
                 std::vector<uint64_t> po(s.count + 1), to(s.count + 1);
                 for (uint64_t k = 0; k <= s.count; ++k) { po[k] = pats.off[s.first + k] - pats.off[s.first]; to[k] = txts.off[s.first + k] - txts.off[s.first]; }
                 b2a_params prm{mode, match, mismatch, gap, B2A_WANT_OPS};
-                s.rc = b2a_align_batch(ctx, &prm, pats.bytes.data() + pats.off[s.first], po.data(),
-                                       txts.bytes.data() + txts.off[s.first], to.data(), s.count, results.data() + s.first);
+                s.rc = b2a_align_batch(ctx, &prm, pats.data + pats.off[s.first], po.data(),
+                                       txts.data + txts.off[s.first], to.data(), s.count, results.data() + s.first);
                 if (s.rc != B2A_OK) s.err = b2a_last_error(ctx);
             });
         }
@@ -182,7 +136,7 @@ int main(int argc, char** argv)
             std::vector<char> buf(24ull * (r.n_ops + 2) + 64);
             b2a_render_cigar(ops.data(), r.n_ops, buf.data(), buf.size());
             cigar = buf.data();
-            b2a_render_mdz(ops.data(), r.n_ops, pats.bytes.data() + pats.off[best], txts.bytes.data() + txts.off[best],
+            b2a_render_mdz(ops.data(), r.n_ops, pats.data + pats.off[best], txts.data + txts.off[best],
                            r.start_i, r.start_j, buf.data(), buf.size());
             mdz = buf.data();
         }
@@ -218,7 +172,7 @@ int main(int argc, char** argv)
                         for (uint32_t q = 0; q < r.n_ops; ++q) ops[q] = L[(w[q >> 4] >> (2 * (q & 15))) & 3u];
                         o += std::to_string(k); o += '\t'; o += std::to_string(r.score); o += '\t'; o += std::to_string(r.overlap); o += '\t';
                         b2a_render_cigar(ops.data(), r.n_ops, buf.data(), buf.size()); o += buf.data(); o += '\t';
-                        b2a_render_mdz(ops.data(), r.n_ops, pats.bytes.data() + pats.off[k], txts.bytes.data() + txts.off[k], r.start_i, r.start_j, buf.data(), buf.size());
+                        b2a_render_mdz(ops.data(), r.n_ops, pats.data + pats.off[k], txts.data + txts.off[k], r.start_i, r.start_j, buf.data(), buf.size());
                         o += buf.data(); o += '\n';
                     }
                 });

@@ -29,9 +29,10 @@
 
 namespace b2a {
 
-// Pattern alphabet of a sub-batch, produced on the device (alphabet kernels in b2a_api.cu) so that the
-// host never has to wait for it: the PRMT score tables hold 4 symbols; with more, the s16x2 kernels
-// return at once and raise `too_many` (the host then re-runs the sub-batch through wide32).
+// Pattern alphabet of a segment, produced on the device (alphabet kernels in b2a_api.cu) so that the host never has
+// to wait for it: the PRMT score tables hold 4 symbols -- the segment's four most frequent pattern bytes.  If the
+// segment holds others too (too_many: an 'N' in a read), the pair-pairs that contain one are flagged per pair-pair
+// (FillArgs::dirty); the s16x2 kernels skip exactly those and the host hands their pairs to wide32 afterwards.
 struct AlphaInfo { uint32_t mask[8]; uint8_t sym[4]; int32_t nsym; int32_t too_many; };
 
 struct FillArgs {
@@ -47,7 +48,8 @@ struct FillArgs {
     uint32_t        n_pp;
     int32_t         match, mismatch, gap, bias;
     uint32_t        radix;      // 2^K, passed at run time so the word update stays an IMAD (FMA pipe)
-    const AlphaInfo* alpha;     // device-resident: the (<= 4) distinct pattern symbols of this sub-batch
+    const AlphaInfo* alpha;     // device-resident: the (<= 4) table symbols of this segment
+    const uint8_t*  dirty;      // per pair-pair of this launch: 1 = a pattern byte outside the table symbols, skip (wide32 serves it)
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -74,7 +76,6 @@ short16_fill_kernel(const FillArgs A)
     __shared__ uint2 s_ring[FILL_WARPS][256];
     __shared__ uint32_t s_tbl4[256];                     // byte -> 4 int8 scores against sym[0..3]
 
-    if (A.alpha->too_many) return;                       // uniform: the whole grid leaves
     const int nsym = A.alpha->nsym;
     uint8_t sym[4];
 #pragma unroll
@@ -92,7 +93,7 @@ short16_fill_kernel(const FillArgs A)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t pp = blockIdx.x * FILL_WARPS + warp;
-    if (pp >= A.n_pp) return;
+    if (pp >= A.n_pp || A.dirty[pp]) return;             // warp-uniform
     uint2* ring = s_ring[warp];
 
     const PPDesc d = A.pps[pp];

@@ -64,18 +64,19 @@ __device__ __forceinline__ void warp_prefetch_window(const PairView& v, const Lo
         const uint32_t pi = i - 32u - (uint32_t)lane, pj = j > 32u + (uint32_t)lane ? j - 32u - (uint32_t)lane : 1u;
         uint32_t L;
         const uint64_t base = chunk_index<FM>(v, pi, 0, L);
-        ld.prefetch(base + (uint64_t)((pj + L) / (uint32_t)FM::CS) * chunk_stride<FM>(v));
+        ld.prefetch(base + (uint64_t)((pj + L * (uint32_t)FM::SKEW) / (uint32_t)FM::CS) * chunk_stride<FM>(v));
     }
 }
 
-// Walks from (i, j) until the reference's loop would stop; returns the stop cell in (i, j).
+// Walks from (i, j) until the reference's loop would stop; returns the stop cell in (i, j).  `cur` is the exact-match run that is open
+// at (i, j) (0 at the start of an alignment; a checkpointed walk carries it from one sub-problem to the next).
 template <class FM, class Loader, bool LOCAL>
 __device__ __forceinline__ void warp_walk(const PairView& v, const Loader& ld, WarpOpsSink& sink, uint32_t& i, uint32_t& j,
-                                           uint32_t& nops, int& best, uint32_t& mism)
+                                           uint32_t& nops, int& best, uint32_t& mism, int& cur)
 {
     const int lane = (int)(threadIdx.x & 31u);
     const bool hw4 = !LOCAL && (v.opt & 4) != 0;            // tie order d > u > l (hw4.cpp:37-46) instead of hw2's d > l > u
-    int cur = 0, hyp = HYP_DIAG;
+    int hyp = HYP_DIAG;
     uint32_t last_op = OP_M;
     while (i > 0 && j > 0) {
         const uint32_t di = hyp == HYP_LEFT ? 0u : (uint32_t)lane, dj = hyp == HYP_UP ? 0u : (uint32_t)lane;
@@ -162,6 +163,7 @@ __device__ __forceinline__ void warp_find_local_end(const PairView& v, const Loa
     M = mloc; bi = iloc;
     uint32_t L;
     const uint64_t rowbase = chunk_index<FM>(v, bi, 0, L);
+    L *= (uint32_t)FM::SKEW;                                        // the row's step offset: column j sits at step q = j + L
     const uint32_t c0 = (L + 1u) / (uint32_t)FM::CS, c1 = (L + v.n) / (uint32_t)FM::CS;   // chunks holding columns 1..n
     uint32_t cand = 0xFFFFFFFFu;                                    // smallest step q with H == M
     for (uint32_t c = c0 + (uint32_t)lane; c <= c1; c += 32u) {

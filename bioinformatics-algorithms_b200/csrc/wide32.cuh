@@ -32,8 +32,14 @@ struct WidePair {
     uint64_t bound_off;             // entry index of the pair's 2 boundary rows (each bound_stride long); multi-band pairs only
     uint64_t rowbest_off;           // uint32 index, nbands*128 entries
     uint32_t m, n, pair, nbands;
-    uint32_t bound_stride, pad;
+    uint32_t bound_stride;
+    // ---- checkpointed long pairs (b2a_api.cu wide_ckpt): the pair may be a SUB-PROBLEM, rows row_base+1 .. row_base+m of a longer pattern ----
+    uint32_t row_base;              // rows above the sub-problem (0 for a whole pair): the left border is H(i, 0) = (row_base + i) gap
+    uint64_t top_off;               // index into WideArgs::ck of the stored row above row 1 (entries 0..n); ~0 = the real border row 0
+    uint64_t ck_off;                // where this launch keeps checkpoint rows: ck[ck_off + (g * ck_stride) + j] = H((g + 1) ck_every bands, j)
+    uint32_t ck_every, ck_stride;   // keep the bottom row of every ck_every-th band (0 = none); entries per kept row
 };
+constexpr uint64_t WIDE_NO_TOP = ~0ull;
 struct WideTask { uint32_t wp, band; };
 
 struct WideArgs {
@@ -50,7 +56,7 @@ struct WideArgs {
     int32_t         match, mismatch, gap;
     uint32_t        radix;
     uint32_t        epoch_tag;      // epoch << 20
-    unsigned long long* debug;      // optional (B2A_WIDE_DEBUG): per task {claimed, first block staged, first block done, band done} in ns
+    int32_t*        ck;             // checkpoint rows (plain int32 H values), see WidePair
     const AlphaInfo* alpha;         // used by the ALPHA4 variant only
 };
 
@@ -91,14 +97,24 @@ __device__ __forceinline__ uint32_t prmt32(uint32_t a, uint32_t b, uint32_t sel)
 
 // K: delta width; LOCAL: Smith-Waterman; STORE: write the traceback record; ALPHA4: pattern alphabet
 // has <= 4 symbols and scores fit int8, so the substitution score is one PRMT from a 4-entry table.
+//
+// A lane owns R rows and computes them C columns at a time (a register tile of R x C cells per MACRO-STEP): the bottom-row values of
+// the lane above for those C columns arrive through C independent shuffles and the tile's cells form a small wavefront of their own.
+// C = 1 for every launch that writes a record (the lanes follow each other one column apart); C = 4 for the score-only launches, where
+// many pairs are in flight and the tile's shorter instruction stream per cell pays (config 5 linear: 3684 -> 4001 GCUPS).  For ONE long
+// pair C = 4 is slower (measured, see b2a_format.h wide_skew).
 template <int K, bool LOCAL, bool STORE, bool ALPHA4>
 __global__ void __launch_bounds__(WIDE_WARPS * 32)
 wide32_fill_kernel(const WideArgs A)
 {
     using FM = Wide32<K>;
-    constexpr int R = WIDE_R, F = FM::F, CS = FM::CS, CPB = 32 / CS;   // chunks per 32-step block
-    __shared__ uint2 s_ring[WIDE_WARPS][64];       // per 1-based column j (slot j & 63): {text entry, H(top row, j)}
-    __shared__ int32_t s_out[WIDE_WARPS][32];      // bottom-row values lane 31 produced during the current block
+    constexpr int C = STORE ? FM::SKEW : WIDE_TILE_SCORE_ONLY;                   // score-only launches (instantiated with K = 2) use the tile
+    static_assert(STORE || K == 2, "score-only kernels are launched with K = 2: no record, the word structure only paces the loop");
+    constexpr int R = WIDE_R, F = FM::F, CS = FM::CS, CPB = 32 / CS;               // CPB: chunks per 32-step block
+    constexpr uint32_t RING = C == 1 ? 64u : 256u, RMASK = RING - 1u;               // live columns of a block: [q0 - 31 C, q0 + 31]
+    static_assert(32 * C + 32 <= (int)RING, "ring too small for the lane skew");
+    __shared__ __align__(16) uint2 s_ring[WIDE_WARPS][RING];   // per 1-based column j (slot j & RMASK): {text entry, H(top row, j)}
+    __shared__ int32_t s_out[WIDE_WARPS][32];                  // bottom-row values lane 31 produced during the current block
     __shared__ uint32_t s_tbl4[256];
     uint8_t sym[4] = {0, 0, 0, 0};
     if (ALPHA4) {
@@ -153,7 +169,7 @@ wide32_fill_kernel(const WideArgs A)
                     for (int k = 1; k < 4; ++k) if (x == sym[k]) c = k; }
                 pc[r] = c | ((8u | c) << 4) | ((8u | c) << 8) | ((8u | c) << 12);
             } else pc[r] = i0 < m ? (uint32_t)pp[i0] : 0xFFFFFFFFu;         // junk rows never match
-            H[r] = LOCAL ? 0 : (int32_t)(i0 + 1) * gap;                      // hw2.cpp:125-130
+            H[r] = LOCAL ? 0 : (int32_t)(wp.row_base + i0 + 1) * gap;        // hw2.cpp:125-130
             best[r] = 0;
         }
         const uint64_t* bin = A.bound + wp.bound_off + (uint64_t)((band + 1u) & 1u) * wp.bound_stride;
@@ -161,11 +177,15 @@ wide32_fill_kernel(const WideArgs A)
         const uint32_t tag_in = A.epoch_tag + band;                          // what the band above writes
         const uint64_t tag_out = (uint64_t)(A.epoch_tag + band + 1u) << 32;
         const bool has_next = band + 1 < wp.nbands;
-        const uint32_t nblk = (n + 32u + 31u) / 32u;
-        const uint32_t NC = num_chunks(n, CS);
+        const uint32_t nblk = (n + 31u * C + 1u + 31u) / 32u;                // lane 31 reaches column n at step n + 31 C
+        const uint32_t NC = num_chunks(n, CS, C);
         Chunk* rec = A.codes + wp.code_off;
-        const int32_t top0 = LOCAL ? 0 : (int32_t)(band * 32u * R) * gap;    // H(top row, 0)
-        int32_t dgn = top0;
+        const int32_t top0 = LOCAL ? 0 : (int32_t)(wp.row_base + band * 32u * R) * gap;    // H(top row, 0)
+        const int32_t* top = wp.top_off != WIDE_NO_TOP ? A.ck + wp.top_off : nullptr;      // band 0 of a sub-problem reads the row above it
+        int32_t dgn = top0;                                                  // bottom row of the lane above, one column left of the tile
+        int32_t outv[C];                                                     // this lane's bottom row at the C columns of its last tile
+#pragma unroll
+        for (int c = 0; c < C; ++c) outv[c] = H[R - 1];                      // before its first column a lane shows its border value
         uint64_t nx = 0;                                                     // this lane's entry of the next block, loaded a block ahead
         if (band != 0 && lane >= 1 && (uint32_t)lane <= n) nx = ld_relaxed_u64(bin + lane);
 
@@ -177,20 +197,16 @@ wide32_fill_kernel(const WideArgs A)
             return ALPHA4 ? s_tbl4[x] : x;
         };
         uint32_t tnext = text_byte((uint32_t)lane);
-        auto stamp = [&](int k) {
-            if (A.debug && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); A.debug[8ull * tk + k] = t; }
-        };
-        stamp(0);
 
         for (uint32_t kb = 0; kb < nblk; ++kb) {
             const uint32_t q0 = kb * 32u;
-            if (kb == 1) stamp(4);
-            if (kb == 2) stamp(6);
             // ---- stage columns q0 .. q0+31 of the text and of the band above into the ring ----
             int32_t bnd;
             const uint32_t jcol = q0 + (uint32_t)lane;
-            if (band == 0) bnd = LOCAL ? 0 : (int32_t)jcol * gap;            // hw2.cpp:131-136
-            else {
+            if (band == 0) {
+                if (top) bnd = (jcol >= 1 && jcol <= n) ? top[jcol] : top0;
+                else bnd = LOCAL ? 0 : (int32_t)jcol * gap;                  // hw2.cpp:131-136
+            } else {
                 const bool need = jcol >= 1 && jcol <= n;
                 const int32_t got = (int32_t)bound_wait(bin + jcol, nx, tag_in, need);
                 bnd = need ? got : top0;
@@ -198,53 +214,72 @@ wide32_fill_kernel(const WideArgs A)
                 if (jn <= n) nx = ld_relaxed_u64(bin + jn);
             }
             __syncwarp();
-            if (kb == 0) stamp(1);
-            if (kb == 1) stamp(5);
-            ring[jcol & 63u] = make_uint2(text_entry(tnext), (uint32_t)bnd);
+            ring[jcol & RMASK] = make_uint2(text_entry(tnext), (uint32_t)bnd);
             __syncwarp();
-            if (kb == 0) stamp(2);
             tnext = text_byte(q0 + 32u + (uint32_t)lane);                    // prefetch the next block's text
-            // One wavefront step.  RAMP = false: every lane is inside its row range (steady state).  RAMP = true: lanes
-            // outside 1 <= q - lane <= n keep their H frozen -- done with selects, NOT a branch: a branch per step stops
+            // RAMP = false: every lane is inside its column range for the whole block (steady state).  RAMP = true: lanes
+            // outside 1 <= j <= n keep their H frozen -- done with selects, NOT a branch: a branch per step stops
             // the scheduler from overlapping the shuffle / shared-memory latencies of neighbouring steps (2.4x slower).
-            const bool steady = q0 >= 32u && q0 + 31u <= n;
-            // HM: what the step contributes to the delta word's Horner sum: 0 = start it (S = H), 1 = S = S * 2^K + H, 2 = nothing
-            auto step = [&](uint32_t q, uint32_t (&S)[R], auto hm_tag, auto ramp_tag, bool active) {
+            const bool steady = q0 >= 31u * C + 1u && q0 + 31u <= n;
+            // One macro-step: the tile of R rows x C columns at lane-steps qm .. qm + C - 1 (columns qm - lane C + c).
+            // POS: where the C steps sit inside their delta word: 0 = first, 1 = middle, 2 = last, 3 = the whole word.
+            auto macro = [&](uint32_t qm, uint32_t (&S)[R], auto pos_tag, auto ramp_tag) {
                 constexpr bool RAMP = decltype(ramp_tag)::value;
-                constexpr int HM = decltype(hm_tag)::value;
-                int32_t up = __shfl_up_sync(0xFFFFFFFFu, H[R - 1], 1);
-                const uint2 e = ring[(q - (uint32_t)lane) & 63u];   // column q-lane; lane 0 also needs it at q = 0 (H(top,0))
-                if (lane == 0) up = (int32_t)e.y;
-                int32_t dg = dgn, u = up;
-                dgn = up;
+                constexpr int POS = decltype(pos_tag)::value;
+                const uint32_t j0 = qm - (uint32_t)lane * C;                 // may wrap below zero: such columns are inactive
+                uint2 e[C];
+                if (C == 4) {
+                    const uint4* e4 = reinterpret_cast<const uint4*>(ring + (j0 & RMASK));   // j0 is a multiple of 4: 32-byte aligned
+                    const uint4 lo = e4[0], hi = e4[1];
+                    e[0] = make_uint2(lo.x, lo.y); e[1 % C] = make_uint2(lo.z, lo.w); e[2 % C] = make_uint2(hi.x, hi.y); e[3 % C] = make_uint2(hi.z, hi.w);
+                } else {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int32_t s = ALPHA4 ? (int32_t)prmt32(e.x, 0u, pc[r]) : (pc[r] == e.x ? A.match : A.mismatch);
-                    const int32_t ds = dg + s;
-                    dg = H[r];
-                    const int32_t a = __viaddmax_s32(H[r], gap, ds);
-                    int32_t h = LOCAL ? __viaddmax_s32_relu(u, gap, a) : __viaddmax_s32(u, gap, a);
-                    if (RAMP) h = active ? h : H[r];
-                    if (LOCAL) best[r] = max(best[r], h);        // a frozen H is a border 0 or a value already counted
-                    H[r] = h; u = h;
+                    for (int c = 0; c < C; ++c) e[c] = ring[(j0 + (uint32_t)c) & RMASK];
                 }
-                if (lane == 31) outb[q & 31u] = H[R - 1];        // bottom row of the band at column q - 31 (published per block)
-                if (STORE && K < 32 && HM != 2) {
+                int32_t upv[C];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) S[r] = HM == 0 ? (uint32_t)H[r] : S[r] * radix + (uint32_t)H[r];
+                for (int c = 0; c < C; ++c) upv[c] = __shfl_up_sync(0xFFFFFFFFu, outv[c], 1);
+                if (lane == 0) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) upv[c] = (int32_t)e[c].y;    // the band above (or the border row 0); also H(top, 0) at column 0
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const bool active = !RAMP || (uint32_t)(j0 + (uint32_t)c - 1u) < n;
+                    int32_t dg = dgn, u = upv[c];
+                    dgn = upv[c];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int32_t s = ALPHA4 ? (int32_t)prmt32(e[c].x, 0u, pc[r]) : (pc[r] == e[c].x ? A.match : A.mismatch);
+                        const int32_t ds = dg + s;
+                        dg = H[r];
+                        const int32_t a = __viaddmax_s32(H[r], gap, ds);
+                        int32_t h = LOCAL ? __viaddmax_s32_relu(u, gap, a) : __viaddmax_s32(u, gap, a);
+                        if (RAMP) h = active ? h : H[r];
+                        if (LOCAL) best[r] = max(best[r], h);    // a frozen H is a border 0 or a value already counted
+                        H[r] = h; u = h;
+                    }
+                    outv[c] = H[R - 1];
+                    if (lane == 31) outb[(qm + (uint32_t)c) & 31u] = H[R - 1];   // bottom row of the band (published per block)
+                    // what the step contributes to the delta word's Horner sum: start it (S = H), S = S * 2^K + H, or nothing (last step)
+                    constexpr bool first_of_word = (POS == 0 || POS == 3);
+                    constexpr bool last_of_word = (POS == 2 || POS == 3);
+                    const bool is_first = first_of_word && c == 0, is_last = last_of_word && c == C - 1;
+                    if (STORE && K < 32 && !(is_last && F > 1) && F > 1) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) S[r] = is_first ? (uint32_t)H[r] : S[r] * radix + (uint32_t)H[r];
+                    }
                 }
             };
-            // The F steps of one delta word.  Deliberately NOT fully unrolled: fully unrolled the two flavours were 38 KB
-            // of straight-line code, and every band of a long pair paid ~6 us of instruction-fetch stalls for its first
-            // (cold) ramp block -- a cost that chains over all bands of the pair (B2A_WIDE_DEBUG timeline, scripts/band_exp.py).
+            // The F steps of one delta word = F / C macro-steps.  Deliberately NOT one straight-line block per chunk: fully unrolled
+            // the two flavours were 38 KB of code and every band of a long pair paid ~6 us of instruction-fetch stalls for its first
+            // (cold) ramp block -- a cost that chains over all bands of the pair.
             auto word_steps = [&](uint32_t qw, uint32_t (&S)[R], auto ramp_tag) {
-                constexpr bool RAMP = decltype(ramp_tag)::value;
-                auto act = [&](uint32_t q) { return !RAMP || (uint32_t)(q - lane - 1u) < n; };
-                if (F == 1) { step(qw, S, std::integral_constant<int, 2>{}, ramp_tag, act(qw)); return; }
-                step(qw, S, std::integral_constant<int, 0>{}, ramp_tag, act(qw));
+                if (F <= C) { macro(qw, S, std::integral_constant<int, 3>{}, ramp_tag); return; }
+                macro(qw, S, std::integral_constant<int, 0>{}, ramp_tag);
 #pragma unroll MID_UNROLL
-                for (int f = 1; f < F - 1; ++f) step(qw + (uint32_t)f, S, std::integral_constant<int, 1>{}, ramp_tag, act(qw + (uint32_t)f));
-                step(qw + (uint32_t)(F - 1), S, std::integral_constant<int, 2>{}, ramp_tag, act(qw + (uint32_t)(F - 1)));
+                for (int f = C; f < F - C; f += C) macro(qw + (uint32_t)f, S, std::integral_constant<int, 1>{}, ramp_tag);
+                macro(qw + (uint32_t)(F - C), S, std::integral_constant<int, 2>{}, ramp_tag);
             };
 
 #pragma unroll 1
@@ -256,11 +291,10 @@ wide32_fill_kernel(const WideArgs A)
 #pragma unroll
                     for (int r = 0; r < R; ++r) pre[r] = K == 32 ? (0u - (uint32_t)H[r] - g32) : (uint32_t)H[r] * negBpow + negGc;
                     const uint32_t qw = q0 + (uint32_t)(cb * CS + wi * F);
-                    // Both flavours are straight-line code of the same speed: the last two blocks of band b wait for the last
+                    // Both flavours are straight-line code of the same speed: the last blocks of band b wait for the last
                     // block of band b-1, so a slow ramp flavour is paid once PER BAND on the critical path of a long pair.
                     if (steady) word_steps(qw, S, std::false_type{});
                     else word_steps(qw, S, std::true_type{});
-                    if (kb == 0 && cb == CPB - 1 && wi == 1) stamp(3);
                     if (STORE) {
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
@@ -281,12 +315,14 @@ wide32_fill_kernel(const WideArgs A)
             // per block instead of a store per step (the per-step stores cost 8 % on the 120 x 100 kb batch)
             if (has_next) {
                 __syncwarp();
-                const uint32_t jc = q0 + (uint32_t)lane - 31u;                // lane 31 was at this column at step q0 + lane
+                const uint32_t jc = q0 + (uint32_t)lane - 31u * C;            // lane 31 was at this column at step q0 + lane
                 if (jc - 1u < n) st_relaxed_u64(bout + jc, tag_out | (uint32_t)outb[lane]);
+                // checkpointed long pairs: every ck_every-th band also keeps its bottom row (columns 0..n) for the re-fill pass
+                if (wp.ck_every && (band + 1u) % wp.ck_every == 0u && jc <= n)
+                    A.ck[wp.ck_off + (uint64_t)((band + 1u) / wp.ck_every - 1u) * wp.ck_stride + jc] = outb[lane];
                 __syncwarp();
             }
         }
-        stamp(7);
         if (LOCAL) {
 #pragma unroll
             for (int r = 0; r < R; ++r) A.rowbest[wp.rowbest_off + ((uint64_t)band * R + r) * 32u + lane] = (uint32_t)best[r];
@@ -363,22 +399,22 @@ wide32_traceback_kernel(const WideTbArgs A)
     }
     const Chunk* rec = A.codes + wp.code_off;
     const PairView v{rec, A.rowbest + wp.rowbest_off, A.pat + wp.pat_off, A.txt + wp.txt_off,
-                     wp.m, wp.n, num_chunks(wp.n, FM::CS), WIDE_R, 0, A.match, A.mismatch, A.gap, 0, A.opt, 0};
+                     wp.m, wp.n, num_chunks(wp.n, FM::CS, FM::SKEW), WIDE_R, 0, A.match, A.mismatch, A.gap, 0, A.opt, 0};
     const WideLoader ld{rec};
     WarpOpsSink sink(A.ops ? A.ops + A.ops_off[wp.pair] : nullptr, lane == 0);
     uint32_t i, j, nops = 0, mism = 0;
-    int best = 0;
+    int best = 0, cur = 0;
     if (LOCAL) {
         int M; uint32_t bi, bj;
         warp_find_local_end<FM>(v, ld, M, bi, bj);
         res.score = M; res.end_i = bi; res.end_j = bj;
         i = bi; j = bj;
-        if (M != 0) warp_walk<FM, WideLoader, true>(v, ld, sink, i, j, nops, best, mism);
+        if (M != 0) warp_walk<FM, WideLoader, true>(v, ld, sink, i, j, nops, best, mism, cur);
     } else {
         i = wp.m; j = wp.n;
         res.end_i = i; res.end_j = j;
         res.score = (i && j) ? A.final_score[t] : (int32_t)(i + j) * A.gap;               // hw2.cpp:186 / borders :125-136
-        warp_walk<FM, WideLoader, false>(v, ld, sink, i, j, nops, best, mism);
+        warp_walk<FM, WideLoader, false>(v, ld, sink, i, j, nops, best, mism, cur);
         sink.put_run(OP_D, i); nops += i; i = 0;                                           // column 0 holds 'u' (hw2.cpp:128)
         sink.put_run(OP_I, j); nops += j; j = 0;                                           // row 0 holds 'l'    (hw2.cpp:134)
     }
@@ -386,6 +422,99 @@ wide32_traceback_kernel(const WideTbArgs A)
     res.start_i = i; res.start_j = j; res.n_ops = nops; res.path = 2;
     res.overlap = (!LOCAL && (A.opt & 4)) ? (int)(nops - (wp.m + wp.n - nops) + mism) : best;       // hw4.cpp:141-152
     if (lane == 0) A.results[wp.pair] = res;
+}
+
+// ---- checkpointed long pairs: the walk of one pair, carried across its sub-problems (b2a_api.cu wide_ckpt_run) ----
+struct CkptWalk {
+    uint32_t i, j;              // current cell, ABSOLUTE row / column
+    uint32_t nops, mism;
+    int32_t  cur, best;         // open / longest exact-match run (hw2.cpp:267-278)
+    uint32_t word, fill;        // 2-bit op writer
+    uint64_t pos;
+    int32_t  score, done;
+    uint32_t end_i, end_j;
+};
+struct CkptWalkArgs {
+    const uint8_t*  pat;
+    const uint8_t*  txt;
+    const WidePair* pair;       // the sub-problem that has just been filled (record at codes + code_off)
+    const Chunk*    codes;
+    const uint32_t* rowbest;
+    const int32_t*  ck;
+    CkptWalk*       st;
+    PairResult*     result;     // the pair's record, written when the walk is complete
+    uint32_t*       ops;        // the pair's op words, may be null
+    uint32_t        m_total, n_total;
+    int32_t         match, mismatch, gap, opt;
+    int32_t         first;      // local mode: this sub-problem holds the end cell; find it (hw2.cpp:225-229) before walking
+};
+
+// first row of the first row-major maximum (hw2.cpp:225-229) from the per-row maxima of a whole-pair score-only fill: st->i / st->score
+__global__ void __launch_bounds__(32) wide32_first_best_row_kernel(const uint32_t* __restrict__ rowbest, uint32_t m, CkptWalk* st)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    int mloc = 0; uint32_t iloc = 0xFFFFFFFFu;
+    for (uint32_t i = lane + 1u; i <= m; i += 32u) {
+        const uint32_t x = i - 1u;
+        const int rb = (int)rowbest[(uint64_t)((x >> 7) * 4u + (x & 3u)) * 32u + ((x >> 2) & 31u)];   // [(band R + r) 32 + L], R = 4
+        if (rb > mloc) { mloc = rb; iloc = i; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const int om = __shfl_xor_sync(0xFFFFFFFFu, mloc, o);
+        const uint32_t oi = __shfl_xor_sync(0xFFFFFFFFu, iloc, o);
+        if (om > mloc || (om == mloc && oi < iloc)) { mloc = om; iloc = oi; }
+    }
+    if (lane == 0) { st->score = mloc; st->i = mloc ? iloc : 0u; }
+}
+
+template <int K, bool LOCAL>
+__global__ void __launch_bounds__(32) wide32_ckpt_walk_kernel(const CkptWalkArgs A)
+{
+    using FM = Wide32<K>;
+    const int lane = (int)(threadIdx.x & 31u);
+    const WidePair wp = *A.pair;
+    CkptWalk s = *A.st;
+    const Chunk* rec = A.codes + wp.code_off;
+    PairView v{rec, A.rowbest + wp.rowbest_off, A.pat + wp.pat_off, A.txt + wp.txt_off,
+               wp.m, wp.n, num_chunks(wp.n, FM::CS, FM::SKEW), WIDE_R, 0, A.match, A.mismatch, A.gap, 0, A.opt, 0};
+    v.top = wp.top_off != WIDE_NO_TOP ? A.ck + wp.top_off : nullptr;
+    const WideLoader ld{rec};
+    WarpOpsSink sink(A.ops, lane == 0);
+    sink.word = s.word; sink.fill = s.fill; sink.pos = s.pos;
+    uint32_t i = s.i - wp.row_base, j = s.j;                     // the sub-problem's own row index
+    int best = s.best, cur = s.cur;
+    bool walk = true;
+    if (LOCAL && A.first) {
+        int M; uint32_t bi, bj;
+        warp_find_local_end<FM>(v, ld, M, bi, bj);                // rows above this sub-problem hold no earlier maximum: the first pass chose row s.i
+        s.score = M; s.end_i = wp.row_base + bi; s.end_j = bj;
+        i = bi; j = bj;
+        if (M == 0) { s.end_i = s.end_j = 0; i = 0; j = 0; walk = false; s.done = 1; }
+    }
+    if (walk) {
+        warp_walk<FM, WideLoader, LOCAL>(v, ld, sink, i, j, s.nops, best, s.mism, cur);
+        if (LOCAL) {
+            // stopped inside the sub-problem (H == 0), at the left edge, or at the real top border: the alignment is complete (hw2.cpp:239)
+            if ((i > 0 && j > 0) || j == 0 || wp.row_base == 0) s.done = 1;
+        } else if (j == 0) {
+            const uint32_t up = wp.row_base + i;                 // column 0 holds 'u' all the way up (hw2.cpp:128)
+            sink.put_run(OP_D, up); s.nops += up; i = 0; s.done = 2;
+        } else if (i == 0 && wp.row_base == 0) {
+            sink.put_run(OP_I, j); s.nops += j; j = 0; s.done = 1;   // row 0 holds 'l' (hw2.cpp:134)
+        }
+    }
+    s.i = s.done == 2 ? 0u : wp.row_base + i; s.j = j; s.best = best; s.cur = cur;
+    s.word = sink.word; s.fill = sink.fill; s.pos = sink.pos;
+    if (s.done) {
+        sink.flush();
+        PairResult res;
+        res.score = s.score; res.end_i = s.end_i; res.end_j = s.end_j; res.start_i = s.i; res.start_j = s.j;
+        res.n_ops = s.nops; res.path = 2;
+        res.overlap = (!LOCAL && (A.opt & 4)) ? (int)(s.nops - (A.m_total + A.n_total - s.nops) + s.mism) : s.best;   // hw4.cpp:141-152
+        if (lane == 0) *A.result = res;
+    }
+    if (lane == 0) *A.st = s;
 }
 
 } // namespace b2a

@@ -12,8 +12,9 @@ import numpy as np
 ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
-def config2(n_pairs, seed=481, m=150, n=1000, psub=0.05, pdel=0.005, pins=0.005, tie_fraction=0.0):
-    """Returns (pat uint8[n_pairs*m], pat_off, txt uint8[n_pairs*n], txt_off) -- uniform shapes."""
+def config2(n_pairs, seed=481, m=150, n=1000, psub=0.05, pdel=0.005, pins=0.005, tie_fraction=0.0, n_rate=0.0):
+    """Returns (pat uint8[n_pairs*m], pat_off, txt uint8[n_pairs*n], txt_off) -- uniform shapes.
+    n_rate > 0: that fraction of the PATTERN bases becomes 'N' afterwards (own generator: the other bases stay those of n_rate = 0)."""
     rng = np.random.default_rng(seed)
     txt = ACGT[rng.integers(0, 4, size=(n_pairs, n), dtype=np.uint8)]
     off = rng.integers(0, n - m + 1, size=n_pairs)
@@ -47,6 +48,8 @@ def config2(n_pairs, seed=481, m=150, n=1000, psub=0.05, pdel=0.005, pins=0.005,
             per2 = int(rng.integers(1, 8))
             unit2 = unit if rng.random() < 0.5 else ACGT[rng.integers(0, 4, size=per2, dtype=np.uint8)]
             pat[i] = np.tile(unit2, m // len(unit2) + 1)[:m]
+    if n_rate > 0:
+        pat[np.random.default_rng(seed + 7919).random(pat.shape) < n_rate] = ord("N")
     pat_off = (np.arange(n_pairs + 1, dtype=np.uint64) * np.uint64(m))
     txt_off = (np.arange(n_pairs + 1, dtype=np.uint64) * np.uint64(n))
     return np.ascontiguousarray(pat.reshape(-1)), pat_off, np.ascontiguousarray(txt.reshape(-1)), txt_off

@@ -171,6 +171,9 @@ int b2a_affine_star_scores(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_
 #define B2A_OPT_SEG_FIRST  5   /* pairs of the first segment of b2a_align_batch (doubling up to the max) */
 #define B2A_OPT_SEG_BYTES  3   /* DP-record bytes per segment                                            */
 #define B2A_OPT_TB         4   /* traceback walker tuning bits (experiments)                             */
+#define B2A_OPT_CKPT_BYTES 6   /* a long pair whose traceback record (0.5 byte per cell) would exceed this many bytes is walked from
+                                  checkpoint rows instead (score pass + band groups re-filled bottom-up): default 48 GB              */
+#define B2A_OPT_CKPT_GROUP 7   /* ... and this is the record size of one re-filled band group: default 1 GB                         */
 int b2a_set_option(b2a_ctx* ctx, int option, int64_t value);
 
 /* ---- result formatting: prepareCigarString hw2.cpp:59-78, prepareMDZString hw2.cpp:80-116 --- */

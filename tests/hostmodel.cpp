@@ -11,6 +11,7 @@
 #include <cstring>
 #include <vector>
 #include "../bioinformatics-algorithms_b200/csrc/b2a_format.h"
+#include "../bioinformatics-algorithms_b200/csrc/fasta_hw2.h"
 
 using namespace b2a;
 static int g_opt = 3;
@@ -127,7 +128,7 @@ int run_wide(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t 
              PairResult* res, uint32_t* ops) {
     using FM = Wide32<K>;
     constexpr int F = FM::F, CS = FM::CS, R = WIDE_R;
-    const uint32_t NC = num_chunks(n, CS);
+    const uint32_t NC = num_chunks(n, CS, FM::SKEW);
     const uint32_t nbands = (m + 32u * R - 1u) / (32u * R);
     const size_t W = (size_t)n + 1;
     // plain DP, unbiased; rows beyond m never match anything (as in the kernel)
@@ -153,7 +154,7 @@ int run_wide(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t 
             for (int r = 0; r < R; ++r) {
                 const uint32_t i = band * 32u * R + L * R + (uint32_t)r + 1;
                 auto P = [&](int64_t q) -> uint32_t {
-                    int64_t j = q - (int64_t)L;
+                    int64_t j = q - (int64_t)L * FM::SKEW;
                     if (j < 0) j = 0;
                     if (j > (int64_t)n) j = n;
                     return (uint32_t)H[i * W + (size_t)j];
@@ -194,6 +195,17 @@ int run_wide(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t 
 } // namespace
 
 extern "C" {
+
+// bin/hw2's FASTA reader with a forced thread count (min_parallel_bytes = 0): count of records, bytes and offsets into caller buffers;
+// returns the record count, -1 if the file cannot be opened, -2 if a buffer is too small
+int64_t hm_load_fasta(const char* path, unsigned threads, uint8_t* bytes, uint64_t bytes_cap, uint64_t* off, uint64_t off_cap) {
+    b2a_cli::FastaBatch fb;
+    if (!b2a_cli::load_fasta(path, fb, 0, threads)) return -1;
+    if (fb.size > bytes_cap || fb.off.size() > off_cap) return -2;
+    std::memcpy(bytes, fb.data, fb.size);
+    std::memcpy(off, fb.off.data(), fb.off.size() * sizeof(uint64_t));
+    return (int64_t)fb.count();
+}
 
 // number of chunks in one pair-pair record
 uint64_t hm_record_chunks(int K, int R, uint32_t n) {

@@ -26,9 +26,10 @@ class PairResult(C.Structure):
 def hostmodel():
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, "libhostmodel.so")
-    srcs = [os.path.join(HERE, "hostmodel.cpp"), os.path.join(ROOT, "bioinformatics-algorithms_b200", "csrc", "b2a_format.h")]
+    srcs = [os.path.join(HERE, "hostmodel.cpp"), os.path.join(ROOT, "bioinformatics-algorithms_b200", "csrc", "b2a_format.h"),
+            os.path.join(ROOT, "bioinformatics-algorithms_b200", "csrc", "fasta_hw2.h")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-o", so, srcs[0]])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-o", so, srcs[0], "-lpthread"])
     lib = C.CDLL(so)
     lib.hm_record_chunks.restype = C.c_uint64
     return lib
@@ -236,3 +237,57 @@ def test_walkers_match_oracle_long_patterns():
         p2 = (mutate(rng, t2) + rnd(rng, m))[:m]
         for mode in (ob.GLOBAL, ob.LOCAL):
             assert check(lib, mode, p1, t1, p2, t2, (1, -1, -1))
+
+
+def read_fasta_hw2(raw: bytes):
+    """readFasta, hw2.cpp:25-57, restated line by line: getline, trailing whitespace stripped (:38), blank lines skipped (:39), a '>' line
+    flushes the current record only if it is non-empty (:41-46), everything else is appended (:48), last record flushed if non-empty (:52)."""
+    seqs, cur = [], b""
+    for line in raw.split(b"\n"):
+        line = line.rstrip(b" \t\r\n\v\f")
+        if not line:
+            continue
+        if line[:1] == b">":
+            if cur:
+                seqs.append(cur); cur = b""
+        else:
+            cur += line
+    if cur:
+        seqs.append(cur)
+    return seqs
+
+
+def test_parallel_fasta_loader_equals_serial_reader_semantics(tmp_path):
+    """bin/hw2's multi-threaded FASTA loader (csrc/fasta_hw2.h) on messy files, with 1..8 threads forced even on tiny inputs so that chunk
+    borders fall inside records, between headers, on blank lines and on CRLF lines."""
+    import random
+    lib = hostmodel()
+    lib.hm_load_fasta.restype = C.c_int64
+    rng = random.Random(11)
+    files = [b"", b"\n\n", b">only header\n", b"ACGT", b"ACGT\n>h\n>h2\n\nTT\r\nGG  \n>x\n", b">a\nAC\n>b\n\n>c\nGT\n"]
+    for _ in range(120):
+        parts = []
+        for _ in range(rng.randint(0, 40)):
+            r = rng.random()
+            if r < 0.30:
+                parts.append(b">" + bytes(rng.choice(b"abc >") for _ in range(rng.randint(0, 6))))
+            elif r < 0.40:
+                parts.append(rng.choice([b"", b"  ", b"\r", b"\t"]))
+            else:
+                parts.append(bytes(rng.choice(b"ACGTN") for _ in range(rng.randint(1, 30))) + rng.choice([b"", b" ", b"\r", b" \t\r"]))
+        files.append(b"\n".join(parts) + rng.choice([b"", b"\n", b"\n\n"]))
+    big = b"".join(b">r%d\n%s\n" % (k, bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 200)))) for k in range(20000))
+    files.append(big)
+    path = str(tmp_path / "x.fa").encode()
+    for raw in files:
+        with open(path, "wb") as f:
+            f.write(raw)
+        want = read_fasta_hw2(raw)
+        for threads in (1, 2, 3, 5, 8):
+            bytes_buf = (C.c_uint8 * (len(raw) + 1))()
+            off_buf = (C.c_uint64 * (raw.count(b">") + 3))()
+            n = lib.hm_load_fasta(path, threads, bytes_buf, len(raw) + 1, off_buf, len(off_buf))
+            assert n == len(want), (threads, raw[:80])
+            got = [bytes(bytes_buf[off_buf[k]:off_buf[k + 1]]) for k in range(n)]
+            assert got == want, (threads, raw[:80])
+    assert lib.hm_load_fasta(b"/nonexistent/file.fa", 2, None, 0, None, 0) == -1

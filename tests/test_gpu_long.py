@@ -80,6 +80,21 @@ def test_config4_ops_equal_checkpointed_oracle(eng):
         assert ops[0] == a.ops
 
 
+def test_config4_checkpointed_walk_equals_stored_record_walk(eng):
+    """The 100 kb pair again through checkpointed recomputation (score pass with kept rows + 13 re-filled band groups of 64 MB): the same
+    record and the same 101 138 ops as the walk over the full 5 GB record."""
+    p, t = workload.config4(100_000, seed=482)
+    e = pkg.Engine(0)
+    try:
+        for mode in (pkg.LOCAL, pkg.GLOBAL):
+            res, ops = eng.align_batch(mode, [p.tobytes()], [t.tobytes()], 1, -1, -1, want_ops=True)
+            e.set_option(pkg.OPT_CKPT_BYTES, 1 << 30); e.set_option(pkg.OPT_CKPT_GROUP, 400 << 20)
+            res2, ops2 = e.align_batch(mode, [p.tobytes()], [t.tobytes()], 1, -1, -1, want_ops=True)
+            assert res[0] == res2[0] and ops[0] == ops2[0]
+    finally:
+        e.close()
+
+
 def test_config5_shipped_input_all_120_pairs(eng):
     """Every pair of the reference's own input16100000.fasta (tandem repeats: extreme ties), linear and affine, against the oracle."""
     seqs = [x for _, x in workload.config5_shipped()]

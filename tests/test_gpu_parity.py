@@ -458,6 +458,77 @@ def test_multi_run_one_upload_equals_single_runs(eng):
             assert (int(single[mode][0]["score"][k]), single[mode][1][k]) == (a.score, a.ops)
 
 
+def test_fifth_pattern_symbol_only_moves_the_pairs_that_hold_it(eng):
+    """0.1 % 'N' in the patterns (14 % of the 150-mers hold one): only the pair-pairs with an 'N' go to the int32 family, the rest stay
+    on the s16x2 path (no whole-segment fallback), and every sampled pair equals the oracle in both modes."""
+    n = 40000
+    pat, po, txt, to = workload.config2(n, seed=21, n_rate=0.001)
+    P, T = pat.reshape(n, -1), txt.reshape(n, -1)
+    has_n = (P == ord("N")).any(axis=1)
+    assert 0.10 < has_n.mean() < 0.18
+    for mode in (pkg.GLOBAL, pkg.LOCAL):
+        res = eng.align_packed(mode, pat, po, txt, to, 1, -1, -1, want_ops=True)
+        words, off = eng.copy_ops(n)
+        wide = res["path"] == 2
+        assert np.all(wide[has_n]), "a pair holding an N must not be served by the 4-symbol tables"
+        assert wide.mean() < 2.1 * has_n.mean() + 0.01, "only the pair-pairs with an N (two pairs each) may leave the s16x2 path"
+        ks = list(np.flatnonzero(has_n)[:150]) + list(np.flatnonzero(~has_n)[:150]) + list(np.flatnonzero(wide & ~has_n)[:50])
+        for k in ks:
+            a = ob.align(mode, P[k].tobytes(), T[k].tobytes(), 1, -1, -1)
+            got = (int(res["score"][k]), int(res["end_i"][k]), int(res["end_j"][k]), int(res["start_i"][k]), int(res["start_j"][k]),
+                   int(res["overlap"][k]), pkg.unpack_ops(words, off, k, res["n_ops"][k]))
+            assert got == (a.score, a.end_i, a.end_j, a.start_i, a.start_j, a.overlap, a.ops), (mode, k)
+    # a text-only fifth symbol needs no fallback at all: its table entry is all-mismatch
+    txt2 = txt.copy(); txt2[::997] = ord("N")
+    res = eng.align_packed(pkg.GLOBAL, workload.config2(n, seed=21)[0], po, txt2, to, 1, -1, -1)
+    assert np.all(res["path"] == 1)
+
+
+def test_checkpointed_traceback_equals_oracle(eng):
+    """Long pairs walked from checkpoint rows (B2A_OPT_CKPT_BYTES = 0 forces every wide32 pair onto that path, a tiny group size forces
+    many re-filled band groups): records and op lists equal the oracle -- random, tandem-repeat (ties), general-alphabet pairs, both modes,
+    hw2's and hw4's tie order, mixed with short pairs in one batch."""
+    rng = random.Random(2024)
+    e = pkg.Engine(0)
+    try:
+        e.set_option(pkg.OPT_CKPT_BYTES, 0)
+        for group_bytes in (1, 600_000, 1 << 30):
+            e.set_option(pkg.OPT_CKPT_GROUP, group_bytes)
+            ps, ts = [], []
+            for _ in range(6):
+                t = rnd(rng, rng.randint(600, 3000))
+                ps.append(mutate(rng, t)[:rng.randint(513, 2500)] or b"A"); ts.append(t)
+            u = rnd(rng, 3)
+            ps += [(u * 400)[:900], rnd(rng, 700, b"ACGTNXY"), rnd(rng, 40), b"ACGT" * 150]
+            ts += [(u * 500)[:1300], rnd(rng, 1500, b"ACGTNXY"), rnd(rng, 300), b"TTTT" * 200]
+            for mode in (pkg.GLOBAL, pkg.LOCAL):
+                for s3 in ((1, -1, -1), (2, -3, -4), (5, -4, -16)):
+                    res, ops = check_batch(e, mode, ps, ts, s3)
+                    assert int(res["path"][0]) == 2
+            res, ops = e.align_batch(pkg.GLOBAL, ps, ts, 1, -1, -1, want_ops=True, tie_hw4=True)
+            for k in range(len(ps)):
+                score, dist, wops = ob.hw4_nw(ps[k], ts[k], 1, -1, -1)
+                assert (int(res["score"][k]), int(res["overlap"][k]), ops[k]) == (score, dist, wops), k
+    finally:
+        e.close()
+
+
+def test_record_that_cannot_fit_is_an_error_not_a_crash(eng):
+    """With checkpointing switched off, a pair whose 0.5 byte/cell record exceeds the device memory fails with B2A_ERR_NOMEM."""
+    e = pkg.Engine(0)
+    try:
+        e.set_option(pkg.OPT_CKPT_BYTES, 1 << 62)
+        p = np.full(800_000, ord("A"), dtype=np.uint8); t = np.full(800_000, ord("C"), dtype=np.uint8)
+        off = np.array([0, 800_000], dtype=np.uint64)
+        with pytest.raises(pkg.B2AError) as ei:
+            e.align_packed(pkg.LOCAL, p, off, t, off, 1, -1, -1, want_ops=True)
+        assert "rc=-3" in str(ei.value)
+        res, ops = e.align_batch(pkg.GLOBAL, [b"ACGT"], [b"ACT"], 1, -1, -1)          # the context stays usable
+        assert int(res["score"][0]) == ob.align(pkg.GLOBAL, b"ACGT", b"ACT", 1, -1, -1).score
+    finally:
+        e.close()
+
+
 def test_multi_gpu_cli_equals_one_gpu_file(eng, tmp_path):
     """B2A_ALL_GPUS=1 bin/hw2 (one host thread + context per device, results in one host array, winner's ops fetched from the
     device that owns the pair) writes the file the 1-GPU run writes.  Needs > 1 GPU."""
