@@ -142,8 +142,14 @@ struct b2a_ctx {
                                                   // the fill of segment k+1 (s_fill); end to end 61.8 -> 59.1 ms per 1 M pairs NW+SW
     bool trace = false;                           // B2A_TRACE=1: per-segment timeline of b2a_align_batch on stderr
     uint64_t seg_budget_bytes = 8ull << 30;       // record bytes per segment (B2A_SEG_MB overrides)
-    uint64_t seg_max_pairs = 98304;               // pairs per segment of b2a_align_batch (B2A_SEG_PAIRS overrides; swept in scripts/seg_e2e_sweep.py)
-    uint64_t seg_first_pairs = 1ull << 14;        // its first segment (then doubling): the kernels start after a short copy
+    // Segments of b2a_align_batch.  Large batches: 16 k pairs, then doubling up to 96 k (the kernels start after a short copy; swept in
+    // scripts/seg_e2e_sweep.py).  Small batches (< 8 maximal segments, e.g. a 1 M batch strong-scaled over 8 GPUs, where the copy takes as
+    // long as the kernels): ~8 equal segments of whole WAVES of the short16 fill grid (sm_count x 6 CTAs x 4 warps x 2 pairs = 7104 pairs on
+    // a B200; a segment of 2.3 waves costs 3), so that only the last segment's kernels are not hidden behind a copy.
+    uint64_t seg_wave_pairs = 7104;               // set from the device in b2a_create
+    uint64_t seg_max_pairs = 98304;               // B2A_SEG_PAIRS / B2A_OPT_SEG_PAIRS override
+    uint64_t seg_first_pairs = 1ull << 14;        // B2A_SEG_FIRST / B2A_OPT_SEG_FIRST override
+    bool seg_user = false;                        // the caller set the schedule: take it literally
     uint64_t seg_resident_pairs = 1ull << 20;     // pairs per segment of b2a_batch_upload / b2a_batch_run ...
     uint64_t seg_resident_bytes = 60ull << 30;    // ... and its record bytes (a 1 M-pair batch with 4-bit deltas would need 110 GB)
     // s_fill runs the fill kernels back to back; s_tb (higher priority) runs the tracebacks, so the
@@ -915,8 +921,10 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
         // ---- pass 1: validate, find the end of the segment, per-pair op offsets ----
         uint64_t k = first, seg_bytes = 0;
         const size_t si_next = ctx->segs.size();
-        const uint64_t lim_pairs = !pipelined ? ctx->seg_resident_pairs
-                                 : std::min<uint64_t>(ctx->seg_max_pairs, si_next < 20 ? ctx->seg_first_pairs << si_next : ctx->seg_max_pairs);
+        uint64_t lim_pairs = !pipelined ? ctx->seg_resident_pairs
+                           : std::min<uint64_t>(ctx->seg_max_pairs, si_next < 20 ? ctx->seg_first_pairs << si_next : ctx->seg_max_pairs);
+        if (pipelined && !ctx->seg_user && n_pairs < 8 * ctx->seg_max_pairs)       // small batch: ~8 equal segments of whole waves
+            lim_pairs = std::max<uint64_t>(2 * ctx->seg_wave_pairs, (n_pairs / 8) / ctx->seg_wave_pairs * ctx->seg_wave_pairs);
         const uint64_t lim_bytes = pipelined ? ctx->seg_budget_bytes : ctx->seg_resident_bytes;
         uint64_t plan_key = ~0ull; bool plan_ok = false; Short16Plan pl{0, 0, 0}; uint64_t pair_bytes = 0;
         for (; k < n_pairs; ++k) {
@@ -1191,8 +1199,9 @@ b2a_ctx* b2a_create(int device) {
     if (const char* e = std::getenv("B2A_TRACE")) ctx->trace = std::atoi(e) != 0;
     if (const char* e = std::getenv("B2A_LANES")) ctx->n_lanes = std::max(1, std::min(MAX_LANES, std::atoi(e)));
     if (const char* e = std::getenv("B2A_SEG_MB")) ctx->seg_budget_bytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;
-    if (const char* e = std::getenv("B2A_SEG_PAIRS")) ctx->seg_max_pairs = ctx->seg_resident_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, std::strtoull(e, nullptr, 10));
-    if (const char* e = std::getenv("B2A_SEG_FIRST")) ctx->seg_first_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, std::strtoull(e, nullptr, 10));
+    ctx->seg_wave_pairs = (uint64_t)ctx->sm_count * FILL_MIN_CTAS * FILL_WARPS * 2;
+    if (const char* e = std::getenv("B2A_SEG_PAIRS")) { ctx->seg_max_pairs = ctx->seg_resident_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, std::strtoull(e, nullptr, 10)); ctx->seg_user = true; }
+    if (const char* e = std::getenv("B2A_SEG_FIRST")) { ctx->seg_first_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, std::strtoull(e, nullptr, 10)); ctx->seg_user = true; }
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // numerically lower = higher priority
     bool ok = cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) == cudaSuccess &&
@@ -1448,8 +1457,8 @@ int b2a_set_option(b2a_ctx* ctx, int option, int64_t value)
     if (!ctx) return B2A_ERR_ARG;
     switch (option) {
         case B2A_OPT_LANES:      if (value < 1 || value > MAX_LANES) break; ctx->n_lanes = (int)value; return B2A_OK;
-        case B2A_OPT_SEG_PAIRS:  if (value < 1) break; ctx->seg_max_pairs = ctx->seg_resident_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, (uint64_t)value); return B2A_OK;
-        case B2A_OPT_SEG_FIRST:  if (value < 1) break; ctx->seg_first_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, (uint64_t)value); return B2A_OK;
+        case B2A_OPT_SEG_PAIRS:  if (value < 1) break; ctx->seg_max_pairs = ctx->seg_resident_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, (uint64_t)value); ctx->seg_user = true; return B2A_OK;
+        case B2A_OPT_SEG_FIRST:  if (value < 1) break; ctx->seg_first_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, (uint64_t)value); ctx->seg_user = true; return B2A_OK;
         case B2A_OPT_SEG_BYTES:  if (value < 1) break; ctx->seg_budget_bytes = (uint64_t)value; return B2A_OK;
         case B2A_OPT_TB:         ctx->tb_opt = (int)value; return B2A_OK;
         case B2A_OPT_CKPT_BYTES: if (value < 0) break; ctx->wide_ckpt_bytes = (uint64_t)value; return B2A_OK;

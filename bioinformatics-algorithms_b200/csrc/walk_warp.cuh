@@ -70,6 +70,9 @@ __device__ __forceinline__ void warp_prefetch_window(const PairView& v, const Lo
 
 // Walks from (i, j) until the reference's loop would stop; returns the stop cell in (i, j).  `cur` is the exact-match run that is open
 // at (i, j) (0 at the start of an alignment; a checkpointed walk carries it from one sub-problem to the next).
+// (Measured and dropped in round 2: rounds that decide the cells of THREE neighbouring diagonals per lane, so that a window survives one
+//  indel and continues on the shifted diagonal.  Fewer rounds, but three seeks + three decisions per lane made a round 1.8x as expensive:
+//  the 100 kb pair of config 4 went from 7.0 to 8.0 ms.  A round is bound by its ~110 instructions per lane, not by the load latency.)
 template <class FM, class Loader, bool LOCAL>
 __device__ __forceinline__ void warp_walk(const PairView& v, const Loader& ld, WarpOpsSink& sink, uint32_t& i, uint32_t& j,
                                            uint32_t& nops, int& best, uint32_t& mism, int& cur)
