@@ -269,11 +269,13 @@ void alpha_from_mask(AlphaInfo& a) {
         if (a.mask[b >> 5] & (1u << (b & 31))) { if (a.nsym == 4) { a.too_many = 1; break; } a.sym[a.nsym++] = (uint8_t)b; }
 }
 
+// two launches per class: the 4-symbol kernel for the pair-pairs the segment's table symbols cover, the 8-symbol kernel for the flagged
+// rest (its grid leaves at once when the segment has no fifth pattern symbol)
 template <int R, int K>
 cudaError_t launch_fill_rk(bool local, const FillArgs& a, cudaStream_t st) {
     const unsigned grid = (a.n_pp + FILL_WARPS - 1) / FILL_WARPS;
-    if (local) short16_fill_kernel<R, K, true><<<grid, FILL_WARPS * 32, 0, st>>>(a);
-    else short16_fill_kernel<R, K, false><<<grid, FILL_WARPS * 32, 0, st>>>(a);
+    if (local) { short16_fill_kernel<R, K, true, false><<<grid, FILL_WARPS * 32, 0, st>>>(a); short16_fill_kernel<R, K, true, true><<<grid, FILL_WARPS * 32, 0, st>>>(a); }
+    else { short16_fill_kernel<R, K, false, false><<<grid, FILL_WARPS * 32, 0, st>>>(a); short16_fill_kernel<R, K, false, true><<<grid, FILL_WARPS * 32, 0, st>>>(a); }
     return cudaGetLastError();
 }
 template <int K>
@@ -637,7 +639,7 @@ int launch_segment(b2a_ctx* ctx, size_t si, int r, uint64_t* launches)
         a.alpha = alpha;
         a.dirty = ctx->d_dirty.p + sg.pp_first + c.first;
         CU(launch_fill(ctx->K, c.R, local, a, st));
-        ++*launches;
+        *launches += 2;
     }
     CU(cudaEventRecord(ev[2], st));
     st = ctx->s_tb;
@@ -1104,13 +1106,14 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
         any_dirty |= a.too_many && ctx->segs[si].n_pp;
     }
     if (any_dirty) {
-        // some segment holds a fifth pattern symbol: the pair-pairs dirty_kernel flagged were skipped by the s16x2 kernels; wide32 serves their pairs
+        // some segment holds a fifth pattern symbol: pair-pairs with MORE THAN 7 distinct pattern symbols were skipped by the s16x2 kernels
+        // (the 8-symbol kernel raised their flag to 2); wide32 serves their pairs
         CU(cudaMemcpyAsync(ctx->h_dirty.p, ctx->d_dirty.p, ctx->n_pp_total, cudaMemcpyDeviceToHost, s0));
         CU(cudaStreamSynchronize(s0));
         ctx->d2h += ctx->n_pp_total;
         const size_t before = ctx->wide_pairs.size();
         for (uint64_t q = 0; q < ctx->n_pp_total; ++q)
-            if (ctx->h_dirty.p[q]) {
+            if (ctx->h_dirty.p[q] == 2) {                      // 1 = served by the 8-symbol s16x2 kernel
                 const PPDesc& d = ctx->h_pps.p[q];
                 ctx->wide_pairs.push_back(d.a); if (d.b != d.a) ctx->wide_pairs.push_back(d.b);
             }

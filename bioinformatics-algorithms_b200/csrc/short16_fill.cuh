@@ -25,6 +25,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "b2a_format.h"
 
 namespace b2a {
@@ -49,7 +50,8 @@ struct FillArgs {
     int32_t         match, mismatch, gap, bias;
     uint32_t        radix;      // 2^K, passed at run time so the word update stays an IMAD (FMA pipe)
     const AlphaInfo* alpha;     // device-resident: the (<= 4) table symbols of this segment
-    const uint8_t*  dirty;      // per pair-pair of this launch: 1 = a pattern byte outside the table symbols, skip (wide32 serves it)
+    uint8_t*        dirty;      // per pair-pair of this launch: 0 = the four table symbols cover its patterns (4-symbol kernel), 1 = they do
+                                // not: the 8-symbol kernel (A8) serves it, or raises it to 2 = more than 7 distinct pattern symbols: wide32
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -65,36 +67,48 @@ constexpr int FILL_WARPS = 4;
                                  // SW 25.5 / 26.6 / 26.6 ms -- the kernel waits on the DPX pipe, not on occupancy
 #endif
 
-template <int R, int K, bool LOCAL>
+// A8 = false: the segment's four table symbols, one PRMT per cell pair from the column's score-table words (the common case).
+// A8 = true : the pair-pairs those tables do not cover (FillArgs::dirty == 1, e.g. a read with an 'N').  Every pair gets its own codes:
+//             its (<= 7) distinct pattern bytes are numbered 0..6 in byte order, text bytes the pattern does not hold get code 7.  Equal
+//             symbols have equal codes, so the score is PRMT(T, rowsel ^ colsel) from ONE constant table T = [match, mismatch x 7]:
+//             the selector nibbles of a row XOR those of the column, nibble 0 picks `match`.  One more ALU instruction (the XOR) per cell
+//             pair; the record is the same.  More than 7 pattern symbols: dirty := 2, the pair-pair goes to wide32.
+template <int R, int K, bool LOCAL, bool A8>
 __global__ void __launch_bounds__(FILL_WARPS * 32, (R <= 5 ? FILL_MIN_CTAS : 1))
 short16_fill_kernel(const FillArgs A)
 {
     constexpr int F = Geo<K>::F, CS = Geo<K>::CS;
-    // Per warp a MIRRORED ring of the last 128 text columns' score tables (tableA, tableB): entry x lives in slots
-    // x & 127 and (x & 127) + 128, so a chunk reads CS consecutive slots from one base with immediate offsets and never
-    // wraps.  (The first version kept the whole text's tables, 8 KB per warp: shared memory capped the SM at 24 warps.)
-    __shared__ uint2 s_ring[FILL_WARPS][256];
-    __shared__ uint32_t s_tbl4[256];                     // byte -> 4 int8 scores against sym[0..3]
-
-    const int nsym = A.alpha->nsym;
-    uint8_t sym[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) sym[c] = A.alpha->sym[c];
-    for (int b = threadIdx.x; b < 256; b += blockDim.x) {
-        uint32_t w = 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int sc = ((c < nsym && sym[c] == (uint8_t)b) ? A.match : A.mismatch) - (LOCAL ? 0 : 2 * A.gap);
-            w |= ((uint32_t)sc & 0xFFu) << (8 * c);
-        }
-        s_tbl4[b] = w;
-    }
-    __syncthreads();
+    // Per warp a MIRRORED ring of the last 128 text columns' entries -- score-table words (tableA, tableB), or the column's selector
+    // nibbles (A8) --: entry x lives in slots x & 127 and (x & 127) + 128, so a chunk reads CS consecutive slots from one base with
+    // immediate offsets and never wraps.  (The first version kept the whole text's tables, 8 KB per warp: shared memory capped the SM at 24 warps.)
+    using RingT = typename std::conditional<A8, uint32_t, uint2>::type;
+    __shared__ RingT s_ring[FILL_WARPS][256];
+    __shared__ uint32_t s_tbl4[A8 ? 1 : 256];            // byte -> 4 int8 scores against sym[0..3]
+    __shared__ uint8_t s_code[A8 ? FILL_WARPS : 1][2][A8 ? 256 : 1];   // A8: byte -> code of pair a / pair b
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t pp = blockIdx.x * FILL_WARPS + warp;
-    if (pp >= A.n_pp || A.dirty[pp]) return;             // warp-uniform
-    uint2* ring = s_ring[warp];
+    uint8_t sym[4] = {0, 0, 0, 0};
+    if (A8) {
+        if (!A.alpha->too_many) return;                  // uniform: the segment has no pair-pair outside its four symbols
+        if (pp >= A.n_pp || A.dirty[pp] != 1) return;    // warp-uniform
+    } else {
+        const int nsym = A.alpha->nsym;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sym[c] = A.alpha->sym[c];
+        for (int b = threadIdx.x; b < 256; b += blockDim.x) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int sc = ((c < nsym && sym[c] == (uint8_t)b) ? A.match : A.mismatch) - (LOCAL ? 0 : 2 * A.gap);
+                w |= ((uint32_t)sc & 0xFFu) << (8 * c);
+            }
+            s_tbl4[b] = w;
+        }
+        __syncthreads();
+        if (pp >= A.n_pp || A.dirty[pp]) return;         // warp-uniform
+    }
+    RingT* ring = s_ring[warp];
 
     const PPDesc d = A.pps[pp];
     const uint32_t ma = pp_dim(d.m, 0), mb = pp_dim(d.m, 1), na = pp_dim(d.n, 0), nb = pp_dim(d.n, 1);
@@ -109,9 +123,47 @@ short16_fill_kernel(const FillArgs A)
     // every pattern symbol, whatever bytes the alphabet holds (a NUL pad would MATCH a NUL pattern symbol)
     uint32_t nxa = (uint32_t)lane < na ? ta[lane] : 0x100u, nxb = (uint32_t)lane < nb ? tb[lane] : 0x100u;
     const uint32_t mmw = ((uint32_t)(A.mismatch - (LOCAL ? 0 : 2 * A.gap)) & 0xFFu) * 0x01010101u;
+    // A8: the constant score table, byte 0 = match, bytes 1..7 = mismatch (NW: both minus 2 gap, see above)
+    const uint32_t t8lo = (mmw & 0xFFFFFF00u) | ((uint32_t)(A.match - (LOCAL ? 0 : 2 * A.gap)) & 0xFFu), t8hi = mmw;
+    if (A8) {
+        // codes of both pairs: presence mask of the pattern's bytes (one warp-wide OR per mask word), code = rank among the present bytes
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const uint8_t* ph = h ? pb : pa;
+            const uint32_t mh = h ? mb : ma;
+            uint32_t msk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int r = 0; r < R; ++r) {
+                const uint32_t i0 = (uint32_t)lane * R + r;
+                if (i0 < mh) { const uint32_t x = ph[i0];
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) if ((x >> 5) == (uint32_t)w) msk[w] |= 1u << (x & 31u); }
+            }
+            uint32_t nsym8 = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { msk[w] = __reduce_or_sync(0xFFFFFFFFu, msk[w]); nsym8 += (uint32_t)__popc(msk[w]); }
+            if (nsym8 > 7u) { if (lane == 0) A.dirty[pp] = 2; return; }          // warp-uniform: wide32 serves this pair-pair
+            // lane L fills the codes of bytes 8L .. 8L+7 (all inside mask word L / 4)
+            uint32_t below = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) if (w < (lane >> 2)) below += (uint32_t)__popc(msk[w]);
+            uint32_t mine = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) if (w == (lane >> 2)) mine = msk[w];
+            const uint32_t base = ((uint32_t)lane & 3u) * 8u;
+            for (uint32_t b = 0; b < 8u; ++b) {
+                const uint32_t bit = base + b;
+                const bool present = (mine >> bit) & 1u;
+                s_code[warp][h][lane * 8 + b] = present ? (uint8_t)(below + (uint32_t)__popc(mine & ((1u << bit) - 1u))) : (uint8_t)7;
+            }
+        }
+        __syncwarp();
+    }
+    auto col_code = [&](int h, uint32_t x) -> uint32_t { return (x & 0x100u) ? 7u : (uint32_t)s_code[A8 ? warp : 0][h][A8 ? x : 0]; };
     auto stage_block = [&]() {
         const uint32_t slot = (staged + (uint32_t)lane) & 127u;
-        const uint2 e = make_uint2((nxa & 0x100u) ? mmw : s_tbl4[nxa], (nxb & 0x100u) ? mmw : s_tbl4[nxb]);
+        RingT e;
+        if constexpr (A8) e = col_code(0, nxa) * 0x11u | col_code(1, nxb) * 0x1100u;      // selector nibbles: pair a in 0-1, pair b in 2-3
+        else e = make_uint2((nxa & 0x100u) ? mmw : s_tbl4[nxa], (nxb & 0x100u) ? mmw : s_tbl4[nxb]);
         __syncwarp();
         ring[slot] = e; ring[slot + 128u] = e;
         __syncwarp();
@@ -127,13 +179,19 @@ short16_fill_kernel(const FillArgs A)
     for (int r = 0; r < R; ++r) {
         const uint32_t i0 = (uint32_t)lane * R + r;     // 0-based row
         uint32_t ca = 0, cb = 0;
-        if (i0 < ma) { const uint8_t xa = pa[i0];
+        if (A8) {
+            if (i0 < ma) ca = s_code[A8 ? warp : 0][0][A8 ? pa[i0] : 0];
+            if (i0 < mb) cb = s_code[A8 ? warp : 0][1][A8 ? pb[i0] : 0];
+            sel[r] = ca | ((8u | ca) << 4) | (cb << 8) | ((8u | cb) << 12);     // XORed with the column's nibbles: 0 = equal symbols
+        } else {
+            if (i0 < ma) { const uint8_t xa = pa[i0];
 #pragma unroll
-            for (int c = 1; c < 4; ++c) if (xa == sym[c]) ca = c; }
-        if (i0 < mb) { const uint8_t xb = pb[i0];
+                for (int c = 1; c < 4; ++c) if (xa == sym[c]) ca = c; }
+            if (i0 < mb) { const uint8_t xb = pb[i0];
 #pragma unroll
-            for (int c = 1; c < 4; ++c) if (xb == sym[c]) cb = c; }
-        sel[r] = ca | ((8u | ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
+                for (int c = 1; c < 4; ++c) if (xb == sym[c]) cb = c; }
+            sel[r] = ca | ((8u | ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
+        }
         // LOCAL: H of the column-0 border (0, hw2.cpp:196-197).  NW: S of the frozen border H(i, 0) = i*gap (hw2.cpp:125-130) as
         // seen from this lane's column before step 0, j = -1 - lane: Z - (lane + 1)|gap|; it grows by |gap| per frozen step
         // and reaches Z = 32|gap| at column 0 (every border cell has S = Z).
@@ -161,17 +219,19 @@ short16_fill_kernel(const FillArgs A)
     uint32_t dgn = LOCAL ? 0u : pack2((31 - lane) * -A.gap);             // value the row above had one column to the left (see H[r] above)
 
     // one wavefront step for this lane; ACTIVE_CHECK selects the ramp (predicated) flavour
-    auto step = [&](const uint2* tcol, int k, uint32_t q, uint32_t (&S)[R], int f, bool active) {
+    auto step = [&](const RingT* tcol, int k, uint32_t q, uint32_t (&S)[R], int f, bool active) {
         uint32_t up = __shfl_up_sync(0xFFFFFFFFu, H[R - 1], 1);
         if (lane == 0) up = LOCAL ? 0u : Z;                              // row 0 border, hw2.cpp:131-136 (S = Z) / :196-197
         const uint32_t dg0 = dgn;
         dgn = up;
         if (active) {
-            const uint2 tw = tcol[k];                                   // tables of column j = q - lane (text index j - 1)
+            const RingT tw = tcol[k];                                   // tables / selector nibbles of column j = q - lane (text index j - 1)
             uint32_t dg = dg0, u = up;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const uint32_t s  = prmt(tw.x, tw.y, sel[r]);
+                uint32_t s;
+                if constexpr (A8) s = prmt(t8lo, t8hi, sel[r] ^ tw);
+                else s = prmt(tw.x, tw.y, sel[r]);
                 uint32_t h;
                 if (LOCAL) {
                     const uint32_t ds = __vadd2(dg, s);
@@ -201,7 +261,7 @@ short16_fill_kernel(const FillArgs A)
     for (uint32_t c = 0; c < NC; ++c) {
         const uint32_t q0 = c * CS;
         while (staged < q0 + CS) stage_block();                        // steps q0 .. q0+CS-1 read text indices q0-32 .. q0+CS-2
-        const uint2* tcol = ring + ((q0 - (uint32_t)lane - 1u) & 127u);  // tcol[k] = entry of text index q0 + k - lane - 1
+        const RingT* tcol = ring + ((q0 - (uint32_t)lane - 1u) & 127u);  // tcol[k] = entry of text index q0 + k - lane - 1
         uint32_t w0[R], w1[R];
         if (q0 >= 32u && q0 + CS - 1 <= n) {
             // steady state: every lane is inside its row range for the whole chunk

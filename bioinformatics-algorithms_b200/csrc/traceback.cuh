@@ -43,7 +43,7 @@ struct TbArgs {
     int32_t         opt;
     int32_t         tie_hw4;    // global mode: tie order d > u > l (hw4.cpp:37-46) and overlap := hw4's distance
     const AlphaInfo* alpha;
-    const uint8_t*  dirty;      // per pair-pair: skipped by the s16x2 kernels (served by wide32)
+    const uint8_t*  dirty;      // per pair-pair: 2 = skipped by the s16x2 fill kernels (served by wide32)
 };
 
 struct DevLoader {
@@ -109,7 +109,7 @@ short16_traceback_kernel(const TbArgs A)
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t pp = t >> 1;
     const int half = (int)(t & 1u);
-    if (pp >= A.n_pp || A.dirty[pp]) return;
+    if (pp >= A.n_pp || A.dirty[pp] == 2) return;         // 2: more than 7 pattern symbols, no s16x2 record (wide32 serves the pair-pair)
     const PPDesc d = A.pps[pp];
     if (half && d.b == d.a) return;                       // singleton: the high half is a duplicate
     const uint32_t pair = half ? d.b : d.a;

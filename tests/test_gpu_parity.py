@@ -235,7 +235,10 @@ def test_wide_general_alphabet_and_odd_scores_vs_oracle(eng):
         ps.append((mutate(rng, t, alpha=prot) + rnd(rng, m, prot))[:m]); ts.append(t)
     for s in ((1, -1, -1), (100, -100, -200), (1, -1, 1), (-1, -2, -1), (7, 9, -2), (300, -200, -5000), (0, 0, 0)):
         for mode in (pkg.GLOBAL, pkg.LOCAL):
-            check_batch(eng, mode, ps, ts, s, expect_path=2)
+            res, _ = check_batch(eng, mode, ps, ts, s)
+            for k, p in enumerate(ps):                       # > 7 distinct pattern symbols cannot use the 8-symbol s16x2 kernel
+                if len(set(p)) > 7:
+                    assert int(res["path"][k]) == 2
 
 
 def test_mixed_batch_short_and_wide(eng):
@@ -458,28 +461,42 @@ def test_multi_run_one_upload_equals_single_runs(eng):
             assert (int(single[mode][0]["score"][k]), single[mode][1][k]) == (a.score, a.ops)
 
 
-def test_fifth_pattern_symbol_only_moves_the_pairs_that_hold_it(eng):
-    """0.1 % 'N' in the patterns (14 % of the 150-mers hold one): only the pair-pairs with an 'N' go to the int32 family, the rest stay
-    on the s16x2 path (no whole-segment fallback), and every sampled pair equals the oracle in both modes."""
+def test_fifth_pattern_symbol_stays_on_the_s16x2_path(eng):
+    """0.1 % 'N' in the patterns (14 % of the 150-mers hold one): the pair-pairs with an 'N' are served by the 8-symbol s16x2 kernel (per-pair
+    codes, XOR-selected score), nothing falls back to the int32 family, and every sampled pair equals the oracle in both modes.  Pairs whose
+    pattern holds MORE than 7 distinct symbols (and only those pair-pairs) go to wide32."""
     n = 40000
     pat, po, txt, to = workload.config2(n, seed=21, n_rate=0.001)
-    P, T = pat.reshape(n, -1), txt.reshape(n, -1)
+    P, T = pat.reshape(n, -1).copy(), txt.reshape(n, -1)
+    many = np.arange(5, n, 4001)                                   # ten patterns over a 9-letter alphabet
+    rng = np.random.default_rng(3)
+    for k in many:
+        P[k] = np.frombuffer(b"ACGTNRYKM", dtype=np.uint8)[rng.integers(0, 9, size=P.shape[1])]
+    pat = np.ascontiguousarray(P.reshape(-1))
     has_n = (P == ord("N")).any(axis=1)
     assert 0.10 < has_n.mean() < 0.18
     for mode in (pkg.GLOBAL, pkg.LOCAL):
         res = eng.align_packed(mode, pat, po, txt, to, 1, -1, -1, want_ops=True)
         words, off = eng.copy_ops(n)
         wide = res["path"] == 2
-        assert np.all(wide[has_n]), "a pair holding an N must not be served by the 4-symbol tables"
-        assert wide.mean() < 2.1 * has_n.mean() + 0.01, "only the pair-pairs with an N (two pairs each) may leave the s16x2 path"
-        ks = list(np.flatnonzero(has_n)[:150]) + list(np.flatnonzero(~has_n)[:150]) + list(np.flatnonzero(wide & ~has_n)[:50])
+        assert np.all(wide[many]) and wide.sum() <= 2 * len(many), "only the pair-pairs with > 7 pattern symbols may leave the s16x2 path"
+        ks = list(np.flatnonzero(has_n)[:200]) + list(np.flatnonzero(~has_n)[:100]) + list(np.flatnonzero(wide))
         for k in ks:
             a = ob.align(mode, P[k].tobytes(), T[k].tobytes(), 1, -1, -1)
             got = (int(res["score"][k]), int(res["end_i"][k]), int(res["end_j"][k]), int(res["start_i"][k]), int(res["start_j"][k]),
                    int(res["overlap"][k]), pkg.unpack_ops(words, off, k, res["n_ops"][k]))
             assert got == (a.score, a.end_i, a.end_j, a.start_i, a.start_j, a.overlap, a.ops), (mode, k)
-    # a text-only fifth symbol needs no fallback at all: its table entry is all-mismatch
-    txt2 = txt.copy(); txt2[::997] = ord("N")
+    # other scorings (4- and 8-bit deltas) and a text that holds the fifth symbol too (an 'N' under an 'N' is a match, hw2.cpp:142)
+    txt2 = txt.copy(); txt2[::97] = ord("N")
+    T2 = txt2.reshape(n, -1)
+    for s3 in ((2, -3, -4), (5, -4, -16)):
+        for mode in (pkg.GLOBAL, pkg.LOCAL):
+            res = eng.align_packed(mode, pat[:3000 * 150], po[:3001], txt2[:3000 * 1000], to[:3001], *s3, want_ops=True)
+            words, off = eng.copy_ops(3000)
+            for k in list(np.flatnonzero(has_n[:3000])[:40]) + list(range(0, 3000, 301)):
+                a = ob.align(mode, P[k].tobytes(), T2[k].tobytes(), *s3)
+                assert (int(res["score"][k]), int(res["overlap"][k]), pkg.unpack_ops(words, off, k, res["n_ops"][k])) == (a.score, a.overlap, a.ops), (s3, mode, k)
+    # a text-only fifth symbol needs no second kernel at all: its table entry is all-mismatch
     res = eng.align_packed(pkg.GLOBAL, workload.config2(n, seed=21)[0], po, txt2, to, 1, -1, -1)
     assert np.all(res["path"] == 1)
 
