@@ -172,6 +172,7 @@ struct b2a_ctx {
     int tb_opt = 0;                               // walker tuning bits (B2A_TB_OPT overrides, for experiments)
     uint64_t wide_ckpt_bytes = 48ull << 30;       // a wide32 pair whose traceback record would be larger is walked from checkpoints instead
     uint64_t wide_ckpt_group_bytes = 1ull << 30;  // ... re-filling groups of bands whose record fits this
+    uint32_t wide_ckpt_col_shift = 13;            // ... cut into tiles at every 2^13-th column, which the score pass keeps too
     std::vector<Segment> segs;
     std::vector<uint32_t> wide_pairs;             // pairs served by the wide32 family
     uint64_t total_ops_words = 0, n_pp_total = 0;
@@ -345,6 +346,14 @@ cudaError_t launch_wide_fill_k(bool local, bool store, bool alpha4, const WideAr
     if (K != 2) return cudaErrorInvalidValue;                 // score-only kernels exist for K = 2 only
     return local ? launch_wide_fill_a<2, true, false>(alpha4, a, grid, st) : launch_wide_fill_a<2, false, false>(alpha4, a, grid, st);
 }
+// pass 1 of a checkpointed pair: score-only + kept columns
+cudaError_t launch_wide_fill_keepcol(bool local, bool alpha4, const WideArgs& a, unsigned grid, cudaStream_t st) {
+    if (local) { if (alpha4) wide32_fill_kernel<2, true, false, true, true><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
+                 else wide32_fill_kernel<2, true, false, false, true><<<grid, WIDE_WARPS * 32, 0, st>>>(a); }
+    else       { if (alpha4) wide32_fill_kernel<2, false, false, true, true><<<grid, WIDE_WARPS * 32, 0, st>>>(a);
+                 else wide32_fill_kernel<2, false, false, false, true><<<grid, WIDE_WARPS * 32, 0, st>>>(a); }
+    return cudaGetLastError();
+}
 cudaError_t launch_wide_fill(int K, bool local, bool store, bool alpha4, const WideArgs& a, unsigned grid, cudaStream_t st) {
     switch (K) {
         case 2:  return launch_wide_fill_k<2>(local, store, alpha4, a, grid, st);
@@ -390,7 +399,7 @@ int wide_plan(b2a_ctx* ctx, const uint64_t* pat_off, const uint64_t* txt_off, bo
         p.m = (uint32_t)(pat_off[k + 1] - pat_off[k]); p.n = (uint32_t)(txt_off[k + 1] - txt_off[k]);
         p.pair = k;
         p.nbands = (p.m && p.n) ? (p.m + 32u * WIDE_R - 1u) / (32u * WIDE_R) : 0u;
-        p.top_off = WIDE_NO_TOP;
+        p.top_off = WIDE_NO_TOP; p.left_off = WIDE_NO_TOP;
         if (p.nbands >= (1u << 20)) return fail(ctx, B2A_ERR_RANGE, "wide32: pattern too long (band index must fit 20 bits)");
         if (store && (uint64_t)p.nbands * WIDE_R * num_chunks(p.n, CS, wide_skew(W.K)) * 32u * sizeof(Chunk) > ctx->wide_ckpt_bytes) {
             W.ckpt_pairs.push_back(WideState::CkptSpec{k, p.m, p.n, p.pat_off, p.txt_off});   // too large to keep: served one by one from checkpoints
@@ -504,7 +513,11 @@ int wide_ckpt_run(b2a_ctx* ctx, int r, cudaStream_t st, uint64_t* launches)
         const uint32_t G = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nbands, ctx->wide_ckpt_group_bytes / std::max<uint64_t>(band_bytes, 1)));
         const uint32_t ck_stride = (n + 1u + 31u) & ~31u, n_ck = (nbands - 1u) / G;     // kept: the bottom rows of bands G-1, 2G-1, ... that have a band below
         const uint32_t bound_stride = ((n + 64u) + 31u) & ~31u;
-        CU(W.d_ck.reserve(std::max<uint64_t>(1, (uint64_t)n_ck * ck_stride)));
+        // kept columns: every 8192-th, so that pass 2 re-fills tiles of G bands x 8192 columns instead of strips as wide as the path's column
+        const uint32_t col_shift = n > (2u << ctx->wide_ckpt_col_shift) ? ctx->wide_ckpt_col_shift : 0u, n_cc = col_shift ? n >> col_shift : 0u;
+        const uint32_t col_stride = (m + 31u) & ~31u;
+        const uint64_t colck_off = (uint64_t)n_ck * ck_stride;
+        CU(W.d_ck.reserve(std::max<uint64_t>(1, colck_off + (uint64_t)n_cc * col_stride)));
         CU(W.d_rowbest.reserve(std::max<uint64_t>((uint64_t)nbands * band_rows, 1)));
         CU(W.d_tasks.reserve(nbands));
         CU(W.d_codes.reserve((uint64_t)G * band_bytes / sizeof(Chunk)));
@@ -525,7 +538,9 @@ int wide_ckpt_run(b2a_ctx* ctx, int r, cudaStream_t st, uint64_t* launches)
             a.radix = K < 32 ? (1u << K) : 0u;
             a.alpha = ctx->d_alpha.p + (ctx->alpha_slots - 1);
             const unsigned need = (unsigned)((p.nbands + WIDE_WARPS - 1) / WIDE_WARPS);
-            CU(launch_wide_fill(store ? K : 2, local, store, W.alpha4, a, std::min<unsigned>(need, (unsigned)ctx->sm_count * 8u), st));
+            const unsigned grid = std::min<unsigned>(need, (unsigned)ctx->sm_count * 8u);
+            if (!store && p.col_shift) CU(launch_wide_fill_keepcol(local, W.alpha4, a, grid, st));
+            else CU(launch_wide_fill(store ? K : 2, local, store, W.alpha4, a, grid, st));
             ++*launches;
             CU(cudaStreamSynchronize(st));                        // &p and the next sub-problem's plan depend on this launch
             return B2A_OK;
@@ -534,7 +549,9 @@ int wide_ckpt_run(b2a_ctx* ctx, int r, cudaStream_t st, uint64_t* launches)
         // ---- pass 1: scores + kept rows ----
         WidePair whole{};
         whole.pat_off = sp.pat_off; whole.txt_off = sp.txt_off; whole.m = m; whole.n = n; whole.pair = k; whole.nbands = nbands;
-        whole.bound_stride = bound_stride; whole.top_off = WIDE_NO_TOP; whole.ck_every = n_ck ? G : 0u; whole.ck_stride = ck_stride;
+        whole.bound_stride = bound_stride; whole.top_off = WIDE_NO_TOP; whole.left_off = WIDE_NO_TOP;
+        whole.ck_every = n_ck ? G : 0u; whole.ck_stride = ck_stride;
+        whole.col_shift = col_shift; whole.colck_off = colck_off; whole.col_stride = col_stride;
         { int rc = fill(whole, false); if (rc != B2A_OK) return rc; }
         CkptWalk wst{};
         wst.i = m; wst.j = n;
@@ -561,11 +578,14 @@ int wide_ckpt_run(b2a_ctx* ctx, int r, cudaStream_t st, uint64_t* launches)
         }
         while (!wst.done) {
             const uint32_t g = (wst.i - 1u) / (G * band_rows), r0 = g * G * band_rows;
+            // local mode, first group: the end column is not known yet -> full width; afterwards the tile right of the last kept column
+            const uint32_t cb = (col_shift && !(local && first)) ? (wst.j - 1u) >> col_shift : 0u, c0 = cb << col_shift;
             WidePair sub{};
-            sub.pat_off = sp.pat_off + r0; sub.txt_off = sp.txt_off; sub.m = wst.i - r0; sub.n = wst.j; sub.pair = k;
+            sub.pat_off = sp.pat_off + r0; sub.txt_off = sp.txt_off + c0; sub.m = wst.i - r0; sub.n = wst.j - c0; sub.pair = k;
             sub.nbands = (sub.m + band_rows - 1u) / band_rows;
-            sub.bound_stride = bound_stride; sub.row_base = r0;
-            sub.top_off = g ? (uint64_t)(g - 1u) * ck_stride : WIDE_NO_TOP;
+            sub.bound_stride = bound_stride; sub.row_base = r0; sub.col_base = c0;
+            sub.top_off = g ? (uint64_t)(g - 1u) * ck_stride + c0 : WIDE_NO_TOP;
+            sub.left_off = cb ? colck_off + (uint64_t)(cb - 1u) * col_stride + r0 : WIDE_NO_TOP;
             { int rc = fill(sub, true); if (rc != B2A_OK) return rc; }
             CU(cudaMemcpyAsync(W.d_walk.p, &wst, sizeof(wst), cudaMemcpyHostToDevice, st));
             CkptWalkArgs wa{};
@@ -582,8 +602,9 @@ int wide_ckpt_run(b2a_ctx* ctx, int r, cudaStream_t st, uint64_t* launches)
             CU(cudaStreamSynchronize(st));
             first = false;
             if (!wst.done && (wst.i == 0 || wst.j == 0)) return fail(ctx, B2A_ERR_STATE, "internal: checkpointed walk left the matrix without finishing");
+            if (!wst.done && wst.i > r0 && wst.j > c0) return fail(ctx, B2A_ERR_STATE, "internal: checkpointed walk stopped inside a tile");
         }
-        ctx->fill_bytes += (uint64_t)n_ck * ck_stride * 4;
+        ctx->fill_bytes += ((uint64_t)n_ck * ck_stride + (uint64_t)n_cc * col_stride) * 4;
     }
     return B2A_OK;
 }
@@ -745,7 +766,7 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
             const AffSpec& sp = specs[k];
             if (sp.m == 0 || sp.n == 0) continue;           // borders only: answered on the host below
             WidePair p{};
-            p.top_off = WIDE_NO_TOP;
+            p.top_off = WIDE_NO_TOP; p.left_off = WIDE_NO_TOP;
             p.pat_off = sp.pat_off; p.txt_off = sp.txt_off; p.m = sp.m; p.n = sp.n; p.pair = (uint32_t)k;
             const uint32_t band_rows = 32u * (uint32_t)(trace ? WIDE_R : AFFINE_R_SCORE);
             p.nbands = (sp.m + band_rows - 1u) / band_rows;
@@ -1466,6 +1487,7 @@ int b2a_set_option(b2a_ctx* ctx, int option, int64_t value)
         case B2A_OPT_TB:         ctx->tb_opt = (int)value; return B2A_OK;
         case B2A_OPT_CKPT_BYTES: if (value < 0) break; ctx->wide_ckpt_bytes = (uint64_t)value; return B2A_OK;
         case B2A_OPT_CKPT_GROUP: if (value < 1) break; ctx->wide_ckpt_group_bytes = (uint64_t)value; return B2A_OK;
+        case B2A_OPT_CKPT_COLS:  if (value < 2 || value > 30) break; ctx->wide_ckpt_col_shift = (uint32_t)value; return B2A_OK;
     }
     return fail(ctx, B2A_ERR_ARG, "b2a_set_option: unknown option or bad value");
 }

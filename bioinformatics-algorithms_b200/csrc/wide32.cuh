@@ -38,6 +38,12 @@ struct WidePair {
     uint64_t top_off;               // index into WideArgs::ck of the stored row above row 1 (entries 0..n); ~0 = the real border row 0
     uint64_t ck_off;                // where this launch keeps checkpoint rows: ck[ck_off + (g * ck_stride) + j] = H((g + 1) ck_every bands, j)
     uint32_t ck_every, ck_stride;   // keep the bottom row of every ck_every-th band (0 = none); entries per kept row
+    // a sub-problem may also start at a kept COLUMN: columns col_base+1 .. col_base+n of a longer text
+    uint32_t col_base;              // columns left of the sub-problem (0 for a whole pair): the top border is H(0, j) = (col_base + j) gap
+    uint32_t col_shift;             // pass 1 keeps every 2^col_shift-th column (0 = none) ...
+    uint64_t left_off;              // index into WideArgs::ck of the stored column left of column 1 (one entry per row of the sub-problem); ~0 = none
+    uint64_t colck_off;             // ... at ck[colck_off + (j / 2^col_shift - 1) * col_stride + row]
+    uint32_t col_stride, pad;
 };
 constexpr uint64_t WIDE_NO_TOP = ~0ull;
 struct WideTask { uint32_t wp, band; };
@@ -103,7 +109,9 @@ __device__ __forceinline__ uint32_t prmt32(uint32_t a, uint32_t b, uint32_t sel)
 // C = 1 for every launch that writes a record (the lanes follow each other one column apart); C = 4 for the score-only launches, where
 // many pairs are in flight and the tile's shorter instruction stream per cell pays (config 5 linear: 3684 -> 4001 GCUPS).  For ONE long
 // pair C = 4 is slower (measured, see b2a_format.h wide_skew).
-template <int K, bool LOCAL, bool STORE, bool ALPHA4>
+// KEEPCOL: pass 1 of a checkpointed pair, which also keeps every 2^col_shift-th column (a test in the innermost loop: 4 % on the 120-pair
+// score-only launch when it was a run-time flag, so only that pass instantiates it).
+template <int K, bool LOCAL, bool STORE, bool ALPHA4, bool KEEPCOL = false>
 __global__ void __launch_bounds__(WIDE_WARPS * 32)
 wide32_fill_kernel(const WideArgs A)
 {
@@ -170,6 +178,7 @@ wide32_fill_kernel(const WideArgs A)
                 pc[r] = c | ((8u | c) << 4) | ((8u | c) << 8) | ((8u | c) << 12);
             } else pc[r] = i0 < m ? (uint32_t)pp[i0] : 0xFFFFFFFFu;         // junk rows never match
             H[r] = LOCAL ? 0 : (int32_t)(wp.row_base + i0 + 1) * gap;        // hw2.cpp:125-130
+            if (wp.left_off != WIDE_NO_TOP && i0 < m) H[r] = A.ck[wp.left_off + i0];   // sub-problem at a kept column: the stored H(i, col_base)
             best[r] = 0;
         }
         const uint64_t* bin = A.bound + wp.bound_off + (uint64_t)((band + 1u) & 1u) * wp.bound_stride;
@@ -180,8 +189,11 @@ wide32_fill_kernel(const WideArgs A)
         const uint32_t nblk = (n + 31u * C + 1u + 31u) / 32u;                // lane 31 reaches column n at step n + 31 C
         const uint32_t NC = num_chunks(n, CS, C);
         Chunk* rec = A.codes + wp.code_off;
-        const int32_t top0 = LOCAL ? 0 : (int32_t)(wp.row_base + band * 32u * R) * gap;    // H(top row, 0)
         const int32_t* top = wp.top_off != WIDE_NO_TOP ? A.ck + wp.top_off : nullptr;      // band 0 of a sub-problem reads the row above it
+        // H(row above the band, column 0 of the (sub-)problem): a border cell, or a kept value when the sub-problem starts inside the matrix
+        int32_t top0 = LOCAL ? 0 : (int32_t)(wp.row_base + band * 32u * R + wp.col_base) * gap;   // row_base or col_base is 0 whenever this formula is used
+        if (band == 0) { if (top) top0 = top[0]; }
+        else if (wp.left_off != WIDE_NO_TOP) top0 = A.ck[wp.left_off + band * 32u * R - 1u];
         int32_t dgn = top0;                                                  // bottom row of the lane above, one column left of the tile
         int32_t outv[C];                                                     // this lane's bottom row at the C columns of its last tile
 #pragma unroll
@@ -205,7 +217,7 @@ wide32_fill_kernel(const WideArgs A)
             const uint32_t jcol = q0 + (uint32_t)lane;
             if (band == 0) {
                 if (top) bnd = (jcol >= 1 && jcol <= n) ? top[jcol] : top0;
-                else bnd = LOCAL ? 0 : (int32_t)jcol * gap;                  // hw2.cpp:131-136
+                else bnd = LOCAL ? 0 : (int32_t)(wp.col_base + jcol) * gap;  // hw2.cpp:131-136
             } else {
                 const bool need = jcol >= 1 && jcol <= n;
                 const int32_t got = (int32_t)bound_wait(bin + jcol, nx, tag_in, need);
@@ -261,6 +273,14 @@ wide32_fill_kernel(const WideArgs A)
                     }
                     outv[c] = H[R - 1];
                     if (lane == 31) outb[(qm + (uint32_t)c) & 31u] = H[R - 1];   // bottom row of the band (published per block)
+                    if (KEEPCOL) {                                               // pass 1 of a checkpointed pair: keep every 2^col_shift-th column
+                        const uint32_t jc = j0 + (uint32_t)c;
+                        if ((jc & ((1u << wp.col_shift) - 1u)) == 0u && jc - 1u < n) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r)
+                                if (row0 + r < m) A.ck[wp.colck_off + (uint64_t)((jc >> wp.col_shift) - 1u) * wp.col_stride + row0 + r] = H[r];
+                        }
+                    }
                     // what the step contributes to the delta word's Horner sum: start it (S = H), S = S * 2^K + H, or nothing (last step)
                     constexpr bool first_of_word = (POS == 0 || POS == 3);
                     constexpr bool last_of_word = (POS == 2 || POS == 3);
@@ -479,32 +499,34 @@ __global__ void __launch_bounds__(32) wide32_ckpt_walk_kernel(const CkptWalkArgs
     PairView v{rec, A.rowbest + wp.rowbest_off, A.pat + wp.pat_off, A.txt + wp.txt_off,
                wp.m, wp.n, num_chunks(wp.n, FM::CS, FM::SKEW), WIDE_R, 0, A.match, A.mismatch, A.gap, 0, A.opt, 0};
     v.top = wp.top_off != WIDE_NO_TOP ? A.ck + wp.top_off : nullptr;
+    if (!LOCAL && !v.top) v.bias = (int)wp.col_base * A.gap;        // the real border row 0, seen from column col_base: H(0, j) = (col_base + j) gap
     const WideLoader ld{rec};
     WarpOpsSink sink(A.ops, lane == 0);
     sink.word = s.word; sink.fill = s.fill; sink.pos = s.pos;
-    uint32_t i = s.i - wp.row_base, j = s.j;                     // the sub-problem's own row index
+    uint32_t i = s.i - wp.row_base, j = s.j - wp.col_base;       // the sub-problem's own row / column index
     int best = s.best, cur = s.cur;
     bool walk = true;
     if (LOCAL && A.first) {
         int M; uint32_t bi, bj;
         warp_find_local_end<FM>(v, ld, M, bi, bj);                // rows above this sub-problem hold no earlier maximum: the first pass chose row s.i
-        s.score = M; s.end_i = wp.row_base + bi; s.end_j = bj;
+        s.score = M; s.end_i = wp.row_base + bi; s.end_j = wp.col_base + bj;
         i = bi; j = bj;
         if (M == 0) { s.end_i = s.end_j = 0; i = 0; j = 0; walk = false; s.done = 1; }
     }
     if (walk) {
         warp_walk<FM, WideLoader, LOCAL>(v, ld, sink, i, j, s.nops, best, s.mism, cur);
         if (LOCAL) {
-            // stopped inside the sub-problem (H == 0), at the left edge, or at the real top border: the alignment is complete (hw2.cpp:239)
-            if ((i > 0 && j > 0) || j == 0 || wp.row_base == 0) s.done = 1;
-        } else if (j == 0) {
+            // stopped inside the sub-problem (H == 0), or at the real left / top border: the alignment is complete (hw2.cpp:239)
+            if ((i > 0 && j > 0) || (j == 0 && wp.col_base == 0) || (i == 0 && wp.row_base == 0)) s.done = 1;
+        } else if (j == 0 && wp.col_base == 0) {
             const uint32_t up = wp.row_base + i;                 // column 0 holds 'u' all the way up (hw2.cpp:128)
             sink.put_run(OP_D, up); s.nops += up; i = 0; s.done = 2;
         } else if (i == 0 && wp.row_base == 0) {
-            sink.put_run(OP_I, j); s.nops += j; j = 0; s.done = 1;   // row 0 holds 'l' (hw2.cpp:134)
+            const uint32_t lf = wp.col_base + j;                 // row 0 holds 'l' all the way left (hw2.cpp:134)
+            sink.put_run(OP_I, lf); s.nops += lf; j = 0; s.done = 3;
         }
     }
-    s.i = s.done == 2 ? 0u : wp.row_base + i; s.j = j; s.best = best; s.cur = cur;
+    s.i = s.done == 2 ? 0u : wp.row_base + i; s.j = s.done == 3 ? 0u : wp.col_base + j; s.best = best; s.cur = cur;
     s.word = sink.word; s.fill = sink.fill; s.pos = sink.pos;
     if (s.done) {
         sink.flush();

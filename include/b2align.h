@@ -174,6 +174,7 @@ int b2a_affine_star_scores(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_
 #define B2A_OPT_CKPT_BYTES 6   /* a long pair whose traceback record (0.5 byte per cell) would exceed this many bytes is walked from
                                   checkpoint rows instead (score pass + band groups re-filled bottom-up): default 48 GB              */
 #define B2A_OPT_CKPT_GROUP 7   /* ... and this is the record size of one re-filled band group: default 1 GB                         */
+#define B2A_OPT_CKPT_COLS  8   /* ... which is cut into tiles at every 2^value-th column (kept by the score pass too): default 13    */
 int b2a_set_option(b2a_ctx* ctx, int option, int64_t value);
 
 /* ---- result formatting: prepareCigarString hw2.cpp:59-78, prepareMDZString hw2.cpp:80-116 --- */

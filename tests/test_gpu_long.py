@@ -81,14 +81,14 @@ def test_config4_ops_equal_checkpointed_oracle(eng):
 
 
 def test_config4_checkpointed_walk_equals_stored_record_walk(eng):
-    """The 100 kb pair again through checkpointed recomputation (score pass with kept rows + 13 re-filled band groups of 64 MB): the same
-    record and the same 101 138 ops as the walk over the full 5 GB record."""
+    """The 100 kb pair again through checkpointed recomputation (score pass that keeps every 16th band's bottom row and every 8192-th column,
+    then 2048 x 8192 tiles re-filled along the path): the same record and the same 101 138 ops as the walk over the full 5 GB record."""
     p, t = workload.config4(100_000, seed=482)
     e = pkg.Engine(0)
     try:
         for mode in (pkg.LOCAL, pkg.GLOBAL):
             res, ops = eng.align_batch(mode, [p.tobytes()], [t.tobytes()], 1, -1, -1, want_ops=True)
-            e.set_option(pkg.OPT_CKPT_BYTES, 1 << 30); e.set_option(pkg.OPT_CKPT_GROUP, 400 << 20)
+            e.set_option(pkg.OPT_CKPT_BYTES, 1 << 30); e.set_option(pkg.OPT_CKPT_GROUP, 100 << 20)       # groups of 16 bands, tiles of 8192 columns
             res2, ops2 = e.align_batch(mode, [p.tobytes()], [t.tobytes()], 1, -1, -1, want_ops=True)
             assert res[0] == res2[0] and ops[0] == ops2[0]
     finally:

@@ -509,8 +509,8 @@ def test_checkpointed_traceback_equals_oracle(eng):
     e = pkg.Engine(0)
     try:
         e.set_option(pkg.OPT_CKPT_BYTES, 0)
-        for group_bytes in (1, 600_000, 1 << 30):
-            e.set_option(pkg.OPT_CKPT_GROUP, group_bytes)
+        for group_bytes, col_shift in ((1, 13), (600_000, 5), (1, 7), (1 << 30, 6)):      # strips of one band, tiles of 32 / 128 / 64 columns
+            e.set_option(pkg.OPT_CKPT_GROUP, group_bytes); e.set_option(pkg.OPT_CKPT_COLS, col_shift)
             ps, ts = [], []
             for _ in range(6):
                 t = rnd(rng, rng.randint(600, 3000))
