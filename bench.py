@@ -255,7 +255,15 @@ def pinned_copy(pkg, arr):
 
 
 def shm_path(tag):
-    return f"/dev/shm/b2a_bench_{os.environ.get('MASTER_PORT', '0')}_{tag}"
+    """files all ranks of the box map: POSIX shared memory when it has room (1.2 GB of sequences + 64 MB of records), else the temp dir"""
+    base = "/dev/shm"
+    try:
+        import shutil
+        if shutil.disk_usage(base).free < (3 << 30):
+            base = tempfile.gettempdir()
+    except OSError:
+        base = tempfile.gettempdir()
+    return os.path.join(base, f"b2a_bench_{os.environ.get('MASTER_PORT', '0')}_{tag}")
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -448,7 +456,7 @@ def bench_c2(args):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         traffic, traffic_src = None, None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_fill_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_fill_traffic.json")))
             per_pair = sum(tr[m]["dram_read_bytes"] + tr[m]["dram_write_bytes"] for m in ("global", "local")) / 2.0 / tr["pairs_per_launch"]
             traffic, traffic_src = per_pair * n_pairs, tr["source"]
         except Exception:
