@@ -308,7 +308,7 @@ def bench_c2(args):
     from __graft_entry__ import load_package
     pkg = load_package()
     from bioinformatics_algorithms_b200 import workload
-    from bioinformatics_algorithms_b200.sharding import max_over_ranks, sum_over_ranks, pair_range, merge_best
+    from bioinformatics_algorithms_b200.sharding import max_over_ranks, sum_over_ranks, pair_range, merge_best, first_strict_max
     dev = Dist()
     rank, world, local_rank = dev.rank, dev.world, dev.local_rank
     n_pairs = args.pairs
@@ -400,13 +400,7 @@ def bench_c2(args):
                 cand[rank, k] = (key, first + b if b >= 0 else -1)
             dev.barrier()                                        # every rank's records are in the one host array, every candidate is posted
             if rank == 0:
-                s_winners = []
-                for k in range(2):
-                    best_key, best_idx = -1000000, -1
-                    for r in range(world):
-                        if int(cand[r, k, 1]) >= 0 and int(cand[r, k, 0]) > best_key:
-                            best_key, best_idx = int(cand[r, k, 0]), int(cand[r, k, 1])
-                    s_winners.append(best_idx)
+                s_winners = [first_strict_max(cand[:, k, :]) for k in range(2)]
 
         for _ in range(max(1, min(args.warmup, 2))):
             strong_step()

@@ -23,7 +23,7 @@ HW4_BIN = os.path.join(HERE, "bin", "hw4")
 GLOBAL, LOCAL = 0, 1
 SCORE_ONLY = 2
 TIE_HW4 = 4
-OPT_LANES, OPT_SEG_PAIRS, OPT_SEG_BYTES, OPT_TB, OPT_SEG_FIRST, OPT_CKPT_BYTES, OPT_CKPT_GROUP, OPT_CKPT_COLS = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_LANES, OPT_SEG_PAIRS, OPT_SEG_BYTES, OPT_SEG_FIRST, OPT_CKPT_BYTES, OPT_CKPT_GROUP, OPT_CKPT_COLS = 1, 2, 3, 5, 6, 7, 8
 WANT_OPS = 1
 
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<u4"), ("end_j", "<u4"), ("start_i", "<u4"),

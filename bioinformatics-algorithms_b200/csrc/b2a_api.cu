@@ -74,10 +74,11 @@ struct Segment {
     std::vector<ClassRange> classes;
 };
 
-struct Lane {                                     // one DP record, reused by every n_lanes-th segment
+struct Lane {                                     // one DP record, reused by every n_lanes-th (segment, run) launch
     DevBuf<Chunk> codes;
     DevBuf<uint32_t> rowbest;
     cudaEvent_t tb_done = nullptr;                // last traceback that read this record
+    cudaStream_t s_tb = nullptr;                  // the lane's traceback stream (high priority): tracebacks of different lanes run concurrently
 };
 
 // host-side state of the wide32 family for the current batch
@@ -129,7 +130,7 @@ struct RunBuf {
     void release() { d_results.release(); d_ops.release(); d_endcell.release(); }
 };
 
-constexpr int MAX_LANES = 2;
+constexpr int MAX_LANES = 8;
 constexpr int MAX_RUNS = B2A_MAX_RUNS;
 constexpr uint64_t SEG_MIN_PAIRS = 2048;          // a segment is never closed below this many pairs
 
@@ -138,14 +139,14 @@ constexpr uint64_t SEG_MIN_PAIRS = 2048;          // a segment is never closed b
 struct b2a_ctx {
     int device = 0;
     int sm_count = 0;
-    int n_lanes = 2;                              // DP records the segments alternate over: the traceback of segment k (s_tb) then overlaps
+    int lanes_cfg = 0;                            // B2A_OPT_LANES / B2A_LANES: 0 = automatic (2, or 8 for small batches, see batch_prepare)
+    int n_lanes = 2;                              // DP records the launches alternate over: the traceback of one launch (its lane's s_tb) overlaps
                                                   // the fill of segment k+1 (s_fill); end to end 61.8 -> 59.1 ms per 1 M pairs NW+SW
     bool trace = false;                           // B2A_TRACE=1: per-segment timeline of b2a_align_batch on stderr
     uint64_t seg_budget_bytes = 8ull << 30;       // record bytes per segment (B2A_SEG_MB overrides)
-    // Segments of b2a_align_batch.  Large batches: 16 k pairs, then doubling up to 96 k (the kernels start after a short copy; swept in
-    // scripts/seg_e2e_sweep.py).  Small batches (< 8 maximal segments, e.g. a 1 M batch strong-scaled over 8 GPUs, where the copy takes as
-    // long as the kernels): ~8 equal segments of whole WAVES of the short16 fill grid (sm_count x 6 CTAs x 4 warps x 2 pairs = 7104 pairs on
-    // a B200; a segment of 2.3 waves costs 3), so that only the last segment's kernels are not hidden behind a copy.
+    // Segments of b2a_align_batch.  16 k pairs, then doubling up to 96 k (the kernels start after a short copy; swept in
+    // scripts/seg_e2e_sweep.py: every schedule between 58.3 and 60.0 ms for 1 M pairs).  Small batches (< 2 maximal segments): equal segments
+    // of two whole WAVES of the short16 fill grid (sm_count x 6 CTAs x 4 warps x 2 pairs = 7104 pairs on a B200), see batch_prepare.
     uint64_t seg_wave_pairs = 7104;               // set from the device in b2a_create
     uint64_t seg_max_pairs = 98304;               // B2A_SEG_PAIRS / B2A_OPT_SEG_PAIRS override
     uint64_t seg_first_pairs = 1ull << 14;        // B2A_SEG_FIRST / B2A_OPT_SEG_FIRST override
@@ -154,7 +155,7 @@ struct b2a_ctx {
     uint64_t seg_resident_bytes = 60ull << 30;    // ... and its record bytes (a 1 M-pair batch with 4-bit deltas would need 110 GB)
     // s_fill runs the fill kernels back to back; s_tb (higher priority) runs the tracebacks, so the
     // latency-bound walk of segment k fills the issue slots the ALU-bound fill of segment k+1 leaves idle
-    cudaStream_t s_copy = nullptr, s_down = nullptr, s_fill = nullptr, s_tb = nullptr;
+    cudaStream_t s_copy = nullptr, s_down = nullptr, s_fill = nullptr;
     Lane lanes[MAX_LANES];
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_pool;             // per segment: ready, fill start, fill end, traceback end
@@ -169,7 +170,6 @@ struct b2a_ctx {
     uint64_t n_launched = 0;                      // (segment, run) launches so far: they alternate over the lanes
     uint64_t n_pairs = 0;
     int K = 0;
-    int tb_opt = 0;                               // walker tuning bits (B2A_TB_OPT overrides, for experiments)
     uint64_t wide_ckpt_bytes = 48ull << 30;       // a wide32 pair whose traceback record would be larger is walked from checkpoints instead
     uint64_t wide_ckpt_group_bytes = 1ull << 30;  // ... re-filling groups of bands whose record fits this
     uint32_t wide_ckpt_col_shift = 13;            // ... cut into tiles at every 2^13-th column, which the score pass keeps too
@@ -465,7 +465,7 @@ int wide_traceback(b2a_ctx* ctx, int r, cudaStream_t st, uint64_t* launches, boo
     a.ops = (prm.flags & B2A_WANT_OPS) && !score_only ? ctx->run[r].d_ops.p : nullptr;
     a.ops_off = ctx->d_ops_off.p;
     a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.score_only = score_only ? 1 : 0;
-    a.opt = (ctx->tb_opt & ~4) | ((prm.flags & B2A_TIE_HW4) ? 4 : 0);
+    a.opt = (prm.flags & B2A_TIE_HW4) ? 4 : 0;
     CU(launch_wide_tb(W.K, ctx->run[r].mode == B2A_MODE_LOCAL, a, st));
     ++*launches;
     return B2A_OK;
@@ -637,8 +637,9 @@ int launch_segment(b2a_ctx* ctx, size_t si, int r, uint64_t* launches)
     cudaEvent_t* ev = seg_events(ctx, si, r);
     cudaEvent_t* ev_in = seg_events(ctx, si, 0);
     if (!ev || !ev_in) return fail(ctx, B2A_ERR_CUDA, "cudaEventCreate failed");
-    if (sg.chunks > ln.codes.cap || sg.rowbest_words > ln.rowbest.cap) {
-        CU(cudaStreamSynchronize(ctx->s_fill)); CU(cudaStreamSynchronize(ctx->s_tb));   // the lane's record is about to be reallocated
+    if (sg.chunks > ln.codes.cap || (local && sg.rowbest_words > ln.rowbest.cap)) {     // (rowbest is a local-mode buffer: a lane that only ever
+                                                                                         // serves global runs never grows it)
+        CU(cudaStreamSynchronize(ctx->s_fill)); CU(cudaStreamSynchronize(ln.s_tb));     // the lane's record is about to be reallocated
         CU(ln.codes.reserve(sg.chunks));
         if (local) CU(ln.rowbest.reserve(sg.rowbest_words));
     }
@@ -663,7 +664,7 @@ int launch_segment(b2a_ctx* ctx, size_t si, int r, uint64_t* launches)
         *launches += 2;
     }
     CU(cudaEventRecord(ev[2], st));
-    st = ctx->s_tb;
+    st = ln.s_tb;
     CU(cudaStreamWaitEvent(st, ev[2], 0));
     for (const ClassRange& c : sg.classes) {
         Short16Plan pl{0, 0, 0};
@@ -676,7 +677,7 @@ int launch_segment(b2a_ctx* ctx, size_t si, int r, uint64_t* launches)
         a.results = rb.d_results.p; a.ops = want_ops ? rb.d_ops.p : nullptr; a.ops_off = ctx->d_ops_off.p;
         a.n_pp = c.count; a.R = c.R;
         a.match = prm.match; a.mismatch = prm.mismatch; a.gap = prm.gap; a.bias = pl.bias;
-        a.opt = ctx->tb_opt;
+        a.opt = 0;
         a.tie_hw4 = (prm.flags & B2A_TIE_HW4) ? 1 : 0;
         a.alpha = alpha;
         a.dirty = ctx->d_dirty.p + sg.pp_first + c.first;
@@ -705,7 +706,8 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
 {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->s_copy)); CU(cudaStreamSynchronize(ctx->s_down));
-    CU(cudaStreamSynchronize(ctx->s_fill)); CU(cudaStreamSynchronize(ctx->s_tb));
+    CU(cudaStreamSynchronize(ctx->s_fill));
+    for (auto& ln : ctx->lanes) CU(cudaStreamSynchronize(ln.s_tb));
     ctx->have_batch = false; ctx->ran = false; ctx->affine_ops = false;   // the batch buffers are reused below
     ctx->cells = ctx->fill_bytes = ctx->launches = ctx->h2d = ctx->d2h = 0;
     const int64_t smag = std::max<int64_t>({std::llabs((long long)match), std::llabs((long long)mismatch),
@@ -884,10 +886,20 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
     CU(cudaSetDevice(ctx->device));
     // a previous batch may still own the pinned plan arrays / device buffers
     CU(cudaStreamSynchronize(ctx->s_copy)); CU(cudaStreamSynchronize(ctx->s_down));
-    CU(cudaStreamSynchronize(ctx->s_fill)); CU(cudaStreamSynchronize(ctx->s_tb));
+    CU(cudaStreamSynchronize(ctx->s_fill));
+    for (auto& ln : ctx->lanes) CU(cudaStreamSynchronize(ln.s_tb));
     ctx->have_batch = false; ctx->ran = false; ctx->affine_ops = false;
     ctx->prm = *prm; ctx->n_pairs = n_pairs;
     ctx->n_runs = n_runs; ctx->sel_run = 0; ctx->n_launched = 0;
+    // A traceback kernel has a latency floor of ~1.3 ms however few pairs it walks (every thread takes its ~700 dependent steps), and a fill
+    // may only overwrite a lane's record after the traceback that reads it.  Large batches: 2 lanes (5 GB each), the next fill is longer
+    // than that floor.  Small batches (below two maximal segments, e.g. one rank's 125 k pairs of a 1 M batch strong-scaled over 8 GPUs):
+    // segments of two waves on 8 lanes, each lane with its own traceback stream, so the tracebacks of consecutive segments run side by
+    // side and no fill waits for one (125 k pairs, both modes, 2-wave segments: 15.3 ms on 2 lanes, 9.9 ms on 8; scripts/small_batch_exp.py).
+    // On one idle GPU the doubling schedule is 8 % faster still (9.1 ms); the fine segments pay when the copies are slow (8 ranks copying
+    // at once get 24 GB/s each instead of 55): only the last segment's kernels are then left uncovered.
+    const bool small_batch = pipelined && !ctx->seg_user && n_pairs < 2 * ctx->seg_max_pairs;
+    ctx->n_lanes = ctx->lanes_cfg ? ctx->lanes_cfg : (small_batch ? MAX_LANES : 2);
     for (uint32_t r = 0; r < n_runs; ++r) ctx->run[r].mode = prms[r].mode;
     ctx->segs.clear(); ctx->wide_pairs.clear();
     ctx->cells = ctx->fill_bytes = ctx->launches = ctx->h2d = ctx->d2h = 0;
@@ -946,8 +958,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
         const size_t si_next = ctx->segs.size();
         uint64_t lim_pairs = !pipelined ? ctx->seg_resident_pairs
                            : std::min<uint64_t>(ctx->seg_max_pairs, si_next < 20 ? ctx->seg_first_pairs << si_next : ctx->seg_max_pairs);
-        if (pipelined && !ctx->seg_user && n_pairs < 8 * ctx->seg_max_pairs)       // small batch: ~8 equal segments of whole waves
-            lim_pairs = std::max<uint64_t>(2 * ctx->seg_wave_pairs, (n_pairs / 8) / ctx->seg_wave_pairs * ctx->seg_wave_pairs);
+        if (small_batch) lim_pairs = 2 * ctx->seg_wave_pairs;                         // equal segments of two whole waves
         const uint64_t lim_bytes = pipelined ? ctx->seg_budget_bytes : ctx->seg_resident_bytes;
         uint64_t plan_key = ~0ull; bool plan_ok = false; Short16Plan pl{0, 0, 0}; uint64_t pair_bytes = 0;
         for (; k < n_pairs; ++k) {
@@ -1219,9 +1230,8 @@ b2a_ctx* b2a_create(int device) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     set_kernel_attributes();
-    if (const char* e = std::getenv("B2A_TB_OPT")) ctx->tb_opt = std::atoi(e);
     if (const char* e = std::getenv("B2A_TRACE")) ctx->trace = std::atoi(e) != 0;
-    if (const char* e = std::getenv("B2A_LANES")) ctx->n_lanes = std::max(1, std::min(MAX_LANES, std::atoi(e)));
+    if (const char* e = std::getenv("B2A_LANES")) ctx->lanes_cfg = std::max(0, std::min(MAX_LANES, std::atoi(e)));
     if (const char* e = std::getenv("B2A_SEG_MB")) ctx->seg_budget_bytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;
     ctx->seg_wave_pairs = (uint64_t)ctx->sm_count * FILL_MIN_CTAS * FILL_WARPS * 2;
     if (const char* e = std::getenv("B2A_SEG_PAIRS")) { ctx->seg_max_pairs = ctx->seg_resident_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, std::strtoull(e, nullptr, 10)); ctx->seg_user = true; }
@@ -1231,10 +1241,10 @@ b2a_ctx* b2a_create(int device) {
     bool ok = cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_down, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithPriority(&ctx->s_fill, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
-              cudaStreamCreateWithPriority(&ctx->s_tb, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
               cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
     for (int l = 0; l < MAX_LANES && ok; ++l)
-        ok = cudaEventCreateWithFlags(&ctx->lanes[l].tb_done, cudaEventDisableTiming) == cudaSuccess;
+        ok = cudaEventCreateWithFlags(&ctx->lanes[l].tb_done, cudaEventDisableTiming) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&ctx->lanes[l].s_tb, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
     if (!ok) { b2a_destroy(ctx); cudaGetLastError(); return nullptr; }
     return ctx;
 }
@@ -1245,13 +1255,13 @@ void b2a_destroy(b2a_ctx* ctx) {
     if (ctx->s_copy) cudaStreamSynchronize(ctx->s_copy);
     if (ctx->s_down) cudaStreamSynchronize(ctx->s_down);
     if (ctx->s_fill) cudaStreamSynchronize(ctx->s_fill);
-    if (ctx->s_tb) cudaStreamSynchronize(ctx->s_tb);
+    for (auto& ln : ctx->lanes) if (ln.s_tb) cudaStreamSynchronize(ln.s_tb);
     for (auto& ln : ctx->lanes) {
         ln.codes.release(); ln.rowbest.release();
         if (ln.tb_done) cudaEventDestroy(ln.tb_done);
     }
     if (ctx->s_fill) cudaStreamDestroy(ctx->s_fill);
-    if (ctx->s_tb) cudaStreamDestroy(ctx->s_tb);
+    for (auto& ln : ctx->lanes) if (ln.s_tb) cudaStreamDestroy(ln.s_tb);
     ctx->d_pat.release(); ctx->d_txt.release(); ctx->d_pat_off.release(); ctx->d_txt_off.release();
     ctx->d_code_off.release(); ctx->d_ops_off.release(); ctx->d_pps.release();
     ctx->d_alpha.release(); ctx->d_nops.release(); ctx->d_hist.release(); ctx->d_dirty.release(); ctx->h_dirty.release();
@@ -1480,11 +1490,10 @@ int b2a_set_option(b2a_ctx* ctx, int option, int64_t value)
 {
     if (!ctx) return B2A_ERR_ARG;
     switch (option) {
-        case B2A_OPT_LANES:      if (value < 1 || value > MAX_LANES) break; ctx->n_lanes = (int)value; return B2A_OK;
+        case B2A_OPT_LANES:      if (value < 0 || value > MAX_LANES) break; ctx->lanes_cfg = (int)value; return B2A_OK;
         case B2A_OPT_SEG_PAIRS:  if (value < 1) break; ctx->seg_max_pairs = ctx->seg_resident_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, (uint64_t)value); ctx->seg_user = true; return B2A_OK;
         case B2A_OPT_SEG_FIRST:  if (value < 1) break; ctx->seg_first_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, (uint64_t)value); ctx->seg_user = true; return B2A_OK;
         case B2A_OPT_SEG_BYTES:  if (value < 1) break; ctx->seg_budget_bytes = (uint64_t)value; return B2A_OK;
-        case B2A_OPT_TB:         ctx->tb_opt = (int)value; return B2A_OK;
         case B2A_OPT_CKPT_BYTES: if (value < 0) break; ctx->wide_ckpt_bytes = (uint64_t)value; return B2A_OK;
         case B2A_OPT_CKPT_GROUP: if (value < 1) break; ctx->wide_ckpt_group_bytes = (uint64_t)value; return B2A_OK;
         case B2A_OPT_CKPT_COLS:  if (value < 2 || value > 30) break; ctx->wide_ckpt_col_shift = (uint32_t)value; return B2A_OK;

@@ -68,7 +68,7 @@ struct WideArgs {
 
 constexpr int WIDE_WARPS = 4;
 #ifndef WIDE_MID_UNROLL
-#define WIDE_MID_UNROLL 32     // unroll of the F-2 middle steps of a delta word (tuned on config 4 / config 5, scripts/bench_long.py)
+#define WIDE_MID_UNROLL 32     // unroll of the F-2 middle steps of a delta word (tuned on config 4 / config 5, bench.py --config c4 / c5)
 #endif
 constexpr int MID_UNROLL = WIDE_MID_UNROLL;
 
@@ -83,7 +83,7 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
 // Waits until this lane's tagged boundary entry (if it `need`s one) carries `tag`; `v` is a copy loaded a block
 // earlier.  WARP-UNIFORM on purpose: every lane leaves the loop in the same iteration (__all_sync).  A per-lane
 // polling loop left the warp split into sub-warps that then executed the whole next block of shuffle-synchronised
-// steps one group after the other (3.5x slower first block of every band, measured with B2A_WIDE_DEBUG stamps).
+// steps one group after the other (3.5x slower first block of every band, measured with per-band globaltimer stamps in round 1).
 // Re-polls back off so that hundreds of waiting bands of one long pair do not flood L2.
 __device__ __forceinline__ uint32_t bound_wait(const uint64_t* p, uint64_t v, uint32_t tag, bool need) {
     uint32_t ns = 32;

@@ -35,6 +35,17 @@ def local_best(mode, results):
     return best, idx
 
 
+def first_strict_max(candidates):
+    """Batch winner from per-shard winners: candidates[r] = (key, global pair index or -1) of shard r, shards own ascending index ranges.
+    hw2.cpp:326-357 scans all pairs with a strict '>' from -1000000, so the winner is the first strict maximum of the candidates in shard
+    order (ties resolve to the lowest index).  Returns the global index, -1 if no pair beats -1000000."""
+    best_key, best_idx = -1000000, -1
+    for key, idx in candidates:
+        if int(idx) >= 0 and int(key) > best_key:
+            best_key, best_idx = int(key), int(idx)
+    return best_idx
+
+
 def _device():
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 

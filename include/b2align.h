@@ -166,11 +166,10 @@ int b2a_affine_star_scores(b2a_ctx* ctx, int32_t match, int32_t mismatch, int32_
 /* ---- tuning knobs (defaults are what bench.py measures) -------------------------------------- */
 /* A batch is cut into segments of consecutive pairs; the copy of segment k+1 overlaps the kernels
  * of segment k and the DP record of a lane is reused by every second segment. */
-#define B2A_OPT_LANES      1   /* compute lanes (streams + records) the segments alternate over: 1 or 2 */
+#define B2A_OPT_LANES      1   /* DP records (+ traceback streams) the launches alternate over: 1..8, 0 = automatic */
 #define B2A_OPT_SEG_PAIRS  2   /* max pairs per segment                                                  */
 #define B2A_OPT_SEG_FIRST  5   /* pairs of the first segment of b2a_align_batch (doubling up to the max) */
 #define B2A_OPT_SEG_BYTES  3   /* DP-record bytes per segment                                            */
-#define B2A_OPT_TB         4   /* traceback walker tuning bits (experiments)                             */
 #define B2A_OPT_CKPT_BYTES 6   /* a long pair whose traceback record (0.5 byte per cell) would exceed this many bytes is walked from
                                   checkpoint rows instead (score pass + band groups re-filled bottom-up): default 48 GB              */
 #define B2A_OPT_CKPT_GROUP 7   /* ... and this is the record size of one re-filled band group: default 1 GB                         */

@@ -690,7 +690,24 @@ def test_abi_error_paths(eng):
     assert lib.b2a_affine_fetch_ops(eng.ctx, 0, buf, 16) == -5                      # no affine batch yet
     sc = np.zeros(2, dtype=np.int32)
     assert lib.b2a_affine_score_batch(eng.ctx, 1 << 29, -1, -2, -1, P(pat), P(po), P(txt), P(to), 2, P(sc)) == -4    # sentinel would wrap
-    assert lib.b2a_set_option(eng.ctx, 99, 1) == -1 and lib.b2a_set_option(eng.ctx, pkg.OPT_LANES, 3) == -1
+    assert lib.b2a_set_option(eng.ctx, 99, 1) == -1 and lib.b2a_set_option(eng.ctx, pkg.OPT_LANES, 9) == -1
+    # several runs over one upload: run count, modes and the shared scoring are validated; b2a_select_run only knows the last batch's runs
+    res2 = np.empty(2, dtype=pkg.RESULT_DTYPE)
+    ptrs = (C.c_void_p * 2)(P(res), P(res2))
+    def multi(prms, n_runs, ptrs_=ptrs):
+        arr = (pkg.Params * len(prms))(*prms)
+        return lib.b2a_align_batch_multi(eng.ctx, arr, n_runs, P(pat), P(po), P(txt), P(to), 2, ptrs_)
+    g, l = pkg.Params(pkg.GLOBAL, 1, -1, -1, pkg.WANT_OPS), pkg.Params(pkg.LOCAL, 1, -1, -1, pkg.WANT_OPS)
+    assert multi([g, l], 0) == -1 and multi([g, l, g], 3) == -1                     # 1 <= n_runs <= B2A_MAX_RUNS
+    assert multi([g, pkg.Params(pkg.LOCAL, 2, -1, -1, pkg.WANT_OPS)], 2) == -1       # runs share the scoring
+    assert multi([g, pkg.Params(pkg.LOCAL, 1, -1, -1, 0)], 2) == -1                  # ... and the flags
+    assert multi([g, pkg.Params(5, 1, -1, -1, pkg.WANT_OPS)], 2) == -1               # bad mode in run 1
+    assert multi([g, l], 2, (C.c_void_p * 2)(P(res), None)) == -1                   # a run without a result array
+    assert multi([g, l], 2) == 0 and lib.b2a_select_run(eng.ctx, 1) == 0 and lib.b2a_select_run(eng.ctx, 2) == -1
+    assert lib.b2a_fetch_ops(eng.ctx, 0, buf, 16) == int(res2["n_ops"][0])          # run 1 = local
+    assert call(pkg.Params(pkg.GLOBAL, 1, -1, -1, pkg.WANT_OPS)) == 0 and lib.b2a_select_run(eng.ctx, 1) == -1
+    assert lib.b2a_host_register(None, 0) == -1 and lib.b2a_host_unregister(None) == -1
+    assert lib.b2a_set_option(eng.ctx, pkg.OPT_CKPT_COLS, 1) == -1 and lib.b2a_set_option(eng.ctx, pkg.OPT_CKPT_GROUP, 0) == -1
     fresh = pkg.Engine(0)
     assert fresh.lib.b2a_batch_run(fresh.ctx, None, None) == -5                     # run before upload
     assert fresh.lib.b2a_batch_download(fresh.ctx, P(res)) == -5

@@ -110,3 +110,28 @@ def test_pair_range_partitions_exactly():
             assert spans[0][0] == 0 and sum(c for _, c in spans) == n
             for (f0, c0), (f1, _) in zip(spans, spans[1:]):
                 assert f0 + c0 == f1
+
+
+def test_per_shard_selection_merges_to_the_serial_winner():
+    """bench.py's strong arm: every rank runs b2a_select_best over its slice of the gathered records, rank 0 takes the first strict maximum of the
+    candidates in rank order -- the same pair the serial scan hw2.cpp:326-357 (b2a_select_best over everything) picks, ties and empty shards included."""
+    import numpy as np
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    from bioinformatics_algorithms_b200 import sharding
+    rng = np.random.default_rng(5)
+    for trial in range(200):
+        n = int(rng.integers(0, 60))
+        res = np.zeros(n, dtype=pkg.RESULT_DTYPE)
+        hi = int(rng.choice([2, 5, 1000]))
+        res["score"] = rng.integers(-3 if trial % 3 else -2000000, hi, size=n)
+        res["overlap"] = rng.integers(0, hi, size=n)
+        for world in (1, 2, 3, 8):
+            for mode in (sharding.GLOBAL, sharding.LOCAL):
+                cands = []
+                for r in range(world):
+                    first, count = sharding.pair_range(n, r, world)
+                    b = pkg.select_best(mode, res[first:first + count])
+                    key = int(res["overlap" if mode == sharding.GLOBAL else "score"][first + b]) if b >= 0 else -1000000
+                    cands.append((key, first + b if b >= 0 else -1))
+                assert sharding.first_strict_max(cands) == pkg.select_best(mode, res), (trial, world, mode)
