@@ -144,11 +144,11 @@ struct b2a_ctx {
                                                   // the fill of segment k+1 (s_fill); end to end 61.8 -> 59.1 ms per 1 M pairs NW+SW
     bool trace = false;                           // B2A_TRACE=1: per-segment timeline of b2a_align_batch on stderr
     uint64_t seg_budget_bytes = 8ull << 30;       // record bytes per segment (B2A_SEG_MB overrides)
-    // Segments of b2a_align_batch.  16 k pairs, then doubling up to 96 k (the kernels start after a short copy; swept in
+    // Segments of b2a_align_batch.  16 k pairs, then doubling up to 128 k (the kernels start after a short copy; swept in
     // scripts/seg_e2e_sweep.py: every schedule between 58.3 and 60.0 ms for 1 M pairs).  Small batches (< 2 maximal segments): equal segments
     // of two whole WAVES of the short16 fill grid (sm_count x 6 CTAs x 4 warps x 2 pairs = 7104 pairs on a B200), see batch_prepare.
     uint64_t seg_wave_pairs = 7104;               // set from the device in b2a_create
-    uint64_t seg_max_pairs = 98304;               // B2A_SEG_PAIRS / B2A_OPT_SEG_PAIRS override
+    uint64_t seg_max_pairs = 131072;              // B2A_SEG_PAIRS / B2A_OPT_SEG_PAIRS override
     uint64_t seg_first_pairs = 1ull << 14;        // B2A_SEG_FIRST / B2A_OPT_SEG_FIRST override
     bool seg_user = false;                        // the caller set the schedule: take it literally
     uint64_t seg_resident_pairs = 1ull << 20;     // pairs per segment of b2a_batch_upload / b2a_batch_run ...

@@ -216,19 +216,31 @@ int orc_align_ckpt(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uin
 int orc_score_only(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t n,
                    int match, int mismatch, int gap, orc_result* res)
 {
-    int32_t* row = (int32_t*)malloc(sizeof(int32_t) * ((size_t)n + 1));
+    /* Per row the cell max(diag + s, up + gap) depends on the previous row only (first loop: no loop-carried dependency, the compiler
+     * vectorises it); the left neighbour is folded in by a second, sequential loop.  max is associative, so every H equals the
+     * reference's; the local arg-max scans the finished row left to right with the same strict '>' (hw2.cpp:225-229). */
+    int32_t* row = (int32_t*)malloc(sizeof(int32_t) * ((size_t)n + 1) * 2);
     if (!row) return -1;
+    int32_t* tmp = row + (size_t)n + 1;
     int score = 0; uint32_t bi = 0, bj = 0;
     for (uint32_t j = 0; j <= n; ++j) row[j] = mode == 0 ? (int32_t)((int64_t)j * gap) : 0;
     for (uint32_t i = 1; i <= m; ++i) {
-        int32_t diagv = row[0];
-        row[0] = mode == 0 ? (int32_t)((int64_t)i * gap) : 0;
+        const uint8_t pc = p[i - 1];
         for (uint32_t j = 1; j <= n; ++j) {
-            int d = diagv + (p[i - 1] == t[j - 1] ? match : mismatch);
-            int u = row[j] + gap, l = row[j - 1] + gap;
-            int v = d; if (l > v) v = l; if (u > v) v = u;
-            if (mode != 0) { if (v < 0) v = 0; if (v > score) { score = v; bi = i; bj = j; } }
-            diagv = row[j]; row[j] = v;
+            const int d = row[j - 1] + (pc == t[j - 1] ? match : mismatch);
+            const int u = row[j] + gap;
+            tmp[j] = d > u ? d : u;
+        }
+        int32_t left = mode == 0 ? (int32_t)((int64_t)i * gap) : 0;
+        row[0] = left;
+        if (mode == 0) {
+            for (uint32_t j = 1; j <= n; ++j) { int v = tmp[j]; const int l = left + gap; if (l > v) v = l; row[j] = v; left = v; }
+        } else {
+            for (uint32_t j = 1; j <= n; ++j) {
+                int v = tmp[j]; const int l = left + gap; if (l > v) v = l; if (v < 0) v = 0;
+                if (v > score) { score = v; bi = i; bj = j; }
+                row[j] = v; left = v;
+            }
         }
     }
     memset(res, 0, sizeof(*res));
@@ -290,18 +302,28 @@ int orc_affine_score(const uint8_t* s1, uint32_t m, const uint8_t* s2, uint32_t 
     int32_t *Vp = V, *Fp = V + W, *Ep = V + 2 * W, *Vc = V + 3 * W, *Fc = V + 4 * W, *Ec = V + 5 * W;
     Vp[0] = 0; Fp[0] = NEG; Ep[0] = NEG;            /* hw3.cpp:40-41 */
     for (uint32_t j = 1; j <= n; ++j) { Vp[j] = NEG; Fp[j] = NEG; Ep[j] = gopen + gext * (int32_t)(j - 1); } /* :48-53 */
+    /* V and F of a row depend on the previous row only (first loop, vectorisable); E runs along the row (second loop).  Same values. */
     for (uint32_t i = 1; i <= m; ++i) {
         Vc[0] = NEG; Ec[0] = NEG; Fc[0] = gopen + gext * (int32_t)(i - 1);                                   /* :42-47 */
+        const uint8_t c1 = s1[i - 1];
+        {
+            const int32_t* restrict vp = Vp; const int32_t* restrict fp = Fp; const int32_t* restrict ep = Ep;   /* six disjoint rows */
+            int32_t* restrict vc = Vc; int32_t* restrict fc = Fc;
+            for (uint32_t j = 1; j <= n; ++j) {
+                const int s = c1 == s2[j - 1] ? match : mismatch;
+                int v = vp[j - 1];                                         /* :59-68: max(V, F, E)[i-1][j-1] + s */
+                if (fp[j - 1] > v) v = fp[j - 1];
+                if (ep[j - 1] > v) v = ep[j - 1];
+                int f = vp[j] + gopen + gext;                              /* :70-75 */
+                if (fp[j] + gext > f) f = fp[j] + gext;
+                vc[j] = v + s; fc[j] = f;
+            }
+        }
+        int32_t e = Ec[0];
         for (uint32_t j = 1; j <= n; ++j) {
-            int s = s1[i - 1] == s2[j - 1] ? match : mismatch;
-            int v = Vp[j - 1] + s;                                         /* :59-68 */
-            if (Fp[j - 1] + s > v) v = Fp[j - 1] + s;
-            if (Ep[j - 1] + s > v) v = Ep[j - 1] + s;
-            int f = Vp[j] + gopen + gext;                                  /* :70-75 */
-            if (Fp[j] + gext > f) f = Fp[j] + gext;
-            int e = Vc[j - 1] + gopen + gext;                              /* :77-82 */
-            if (Ec[j - 1] + gext > e) e = Ec[j - 1] + gext;
-            Vc[j] = v; Fc[j] = f; Ec[j] = e;
+            int open = Vc[j - 1] + gopen + gext;                           /* :77-82 */
+            e = e + gext > open ? e + gext : open;
+            Ec[j] = e;
         }
         int32_t* x;
         x = Vp; Vp = Vc; Vc = x; x = Fp; Fp = Fc; Fc = x; x = Ep; Ep = Ec; Ec = x;
