@@ -154,16 +154,21 @@ int orc_align_ckpt(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uin
     int score = 0; uint32_t bi = 0, bj = 0;
     for (uint32_t j = 0; j <= n; ++j) row[j] = mode == 0 ? (int32_t)((int64_t)j * gap) : 0;
     memcpy(cp, row, sizeof(int32_t) * W);
+    int32_t* tmp = blk;                                     /* scratch for pass 1 (blk is not in use yet) */
     for (uint32_t i = 1; i <= m; ++i) {
-        int32_t diagv = row[0];
-        row[0] = mode == 0 ? (int32_t)((int64_t)i * gap) : 0;
+        /* as in orc_score_only: max(diag + s, up + gap) from the previous row (vectorisable), then the left neighbour along the row */
+        const uint8_t pc = p[i - 1];
         for (uint32_t j = 1; j <= n; ++j) {
-            int d = diagv + (p[i - 1] == t[j - 1] ? match : mismatch);
-            int u = row[j] + gap, l = row[j - 1] + gap;
-            int v;
-            if (mode == 0) { v = d; if (l > v) v = l; if (u > v) v = u; }
-            else { int ul = u > l ? u : l; v = d > ul ? d : ul; if (v < 0) v = 0; if (v > score) { score = v; bi = i; bj = j; } }
-            diagv = row[j]; row[j] = v;
+            const int d = row[j - 1] + (pc == t[j - 1] ? match : mismatch);
+            const int u = row[j] + gap;
+            tmp[j] = d > u ? d : u;
+        }
+        int32_t left = mode == 0 ? (int32_t)((int64_t)i * gap) : 0;
+        row[0] = left;
+        for (uint32_t j = 1; j <= n; ++j) {
+            int v = tmp[j]; const int l = left + gap; if (l > v) v = l;
+            if (mode != 0) { if (v < 0) v = 0; if (v > score) { score = v; bi = i; bj = j; } }
+            row[j] = v; left = v;
         }
         if (i % ck == 0) memcpy(cp + (size_t)(i / ck) * W, row, sizeof(int32_t) * W);
     }
@@ -177,14 +182,17 @@ int orc_align_ckpt(int mode, const uint8_t* p, uint32_t m, const uint8_t* t, uin
         memcpy(blk, cp + (size_t)b * W, sizeof(int32_t) * BW);
         for (uint32_t i = r0 + 1; i <= ti; ++i) {
             int32_t* prev = blk + (size_t)(i - 1 - r0) * BW; int32_t* curr = blk + (size_t)(i - r0) * BW;
-            curr[0] = mode == 0 ? (int32_t)((int64_t)i * gap) : 0;
+            const uint8_t pc = p[i - 1];
             for (uint32_t j = 1; j <= tj; ++j) {
-                int d = prev[j - 1] + (p[i - 1] == t[j - 1] ? match : mismatch);
-                int u = prev[j] + gap, l = curr[j - 1] + gap;
-                int v;
-                if (mode == 0) { v = d; if (l > v) v = l; if (u > v) v = u; }
-                else { int ul = u > l ? u : l; v = d > ul ? d : ul; if (v < 0) v = 0; }
-                curr[j] = v;
+                const int d = prev[j - 1] + (pc == t[j - 1] ? match : mismatch);
+                const int u = prev[j] + gap;
+                curr[j] = d > u ? d : u;
+            }
+            int32_t left = mode == 0 ? (int32_t)((int64_t)i * gap) : 0;
+            curr[0] = left;
+            for (uint32_t j = 1; j <= tj; ++j) {
+                int v = curr[j]; const int l = left + gap; if (l > v) v = l; if (mode != 0 && v < 0) v = 0;
+                curr[j] = v; left = v;
             }
         }
         while (ti > r0 && tj > 0) {
