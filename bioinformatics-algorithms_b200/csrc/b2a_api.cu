@@ -145,9 +145,7 @@ struct b2a_ctx {
     bool trace = false;                           // B2A_TRACE=1: per-segment timeline of b2a_align_batch on stderr
     uint64_t seg_budget_bytes = 8ull << 30;       // record bytes per segment (B2A_SEG_MB overrides)
     // Segments of b2a_align_batch.  16 k pairs, then doubling up to 128 k (the kernels start after a short copy; swept in
-    // scripts/seg_e2e_sweep.py: every schedule between 58.3 and 60.0 ms for 1 M pairs).  Small batches (< 2 maximal segments): equal segments
-    // of two whole WAVES of the short16 fill grid (sm_count x 6 CTAs x 4 warps x 2 pairs = 7104 pairs on a B200), see batch_prepare.
-    uint64_t seg_wave_pairs = 7104;               // set from the device in b2a_create
+    // scripts/seg_e2e_sweep.py: every schedule between 58.3 and 60.0 ms for 1 M pairs).
     uint64_t seg_max_pairs = 131072;              // B2A_SEG_PAIRS / B2A_OPT_SEG_PAIRS override
     uint64_t seg_first_pairs = 1ull << 14;        // B2A_SEG_FIRST / B2A_OPT_SEG_FIRST override
     bool seg_user = false;                        // the caller set the schedule: take it literally
@@ -892,12 +890,12 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
     ctx->prm = *prm; ctx->n_pairs = n_pairs;
     ctx->n_runs = n_runs; ctx->sel_run = 0; ctx->n_launched = 0;
     // A traceback kernel has a latency floor of ~1.3 ms however few pairs it walks (every thread takes its ~700 dependent steps), and a fill
-    // may only overwrite a lane's record after the traceback that reads it.  Large batches: 2 lanes (5 GB each), the next fill is longer
+    // may only overwrite a lane's record after the traceback that reads it.  Large batches: 2 lanes (7 GB each), the next fill is longer
     // than that floor.  Small batches (below two maximal segments, e.g. one rank's 125 k pairs of a 1 M batch strong-scaled over 8 GPUs):
-    // segments of two waves on 8 lanes, each lane with its own traceback stream, so the tracebacks of consecutive segments run side by
-    // side and no fill waits for one (125 k pairs, both modes, 2-wave segments: 15.3 ms on 2 lanes, 9.9 ms on 8; scripts/small_batch_exp.py).
-    // On one idle GPU the doubling schedule is 8 % faster still (9.1 ms); the fine segments pay when the copies are slow (8 ranks copying
-    // at once get 24 GB/s each instead of 55): only the last segment's kernels are then left uncovered.
+    // 8 lanes, each with its own traceback stream, so the tracebacks of consecutive segments run side by side and no fill waits for one
+    // (125 k pairs, both modes: 9.8 -> 9.1 ms; with 14 k-pair segments 15.3 -> 9.9 ms: scripts/small_batch_exp.py).  The segment schedule
+    // stays the doubling one: equal segments of exactly two waves were tried for such batches and lose (12.7 vs ~11 ms per step at 8
+    // GPUs): the resident traceback CTAs of earlier segments take a CTA slot per SM from the fill, which turns two waves into three.
     const bool small_batch = pipelined && !ctx->seg_user && n_pairs < 2 * ctx->seg_max_pairs;
     ctx->n_lanes = ctx->lanes_cfg ? ctx->lanes_cfg : (small_batch ? MAX_LANES : 2);
     for (uint32_t r = 0; r < n_runs; ++r) ctx->run[r].mode = prms[r].mode;
@@ -956,9 +954,8 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
         // ---- pass 1: validate, find the end of the segment, per-pair op offsets ----
         uint64_t k = first, seg_bytes = 0;
         const size_t si_next = ctx->segs.size();
-        uint64_t lim_pairs = !pipelined ? ctx->seg_resident_pairs
+        const uint64_t lim_pairs = !pipelined ? ctx->seg_resident_pairs
                            : std::min<uint64_t>(ctx->seg_max_pairs, si_next < 20 ? ctx->seg_first_pairs << si_next : ctx->seg_max_pairs);
-        if (small_batch) lim_pairs = 2 * ctx->seg_wave_pairs;                         // equal segments of two whole waves
         const uint64_t lim_bytes = pipelined ? ctx->seg_budget_bytes : ctx->seg_resident_bytes;
         uint64_t plan_key = ~0ull; bool plan_ok = false; Short16Plan pl{0, 0, 0}; uint64_t pair_bytes = 0;
         for (; k < n_pairs; ++k) {
@@ -1233,7 +1230,6 @@ b2a_ctx* b2a_create(int device) {
     if (const char* e = std::getenv("B2A_TRACE")) ctx->trace = std::atoi(e) != 0;
     if (const char* e = std::getenv("B2A_LANES")) ctx->lanes_cfg = std::max(0, std::min(MAX_LANES, std::atoi(e)));
     if (const char* e = std::getenv("B2A_SEG_MB")) ctx->seg_budget_bytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;
-    ctx->seg_wave_pairs = (uint64_t)ctx->sm_count * FILL_MIN_CTAS * FILL_WARPS * 2;
     if (const char* e = std::getenv("B2A_SEG_PAIRS")) { ctx->seg_max_pairs = ctx->seg_resident_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, std::strtoull(e, nullptr, 10)); ctx->seg_user = true; }
     if (const char* e = std::getenv("B2A_SEG_FIRST")) { ctx->seg_first_pairs = std::max<uint64_t>(SEG_MIN_PAIRS, std::strtoull(e, nullptr, 10)); ctx->seg_user = true; }
     int prio_lo = 0, prio_hi = 0;

@@ -13,14 +13,15 @@ def pin(a):
 pat, po, txt, to = pin(pat_np), pin(po_np), pin(txt_np), pin(to_np)
 res = [pkg.pinned_empty(n, pkg.RESULT_DTYPE) for _ in range(2)]
 W = 7104
-for first, mx in ((16384, 98304), (2 * W, 14 * W), (2 * W, 16 * W), (4 * W, 14 * W), (W, 14 * W), (16384, 131072), (2 * W, 28 * W), (32768, 98304)):
+for first, mx, lanes in ((16384, 131072, 2), (16384, 131072, 3), (16384, 131072, 4), (16384, 131072, 8), (16384, 98304, 2), (16384, 98304, 4),
+                         (2 * W, 16 * W, 4), (32768, 131072, 4), (16384, 262144, 4)):
     e = pkg.Engine(0)
-    e.set_option(pkg.OPT_SEG_FIRST, first); e.set_option(pkg.OPT_SEG_PAIRS, mx)
+    e.set_option(pkg.OPT_SEG_FIRST, first); e.set_option(pkg.OPT_SEG_PAIRS, mx); e.set_option(pkg.OPT_LANES, lanes)
     e.align_packed_multi([0, 1], pat, po, txt, to, 1, -1, -1, want_ops=True, results=res)
     ts = []
     for _ in range(4):
         t0 = time.perf_counter()
         e.align_packed_multi([0, 1], pat, po, txt, to, 1, -1, -1, want_ops=True, results=res)
         ts.append((time.perf_counter() - t0) * 1e3)
-    print(f"first {first:6d} max {mx:6d}: e2e ms {min(ts):.2f} (min) {np.median(ts):.2f} (median); launches {e.stats()['launches']}", flush=True)
+    print(f"first {first:6d} max {mx:6d} lanes {lanes}: e2e ms {min(ts):.2f} (min) {np.median(ts):.2f} (median); launches {e.stats()['launches']}", flush=True)
     e.close()
