@@ -79,6 +79,7 @@ struct Lane {                                     // one DP record, reused by ev
     DevBuf<uint32_t> rowbest;
     cudaEvent_t tb_done = nullptr;                // last traceback that read this record
     cudaStream_t s_tb = nullptr;                  // the lane's traceback stream (high priority): tracebacks of different lanes run concurrently
+    cudaStream_t s_tb_lo = nullptr;               // the same at the fill's priority: used when there are >= 3 lanes (see batch_prepare)
 };
 
 // host-side state of the wide32 family for the current batch
@@ -139,6 +140,7 @@ constexpr uint64_t SEG_MIN_PAIRS = 2048;          // a segment is never closed b
 struct b2a_ctx {
     int device = 0;
     int sm_count = 0;
+    bool tb_low = false;                          // tracebacks at the fill's stream priority (chosen per batch with the lane count)
     int lanes_cfg = 0;                            // B2A_OPT_LANES / B2A_LANES: 0 = automatic (2, or 8 for small batches, see batch_prepare)
     int n_lanes = 2;                              // DP records the launches alternate over: the traceback of one launch (its lane's s_tb) overlaps
                                                   // the fill of segment k+1 (s_fill); end to end 61.8 -> 59.1 ms per 1 M pairs NW+SW
@@ -637,7 +639,7 @@ int launch_segment(b2a_ctx* ctx, size_t si, int r, uint64_t* launches)
     if (!ev || !ev_in) return fail(ctx, B2A_ERR_CUDA, "cudaEventCreate failed");
     if (sg.chunks > ln.codes.cap || (local && sg.rowbest_words > ln.rowbest.cap)) {     // (rowbest is a local-mode buffer: a lane that only ever
                                                                                          // serves global runs never grows it)
-        CU(cudaStreamSynchronize(ctx->s_fill)); CU(cudaStreamSynchronize(ln.s_tb));     // the lane's record is about to be reallocated
+        CU(cudaStreamSynchronize(ctx->s_fill)); CU(cudaStreamSynchronize(ln.s_tb)); CU(cudaStreamSynchronize(ln.s_tb_lo));   // the lane's record is about to be reallocated
         CU(ln.codes.reserve(sg.chunks));
         if (local) CU(ln.rowbest.reserve(sg.rowbest_words));
     }
@@ -662,7 +664,7 @@ int launch_segment(b2a_ctx* ctx, size_t si, int r, uint64_t* launches)
         *launches += 2;
     }
     CU(cudaEventRecord(ev[2], st));
-    st = ln.s_tb;
+    st = ctx->tb_low ? ln.s_tb_lo : ln.s_tb;
     CU(cudaStreamWaitEvent(st, ev[2], 0));
     for (const ClassRange& c : sg.classes) {
         Short16Plan pl{0, 0, 0};
@@ -705,7 +707,7 @@ int affine_run(b2a_ctx* ctx, int match, int mismatch, int gopen, int gext, const
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->s_copy)); CU(cudaStreamSynchronize(ctx->s_down));
     CU(cudaStreamSynchronize(ctx->s_fill));
-    for (auto& ln : ctx->lanes) CU(cudaStreamSynchronize(ln.s_tb));
+    for (auto& ln : ctx->lanes) { CU(cudaStreamSynchronize(ln.s_tb)); CU(cudaStreamSynchronize(ln.s_tb_lo)); }
     ctx->have_batch = false; ctx->ran = false; ctx->affine_ops = false;   // the batch buffers are reused below
     ctx->cells = ctx->fill_bytes = ctx->launches = ctx->h2d = ctx->d2h = 0;
     const int64_t smag = std::max<int64_t>({std::llabs((long long)match), std::llabs((long long)mismatch),
@@ -885,19 +887,22 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
     // a previous batch may still own the pinned plan arrays / device buffers
     CU(cudaStreamSynchronize(ctx->s_copy)); CU(cudaStreamSynchronize(ctx->s_down));
     CU(cudaStreamSynchronize(ctx->s_fill));
-    for (auto& ln : ctx->lanes) CU(cudaStreamSynchronize(ln.s_tb));
+    for (auto& ln : ctx->lanes) { CU(cudaStreamSynchronize(ln.s_tb)); CU(cudaStreamSynchronize(ln.s_tb_lo)); }
     ctx->have_batch = false; ctx->ran = false; ctx->affine_ops = false;
     ctx->prm = *prm; ctx->n_pairs = n_pairs;
     ctx->n_runs = n_runs; ctx->sel_run = 0; ctx->n_launched = 0;
     // A traceback kernel has a latency floor of ~1.3 ms however few pairs it walks (every thread takes its ~700 dependent steps), and a fill
-    // may only overwrite a lane's record after the traceback that reads it.  Large batches: 2 lanes (7 GB each), the next fill is longer
-    // than that floor.  Small batches (below two maximal segments, e.g. one rank's 125 k pairs of a 1 M batch strong-scaled over 8 GPUs):
-    // 8 lanes, each with its own traceback stream, so the tracebacks of consecutive segments run side by side and no fill waits for one
-    // (125 k pairs, both modes: 9.8 -> 9.1 ms; with 14 k-pair segments 15.3 -> 9.9 ms: scripts/small_batch_exp.py).  The segment schedule
-    // stays the doubling one: equal segments of exactly two waves were tried for such batches and lose (12.7 vs ~11 ms per step at 8
-    // GPUs): the resident traceback CTAs of earlier segments take a CTA slot per SM from the fill, which turns two waves into three.
+    // may only overwrite a lane's record after the traceback that reads it.  So the launches alternate over several record lanes, each with
+    // its own traceback stream: 4 lanes (7 GB each) for large batches, 8 for batches below two maximal segments (e.g. one rank's 125 k
+    // pairs of a 1 M batch strong-scaled over 8 GPUs), whose tracebacks would otherwise gate the next fill.  With >= 3 lanes the
+    // tracebacks run at the fill's priority and fill the gaps the fill grids leave; with 2 lanes they must overtake the next fill (high
+    // priority) or that fill waits.  Measured end to end, both modes (scripts/small_batch_exp.py, scripts/seg_e2e_sweep.py):
+    //   125 k pairs: 2 lanes 9.80 ms, 8 lanes 9.19 ms, 8 lanes + fill priority 8.40 ms;   1 M pairs: 57.98 / 57.25 (4 lanes) / 57.06 ms.
+    // Equal segments of exactly two fill waves were tried for small batches and lose: resident traceback CTAs take a CTA slot per SM from
+    // the fill, which turns two waves into three.
     const bool small_batch = pipelined && !ctx->seg_user && n_pairs < 2 * ctx->seg_max_pairs;
-    ctx->n_lanes = ctx->lanes_cfg ? ctx->lanes_cfg : (small_batch ? MAX_LANES : 2);
+    ctx->n_lanes = ctx->lanes_cfg ? ctx->lanes_cfg : (small_batch ? MAX_LANES : (pipelined ? 4 : 2));
+    ctx->tb_low = ctx->n_lanes >= 3;
     for (uint32_t r = 0; r < n_runs; ++r) ctx->run[r].mode = prms[r].mode;
     ctx->segs.clear(); ctx->wide_pairs.clear();
     ctx->cells = ctx->fill_bytes = ctx->launches = ctx->h2d = ctx->d2h = 0;
@@ -1240,7 +1245,9 @@ b2a_ctx* b2a_create(int device) {
               cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
     for (int l = 0; l < MAX_LANES && ok; ++l)
         ok = cudaEventCreateWithFlags(&ctx->lanes[l].tb_done, cudaEventDisableTiming) == cudaSuccess &&
-             cudaStreamCreateWithPriority(&ctx->lanes[l].s_tb, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+             cudaStreamCreateWithPriority(&ctx->lanes[l].s_tb, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&ctx->lanes[l].s_tb_lo, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
+
     if (!ok) { b2a_destroy(ctx); cudaGetLastError(); return nullptr; }
     return ctx;
 }
@@ -1251,13 +1258,13 @@ void b2a_destroy(b2a_ctx* ctx) {
     if (ctx->s_copy) cudaStreamSynchronize(ctx->s_copy);
     if (ctx->s_down) cudaStreamSynchronize(ctx->s_down);
     if (ctx->s_fill) cudaStreamSynchronize(ctx->s_fill);
-    for (auto& ln : ctx->lanes) if (ln.s_tb) cudaStreamSynchronize(ln.s_tb);
+    for (auto& ln : ctx->lanes) { if (ln.s_tb) cudaStreamSynchronize(ln.s_tb); if (ln.s_tb_lo) cudaStreamSynchronize(ln.s_tb_lo); }
     for (auto& ln : ctx->lanes) {
         ln.codes.release(); ln.rowbest.release();
         if (ln.tb_done) cudaEventDestroy(ln.tb_done);
     }
     if (ctx->s_fill) cudaStreamDestroy(ctx->s_fill);
-    for (auto& ln : ctx->lanes) if (ln.s_tb) cudaStreamDestroy(ln.s_tb);
+    for (auto& ln : ctx->lanes) { if (ln.s_tb) cudaStreamDestroy(ln.s_tb); if (ln.s_tb_lo) cudaStreamDestroy(ln.s_tb_lo); }
     ctx->d_pat.release(); ctx->d_txt.release(); ctx->d_pat_off.release(); ctx->d_txt_off.release();
     ctx->d_code_off.release(); ctx->d_ops_off.release(); ctx->d_pps.release();
     ctx->d_alpha.release(); ctx->d_nops.release(); ctx->d_hist.release(); ctx->d_dirty.release(); ctx->h_dirty.release();
