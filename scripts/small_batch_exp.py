@@ -13,25 +13,24 @@ def pin(a):
 pat, po, txt, to = pin(pat_np), pin(po_np), pin(txt_np), pin(to_np)
 res = [pkg.pinned_empty(n, pkg.RESULT_DTYPE) for _ in range(2)]
 W = 7104
-for _once in (0,):
-  for name, first, mx, lanes in (("library default", 0, 0, 0), ("16k doubling to 96k, 2 lanes", 16384, 98304, 2), ("uniform 2 waves, 2 lanes", 2 * W, 2 * W, 2),
-                                 ("uniform 2 waves, 4 lanes", 2 * W, 2 * W, 4), ("uniform 2 waves, 8 lanes", 2 * W, 2 * W, 8), ("uniform 1 wave, 8 lanes", W, W, 8),
-                                 ("uniform 4 waves, 8 lanes", 4 * W, 4 * W, 8), ("16k doubling, 8 lanes", 16384, 98304, 8), ("2 segments, 2 lanes", 62500, 62500, 2)):
-      os.environ["B2A_TRACE"] = "0"
-      e = pkg.Engine(0)
-      if first:
-          e.set_option(pkg.OPT_SEG_FIRST, first); e.set_option(pkg.OPT_SEG_PAIRS, mx)
-      if lanes:
-          e.set_option(pkg.OPT_LANES, lanes)
-      for _ in range(2):
-          e.align_packed_multi([0, 1], pat, po, txt, to, 1, -1, -1, want_ops=True, results=res)
-      ts = []
-      for _ in range(6):
-          t0 = time.perf_counter()
-          e.align_packed_multi([0, 1], pat, po, txt, to, 1, -1, -1, want_ops=True, results=res)
-          ts.append((time.perf_counter() - t0) * 1e3)
-      print(f"{name:30s}: e2e ms min {min(ts):.2f} median {np.median(ts):.2f}; launches {e.stats()['launches']}", flush=True)
-      e.close()
+for name, first, mx, lanes in (("library default", 0, 0, 0), ("16k doubling to 128k, 8 lanes", 16384, 131072, 8), ("16k doubling to 32k, 8 lanes", 16384, 32768, 8),
+                               ("8k doubling to 32k, 8 lanes", 8192, 32768, 8), ("16k flat, 8 lanes", 16384, 16384, 8), ("16k doubling to 64k, 8 lanes", 16384, 65536, 8),
+                               ("24k flat, 8 lanes", 24576, 24576, 8), ("16k doubling to 128k, 2 lanes", 16384, 131072, 2)):
+    os.environ["B2A_TRACE"] = "0"
+    e = pkg.Engine(0)
+    if first:
+        e.set_option(pkg.OPT_SEG_FIRST, first); e.set_option(pkg.OPT_SEG_PAIRS, mx)
+    if lanes:
+        e.set_option(pkg.OPT_LANES, lanes)
+    for _ in range(2):
+        e.align_packed_multi([0, 1], pat, po, txt, to, 1, -1, -1, want_ops=True, results=res)
+    ts = []
+    for _ in range(6):
+        t0 = time.perf_counter()
+        e.align_packed_multi([0, 1], pat, po, txt, to, 1, -1, -1, want_ops=True, results=res)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    print(f"{name:30s}: e2e ms min {min(ts):.2f} median {np.median(ts):.2f}; launches {e.stats()['launches']}", flush=True)
+    e.close()
 for name, first, mx in (("library default", 0, 0),):
     os.environ["B2A_TRACE"] = "1"
     e = pkg.Engine(0)
