@@ -4,12 +4,15 @@
 // SEGMENTS of consecutive pairs.  Per segment the host (1) queues the host->device copy of the
 // segment's sequence bytes, (2) plans it while the copy is in flight: pairs of identical shape are
 // zipped into pair-pairs (the two 16-bit halves of the s16x2 kernels) and grouped by rows-per-lane,
-// (3) queues the fill + traceback kernels on one of two compute lanes.  Nothing in that loop waits
-// for the device: the pattern alphabet of a segment is discovered by a device kernel and stays on
-// the device (AlphaInfo), the DP record of a lane is reused by every second segment, so the copy of
-// segment k+1 overlaps the kernels of segment k and the record footprint is two segments, not the
-// batch.  Pairs the s16x2 record cannot hold (long patterns, wide scores, > 4 pattern symbols) are
-// collected and served afterwards by the wide32 family.
+// (3) queues the fill + traceback kernels of every RUN of the batch (one mode each: -g, -l) on the
+// next of several record lanes.  Nothing in that loop waits for the device: the pattern alphabet of
+// a segment is discovered by device kernels and stays on the device (AlphaInfo, per-pair-pair
+// `dirty` flags), the DP record of a lane is reused by a later launch, so the copy of segment k+1
+// overlaps the kernels of segment k and the record footprint is a few segments, not the batch.
+// Pair-pairs whose patterns hold a fifth symbol are served by the 8-symbol variant of the s16x2
+// kernel; pairs the s16x2 record cannot hold (long patterns, wide scores, > 7 pattern symbols) are
+// collected and served afterwards by the wide32 family, and those whose wide32 record would not fit
+// in memory by checkpointed recomputation (wide_ckpt_run).
 // No CPU alignment code lives here: if CUDA is unavailable every compute entry point fails.
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -153,8 +156,8 @@ struct b2a_ctx {
     bool seg_user = false;                        // the caller set the schedule: take it literally
     uint64_t seg_resident_pairs = 1ull << 20;     // pairs per segment of b2a_batch_upload / b2a_batch_run ...
     uint64_t seg_resident_bytes = 60ull << 30;    // ... and its record bytes (a 1 M-pair batch with 4-bit deltas would need 110 GB)
-    // s_fill runs the fill kernels back to back; s_tb (higher priority) runs the tracebacks, so the
-    // latency-bound walk of segment k fills the issue slots the ALU-bound fill of segment k+1 leaves idle
+    // s_fill runs the fill kernels back to back; every lane has its own traceback stream, so the latency-bound
+    // walks of earlier launches fill the issue slots the ALU-bound fill of the current one leaves idle
     cudaStream_t s_copy = nullptr, s_down = nullptr, s_fill = nullptr;
     Lane lanes[MAX_LANES];
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
