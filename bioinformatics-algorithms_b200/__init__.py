@@ -30,7 +30,8 @@ RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<u4"), ("end_j", "<u4"), (
                          ("start_j", "<u4"), ("overlap", "<i4"), ("n_ops", "<u4"), ("path", "<u4")])
 
 EXPORTS = ["b2a_device_count", "b2a_create", "b2a_destroy", "b2a_last_error", "b2a_host_alloc", "b2a_host_free",
-           "b2a_host_register", "b2a_host_unregister", "b2a_align_batch", "b2a_align_batch_multi", "b2a_select_run", "b2a_affine_score_batch", "b2a_affine_align_batch", "b2a_affine_fetch_ops", "b2a_affine_star_scores", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
+           "b2a_host_register", "b2a_host_unregister", "b2a_align_batch", "b2a_align_batch_multi", "b2a_select_run",
+           "b2a_seq2_pack", "b2a_seq2_unpack", "b2a_align_batch_multi_seq2", "b2a_affine_score_batch", "b2a_affine_align_batch", "b2a_affine_fetch_ops", "b2a_affine_star_scores", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
            "b2a_batch_download", "b2a_batch_times", "b2a_set_option", "b2a_batch_stats", "b2a_render_cigar", "b2a_render_mdz", "b2a_select_best",
            "b2a_upgma_newick", "b2a_center_star_phylip",
            "b2a_microbench_int16x2", "b2a_debug_copy_record"]
@@ -39,6 +40,12 @@ EXPORTS = ["b2a_device_count", "b2a_create", "b2a_destroy", "b2a_last_error", "b
 class Params(C.Structure):
     _fields_ = [("mode", C.c_int32), ("match", C.c_int32), ("mismatch", C.c_int32), ("gap", C.c_int32),
                 ("flags", C.c_uint32)]
+
+
+class Seq2(C.Structure):
+    """b2a_seq2 (include/b2align.h): a concatenated byte buffer as 2-bit codes + an exception list."""
+    _fields_ = [("codes", C.c_void_p), ("n_bytes", C.c_uint64), ("alphabet", C.c_uint8 * 4), ("reserved", C.c_uint32),
+                ("exc_pos", C.c_void_p), ("exc_byte", C.c_void_p), ("n_exc", C.c_uint64)]
 
 
 class B2AError(RuntimeError):
@@ -67,6 +74,10 @@ def load_library():
         lib.b2a_align_batch.argtypes = [P, C.POINTER(Params), P, P, P, P, C.c_uint64, P]
         lib.b2a_align_batch_multi.argtypes = [P, C.POINTER(Params), C.c_uint32, P, P, P, P, C.c_uint64, P]
         lib.b2a_select_run.argtypes = [P, C.c_uint32]
+        lib.b2a_seq2_pack.restype = C.c_int64
+        lib.b2a_seq2_pack.argtypes = [P, C.c_uint64, P, P, P, P, C.c_uint64]
+        lib.b2a_seq2_unpack.argtypes = [C.POINTER(Seq2), C.c_uint64, C.c_uint64, P]
+        lib.b2a_align_batch_multi_seq2.argtypes = [P, C.POINTER(Params), C.c_uint32, C.POINTER(Seq2), P, C.POINTER(Seq2), P, C.c_uint64, P]
         lib.b2a_host_register.argtypes = [P, C.c_size_t]
         lib.b2a_host_unregister.argtypes = [P]
         lib.b2a_batch_upload.argtypes = [P, C.POINTER(Params), P, P, P, P, C.c_uint64]
@@ -107,6 +118,42 @@ def pack(seqs):
         np.cumsum([len(s) for s in seqs], out=off[1:])
     data = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy() if len(seqs) else np.zeros(0, np.uint8)
     return data, off
+
+
+class PackedSeq:
+    """Owner of the arrays a b2a_seq2 points to (b2a_seq2_pack); .c is the struct the C ABI takes."""
+
+    def __init__(self, data, alphabet=b"ACGT", pinned=False):
+        lib = load_library()
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        assert len(alphabet) == 4
+        alpha = (C.c_uint8 * 4)(*alphabet)
+        n = data.size
+        alloc = pinned_empty if pinned else (lambda k, dt: np.empty(max(k, 1), dtype=dt))
+        self.codes = alloc((n + 3) // 4, np.uint8)
+        n_exc = lib.b2a_seq2_pack(data.ctypes.data, n, alpha, None, None, None, 0)
+        if n_exc < 0:
+            raise B2AError("b2a_seq2_pack failed")
+        self.exc_pos = alloc(n_exc, np.uint64)
+        self.exc_byte = alloc(n_exc, np.uint8)
+        got = lib.b2a_seq2_pack(data.ctypes.data, n, alpha, self.codes.ctypes.data, self.exc_pos.ctypes.data,
+                                self.exc_byte.ctypes.data, n_exc)
+        if got != n_exc:
+            raise B2AError("b2a_seq2_pack failed")
+        self.n_bytes, self.n_exc = n, int(n_exc)
+        self.c = Seq2(self.codes.ctypes.data, n, alpha, 0, self.exc_pos.ctypes.data, self.exc_byte.ctypes.data, n_exc)
+
+    @property
+    def nbytes(self):
+        """bytes that cross PCIe for the whole buffer"""
+        return (self.n_bytes + 3) // 4 + 9 * self.n_exc
+
+    def unpack(self, first=0, count=None):
+        count = self.n_bytes - first if count is None else count
+        out = np.empty(max(count, 1), dtype=np.uint8)
+        if load_library().b2a_seq2_unpack(C.byref(self.c), first, count, out.ctypes.data) != 0:
+            raise B2AError("b2a_seq2_unpack failed")
+        return out[:count]
 
 
 def pinned_empty(n, dtype):
@@ -231,6 +278,17 @@ class Engine:
         ptrs = (C.c_void_p * len(modes))(*[r.ctypes.data for r in results])
         self._check(self.lib.b2a_align_batch_multi(self.ctx, prms, len(modes), pat.ctypes.data, pat_off.ctypes.data,
                                                    txt.ctypes.data, txt_off.ctypes.data, n, ptrs), "b2a_align_batch_multi")
+        return results
+
+    def align_seq2_multi(self, modes, pat2, pat_off, txt2, txt_off, match, mismatch, gap, want_ops=False, results=None):
+        """align_packed_multi over compact inputs (PackedSeq, b2a_align_batch_multi_seq2): a quarter of the upload, the same results."""
+        n = len(pat_off) - 1
+        if results is None:
+            results = [np.empty(n, dtype=RESULT_DTYPE) for _ in modes]
+        prms = (Params * len(modes))(*[Params(m, match, mismatch, gap, WANT_OPS if want_ops else 0) for m in modes])
+        ptrs = (C.c_void_p * len(modes))(*[r.ctypes.data for r in results])
+        self._check(self.lib.b2a_align_batch_multi_seq2(self.ctx, prms, len(modes), C.byref(pat2.c), pat_off.ctypes.data,
+                                                        C.byref(txt2.c), txt_off.ctypes.data, n, ptrs), "b2a_align_batch_multi_seq2")
         return results
 
     def select_run(self, run):

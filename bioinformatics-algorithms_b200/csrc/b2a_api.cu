@@ -190,6 +190,8 @@ struct b2a_ctx {
     DevBuf<uint32_t> d_hist;                      // 256 pattern-byte counts per segment
     DevBuf<uint8_t> d_dirty;                      // per pair-pair: a pattern byte outside the segment's 4 table symbols -> wide32 serves its pairs
     HostBuf<uint8_t> h_dirty;
+    // compact input (b2a_seq2): the codes and exception lists as they arrive, [0] patterns, [1] texts; expanded into d_pat / d_txt
+    struct Seq2Dev { DevBuf<uint8_t> codes, ebyte; DevBuf<uint64_t> epos; void release() { codes.release(); ebyte.release(); epos.release(); } } seq2[2];
     HostBuf<PPDesc> h_pps;
     HostBuf<uint64_t> h_code_off, h_ops_off;
     HostBuf<AlphaInfo> h_alpha;
@@ -206,6 +208,34 @@ int cuda_fail(b2a_ctx* c, cudaError_t e, const char* where) {
                 std::string(where) + ": " + cudaGetErrorString(e));
 }
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); } while (0)
+
+// ---- compact input (b2a_seq2): expand 2-bit codes to the byte buffer the kernels read --------------------------------------------------
+// One thread per 16-byte group of the OUTPUT (global group index, so the vector store is aligned whatever the segment's first byte is):
+// one 32-bit load of 16 codes, four PRMTs against the alphabet word, one 16-byte store.  Groups that straddle the segment's ends store
+// their bytes one by one: the neighbouring segment owns the rest (its bytes may already carry patched exceptions).  HBM-bound:
+// 0.25 + 1 bytes of traffic per base.
+__global__ void seq2_expand_kernel(const uint8_t* __restrict__ codes, uint8_t* __restrict__ out, uint64_t b0, uint64_t b1, uint32_t alphabet) {
+    const uint64_t g = b0 / 16 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t p = g * 16;
+    if (p >= b1) return;
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(codes + g * 4);
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t x = (w >> (8 * k)) & 0xFFu;                         // four codes -> four PRMT selector nibbles
+        const uint32_t sel = (x & 3u) | ((x & 0xCu) << 2) | ((x & 0x30u) << 4) | ((x & 0xC0u) << 6);
+        v[k] = __byte_perm(alphabet, 0u, sel);
+    }
+    if (p >= b0 && p + 16 <= b1) { *reinterpret_cast<uint4*>(out + p) = make_uint4(v[0], v[1], v[2], v[3]); return; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (p + k >= b0 && p + k < b1) out[p + k] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));
+}
+// ... and put the listed exceptions back
+__global__ void seq2_patch_kernel(uint8_t* __restrict__ out, const uint64_t* __restrict__ pos, const uint8_t* __restrict__ byte, uint64_t n) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[pos[e]] = byte[e];
+}
 
 // Histogram of the pattern bytes of a segment: hist[256] += counts of the bytes in [p, p+n)
 __global__ void alphabet_kernel(const uint8_t* __restrict__ p, uint64_t n, uint32_t* __restrict__ hist) {
@@ -869,9 +899,11 @@ bool is_pinned(const void* p) {
 // segment as soon as it is planned and returns the result records.  With pipelined == false the
 // batch ends up resident and planned; b2a_batch_run launches it.
 int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const uint8_t* pat, const uint64_t* pat_off,
-                  const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs, bool pipelined, b2a_result* const* results)
+                  const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs, bool pipelined, b2a_result* const* results,
+                  const b2a_seq2* pat2 = nullptr, const b2a_seq2* txt2 = nullptr)
 {
     if (!ctx) return B2A_ERR_ARG;
+    const bool compact = pat2 != nullptr;                          // b2a_seq2 inputs: pat / txt are null, the device expands the codes
     if (!prms || !pat_off || !txt_off || n_runs < 1 || n_runs > (uint32_t)MAX_RUNS)
         return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: null argument or bad run count");
     const b2a_params* prm = &prms[0];
@@ -911,7 +943,17 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
     ctx->cells = ctx->fill_bytes = ctx->launches = ctx->h2d = ctx->d2h = 0;
     ctx->n_pp_total = 0;
     const uint64_t pat_bytes = n_pairs ? pat_off[n_pairs] : 0, txt_bytes = n_pairs ? txt_off[n_pairs] : 0;
-    if ((pat_bytes && !pat) || (txt_bytes && !txt)) return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: null sequence buffer");
+    if (!compact && ((pat_bytes && !pat) || (txt_bytes && !txt))) return fail(ctx, B2A_ERR_ARG, "b2a_batch_upload: null sequence buffer");
+    const b2a_seq2* sq[2] = {pat2, txt2};
+    const uint64_t sq_bytes[2] = {pat_bytes, txt_bytes};
+    uint64_t sq_copied[2] = {0, 0}, sq_exc[2] = {0, 0};            // code bytes / exceptions already queued (segments ascend)
+    uint32_t sq_alpha[2] = {0, 0};
+    for (int w = 0; compact && w < 2; ++w) {
+        if (!sq[w]) return fail(ctx, B2A_ERR_ARG, "b2a_align_batch_multi_seq2: null b2a_seq2");
+        if (sq[w]->n_bytes < sq_bytes[w] || (sq_bytes[w] && !sq[w]->codes) || (sq[w]->n_exc && (!sq[w]->exc_pos || !sq[w]->exc_byte)))
+            return fail(ctx, B2A_ERR_ARG, "b2a_align_batch_multi_seq2: the b2a_seq2 is shorter than its offsets say, or lacks an array");
+        std::memcpy(&sq_alpha[w], sq[w]->alphabet, 4);
+    }
     // Appendix A.8: (m+n)*max|score| must stay inside int32 (beyond that the reference itself is undefined)
     const int64_t smag = std::max<int64_t>({std::llabs((long long)prm->match), std::llabs((long long)prm->mismatch),
                                             std::llabs((long long)prm->gap)});
@@ -931,6 +973,10 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
     ctx->alpha_slots = (size_t)(n_pairs / SEG_MIN_PAIRS + 3);        // >= segments + 1
     CU(ctx->d_pat.reserve(pat_bytes + 16)); CU(ctx->d_txt.reserve(txt_bytes + 16));
     CU(ctx->d_pat_off.reserve(n_pairs + 1)); CU(ctx->d_txt_off.reserve(n_pairs + 1));
+    for (int w = 0; compact && w < 2; ++w) {
+        CU(ctx->seq2[w].codes.reserve(sq_bytes[w] / 4 + 32));
+        if (sq[w]->n_exc) { CU(ctx->seq2[w].epos.reserve(sq[w]->n_exc)); CU(ctx->seq2[w].ebyte.reserve(sq[w]->n_exc)); }
+    }
     CU(ctx->d_pps.reserve(n_pairs)); CU(ctx->d_code_off.reserve(n_pairs));
     CU(ctx->h_pps.reserve(n_pairs)); CU(ctx->h_code_off.reserve(n_pairs)); CU(ctx->h_ops_off.reserve(n_pairs + 1));
     for (uint32_t r = 0; r < n_runs; ++r) {
@@ -996,11 +1042,39 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
         // ---- queue the copies of this segment's inputs ----
         cudaStream_t sc = ctx->s_copy;
         const uint64_t pb0 = pat_off[first], pb1 = pat_off[k], tb0 = txt_off[first], tb1 = txt_off[k];
-        if (pb1 > pb0) CU(cudaMemcpyAsync(ctx->d_pat.p + pb0, pat + pb0, pb1 - pb0, cudaMemcpyHostToDevice, sc));
-        if (tb1 > tb0) CU(cudaMemcpyAsync(ctx->d_txt.p + tb0, txt + tb0, tb1 - tb0, cudaMemcpyHostToDevice, sc));
+        const uint64_t sb0[2] = {pb0, tb0}, sb1[2] = {pb1, tb1};
+        uint64_t se0[2] = {0, 0}, se1[2] = {0, 0};                       // the segment's slice of each exception list
+        if (!compact) {
+            if (pb1 > pb0) CU(cudaMemcpyAsync(ctx->d_pat.p + pb0, pat + pb0, pb1 - pb0, cudaMemcpyHostToDevice, sc));
+            if (tb1 > tb0) CU(cudaMemcpyAsync(ctx->d_txt.p + tb0, txt + tb0, tb1 - tb0, cudaMemcpyHostToDevice, sc));
+            ctx->h2d += (pb1 - pb0) + (tb1 - tb0);
+        } else {
+            for (int w = 0; w < 2; ++w) {
+                // code bytes [copied, ceil(b1 / 4)): a byte shared with the previous segment went up with that one
+                const uint64_t c1 = (sb1[w] + 3) / 4;
+                if (c1 > sq_copied[w]) {
+                    CU(cudaMemcpyAsync(ctx->seq2[w].codes.p + sq_copied[w], sq[w]->codes + sq_copied[w], c1 - sq_copied[w], cudaMemcpyHostToDevice, sc));
+                    ctx->h2d += c1 - sq_copied[w];
+                    sq_copied[w] = c1;
+                }
+                uint64_t e = sq_exc[w];
+                se0[w] = e;
+                while (e < sq[w]->n_exc && sq[w]->exc_pos[e] < sb1[w]) {
+                    if (sq[w]->exc_pos[e] < sb0[w] || (e > se0[w] && sq[w]->exc_pos[e] <= sq[w]->exc_pos[e - 1]))
+                        return fail(ctx, B2A_ERR_ARG, "b2a_align_batch_multi_seq2: exception positions must ascend");
+                    ++e;
+                }
+                se1[w] = sq_exc[w] = e;
+                if (e > se0[w]) {
+                    CU(cudaMemcpyAsync(ctx->seq2[w].epos.p + se0[w], sq[w]->exc_pos + se0[w], (e - se0[w]) * 8, cudaMemcpyHostToDevice, sc));
+                    CU(cudaMemcpyAsync(ctx->seq2[w].ebyte.p + se0[w], sq[w]->exc_byte + se0[w], e - se0[w], cudaMemcpyHostToDevice, sc));
+                    ctx->h2d += (e - se0[w]) * 9;
+                }
+            }
+        }
         CU(cudaMemcpyAsync(ctx->d_pat_off.p + first, pat_off + first, (sg.count + 1) * 8, cudaMemcpyHostToDevice, sc));
         CU(cudaMemcpyAsync(ctx->d_txt_off.p + first, txt_off + first, (sg.count + 1) * 8, cudaMemcpyHostToDevice, sc));
-        ctx->h2d += (pb1 - pb0) + (tb1 - tb0) + 2 * (sg.count + 1) * 8;
+        ctx->h2d += 2 * (sg.count + 1) * 8;
 
         // ---- pass 2 (overlaps the copies): zip pairs of identical shape into pair-pairs, group by R ----
         for (auto& v : pps) v.clear();
@@ -1094,6 +1168,20 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
         // Pattern alphabet of the segment, found on the device.  NOT on the copy stream: a kernel there
         // queues behind the running traceback and stalls every later copy (measured: +25 % end to end).
         CU(cudaStreamWaitEvent(ctx->s_fill, ev[0], 0));
+        for (int w = 0; compact && w < 2; ++w) {                         // codes -> bytes in HBM, ahead of everything that reads the segment
+            if (sb1[w] == sb0[w]) continue;
+            uint8_t* out = w ? ctx->d_txt.p : ctx->d_pat.p;
+            const uint64_t groups = (sb1[w] + 15) / 16 - sb0[w] / 16;
+            seq2_expand_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, ctx->s_fill>>>(ctx->seq2[w].codes.p, out, sb0[w], sb1[w], sq_alpha[w]);
+            CU(cudaGetLastError());
+            ++launches;
+            if (se1[w] > se0[w]) {
+                const uint64_t ne = se1[w] - se0[w];
+                seq2_patch_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->s_fill>>>(out, ctx->seq2[w].epos.p + se0[w], ctx->seq2[w].ebyte.p + se0[w], ne);
+                CU(cudaGetLastError());
+                ++launches;
+            }
+        }
         if (pb1 > pb0) {
             const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count * 4u, (pb1 - pb0 + 4095) / 4096);
             alphabet_kernel<<<grid, 256, 0, ctx->s_fill>>>(ctx->d_pat.p + pb0, pb1 - pb0, ctx->d_hist.p + si * 256);
@@ -1270,6 +1358,7 @@ void b2a_destroy(b2a_ctx* ctx) {
     for (auto& ln : ctx->lanes) { if (ln.s_tb) cudaStreamDestroy(ln.s_tb); if (ln.s_tb_lo) cudaStreamDestroy(ln.s_tb_lo); }
     ctx->d_pat.release(); ctx->d_txt.release(); ctx->d_pat_off.release(); ctx->d_txt_off.release();
     ctx->d_code_off.release(); ctx->d_ops_off.release(); ctx->d_pps.release();
+    ctx->seq2[0].release(); ctx->seq2[1].release();
     ctx->d_alpha.release(); ctx->d_nops.release(); ctx->d_hist.release(); ctx->d_dirty.release(); ctx->h_dirty.release();
     for (auto& rb : ctx->run) rb.release();
     ctx->h_pps.release(); ctx->h_code_off.release(); ctx->h_ops_off.release(); ctx->h_alpha.release();
@@ -1372,6 +1461,14 @@ int b2a_align_batch_multi(b2a_ctx* ctx, const b2a_params* prm, uint32_t n_runs, 
                           const uint8_t* txt, const uint64_t* txt_off, uint64_t n_pairs, b2a_result* const* results)
 {
     return batch_prepare(ctx, prm, n_runs, pat, pat_off, txt, txt_off, n_pairs, true, results);
+}
+
+int b2a_align_batch_multi_seq2(b2a_ctx* ctx, const b2a_params* prm, uint32_t n_runs, const b2a_seq2* pat, const uint64_t* pat_off,
+                               const b2a_seq2* txt, const uint64_t* txt_off, uint64_t n_pairs, b2a_result* const* results)
+{
+    if (!ctx) return B2A_ERR_ARG;
+    if (!pat || !txt) return fail(ctx, B2A_ERR_ARG, "b2a_align_batch_multi_seq2: null b2a_seq2");
+    return batch_prepare(ctx, prm, n_runs, nullptr, pat_off, nullptr, txt_off, n_pairs, true, results, pat, txt);
 }
 
 int b2a_select_run(b2a_ctx* ctx, uint32_t run)

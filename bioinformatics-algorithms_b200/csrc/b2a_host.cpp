@@ -5,9 +5,11 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b2align.h"
@@ -197,4 +199,66 @@ extern "C" int64_t b2a_center_star_phylip(uint32_t n_seqs, uint32_t centre, cons
     std::memcpy(out, text.data(), text.size());
     out[text.size()] = 0;
     return (int64_t)text.size();
+}
+
+// ---- compact sequence input (b2a_seq2, include/b2align.h): host-side packer / unpacker --------------------------------------------
+// The reference holds sequences as std::string and compares raw bytes (hw2.cpp:142, :208); the 2-bit form is this engine's wire format
+// for them, lossless through the exception list.
+extern "C" int64_t b2a_seq2_pack(const uint8_t* seq, uint64_t n_bytes, const uint8_t alphabet[4],
+                                 uint8_t* codes, uint64_t* exc_pos, uint8_t* exc_byte, uint64_t exc_cap)
+{
+    if ((!seq && n_bytes) || !alphabet) return B2A_ERR_ARG;
+    if (exc_cap && (!exc_pos || !exc_byte)) return B2A_ERR_ARG;
+    uint8_t lut[256];
+    std::memset(lut, 0xFF, sizeof lut);
+    for (int c = 3; c >= 0; --c) lut[alphabet[c]] = (uint8_t)c;          // a repeated alphabet byte takes its lowest code
+    // slices of whole code bytes, one per thread; pass 1 counts the exceptions, pass 2 writes codes and exceptions at their offsets
+    const uint64_t quads = (n_bytes + 3) / 4;
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    if (const char* e = std::getenv("B2A_HOST_THREADS")) nt = (unsigned)std::max(1, std::atoi(e));
+    nt = (unsigned)std::min<uint64_t>(nt, std::max<uint64_t>(1, quads / 65536));
+    std::vector<uint64_t> cnt(nt + 1, 0);
+    auto slice = [&](unsigned t, uint64_t& b0, uint64_t& b1) {
+        b0 = std::min(n_bytes, quads * t / nt * 4); b1 = std::min(n_bytes, quads * (t + 1) / nt * 4);
+    };
+    auto run = [&](auto&& fn) {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(fn, t);
+        fn(0u);
+        for (auto& x : th) x.join();
+    };
+    run([&](unsigned t) {
+        uint64_t b0, b1, c = 0; slice(t, b0, b1);
+        for (uint64_t p = b0; p < b1; ++p) c += lut[seq[p]] == 0xFF;
+        cnt[t + 1] = c;
+    });
+    for (unsigned t = 0; t < nt; ++t) cnt[t + 1] += cnt[t];
+    run([&](unsigned t) {
+        uint64_t b0, b1, e = cnt[t]; slice(t, b0, b1);
+        for (uint64_t p = b0; p < b1; p += 4) {
+            uint32_t byte = 0;
+            const uint64_t lim = std::min<uint64_t>(4, b1 - p);
+            for (uint64_t k = 0; k < lim; ++k) {
+                uint32_t c = lut[seq[p + k]];
+                if (c == 0xFF) { if (e < exc_cap) { exc_pos[e] = p + k; exc_byte[e] = seq[p + k]; } ++e; c = 0; }
+                byte |= c << (2 * k);
+            }
+            if (codes) codes[p / 4] = (uint8_t)byte;
+        }
+    });
+    return (int64_t)cnt[nt];
+}
+
+extern "C" int b2a_seq2_unpack(const b2a_seq2* s, uint64_t first, uint64_t count, uint8_t* out)
+{
+    if (!s || (count && !out) || first > s->n_bytes || count > s->n_bytes - first) return B2A_ERR_ARG;
+    if (count && !s->codes) return B2A_ERR_ARG;
+    if (s->n_exc && (!s->exc_pos || !s->exc_byte)) return B2A_ERR_ARG;
+    for (uint64_t k = 0; k < count; ++k) {
+        const uint64_t p = first + k;
+        out[k] = s->alphabet[(s->codes[p / 4] >> (2 * (p % 4))) & 3u];
+    }
+    const uint64_t* lo = std::lower_bound(s->exc_pos, s->exc_pos + s->n_exc, first);
+    for (; lo != s->exc_pos + s->n_exc && *lo < first + count; ++lo) out[*lo - first] = s->exc_byte[lo - s->exc_pos];
+    return B2A_OK;
 }

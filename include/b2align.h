@@ -112,6 +112,36 @@ int b2a_align_batch_multi(b2a_ctx* ctx, const b2a_params* prm, uint32_t n_runs,
                           uint64_t n_pairs, b2a_result* const* results);
 int b2a_select_run(b2a_ctx* ctx, uint32_t run);
 
+/* ---- compact sequence input: 2 bits per base + an exception list (lossless) ----------------- */
+/* The reference keeps every sequence as a std::string and compares raw bytes (hw2.cpp:142, :208), so any byte may occur.  A b2a_seq2
+ * describes the SAME concatenated byte buffer `seq[0 .. n_bytes)` that b2a_align_batch takes, at a quarter of its size: byte p is
+ * alphabet[c] with c = bits 2*(p%4) .. 2*(p%4)+1 of codes[p/4], except at the positions listed in exc_pos (ascending), where it is
+ * exc_byte[] (an 'N' in a read, lower case, ...; the code stored there is 0).  Host->device traffic drops 4x; the device expands the
+ * buffer back to bytes in HBM (one HBM-bound kernel per segment, < 1 % of the step) and everything downstream is unchanged, so the
+ * results are those of the byte call bit for bit.  Offsets stay byte offsets. */
+typedef struct b2a_seq2 {
+    const uint8_t*  codes;        /* (n_bytes + 3) / 4 bytes                                        */
+    uint64_t        n_bytes;      /* bytes the buffer stands for (= off[n_pairs] of its offsets)     */
+    uint8_t         alphabet[4];  /* code c stands for byte alphabet[c]                              */
+    uint32_t        reserved;     /* 0                                                              */
+    const uint64_t* exc_pos;      /* n_exc ascending byte positions outside the alphabet ...         */
+    const uint8_t*  exc_byte;     /* ... and the bytes that stand there                              */
+    uint64_t        n_exc;
+} b2a_seq2;
+/* Host only, multi-threaded: packs seq[0 .. n_bytes) into codes ((n_bytes+3)/4 bytes) and lists the exceptions.  Returns the number
+ * of exceptions the buffer holds (>= 0) and writes the first min(that, exc_cap) of them (snprintf style: call with exc_cap = 0 to
+ * size the arrays, codes may then be NULL), or <0. */
+int64_t b2a_seq2_pack(const uint8_t* seq, uint64_t n_bytes, const uint8_t alphabet[4],
+                      uint8_t* codes, uint64_t* exc_pos, uint8_t* exc_byte, uint64_t exc_cap);
+/* Host only: bytes [first, first + count) of the buffer a b2a_seq2 stands for (e.g. the winner's pattern and text for
+ * b2a_render_mdz).  Returns B2A_OK or B2A_ERR_ARG. */
+int b2a_seq2_unpack(const b2a_seq2* s, uint64_t first, uint64_t count, uint8_t* out);
+/* b2a_align_batch_multi over compact inputs: same pairs, same results, a quarter of the upload. */
+int b2a_align_batch_multi_seq2(b2a_ctx* ctx, const b2a_params* prm, uint32_t n_runs,
+                               const b2a_seq2* pat, const uint64_t* pat_off,
+                               const b2a_seq2* txt, const uint64_t* txt_off,
+                               uint64_t n_pairs, b2a_result* const* results);
+
 /* After a batch run with B2A_WANT_OPS: traceback ops of one pair as ASCII 'M'/'D'/'I', in
  * TRACEBACK order (alignment end -> start, exactly the reference's `tracebacks` vector,
  * hw2.cpp:161).  Returns the op count, or <0.  ops_cap must be >= results[pair].n_ops. */

@@ -190,3 +190,32 @@ def test_hw3_cli_messages_match_reference(tmp_path):
             body = (tmp_path / "o.phy").read_bytes() if (tmp_path / "o.phy").exists() else None
             outs.append((p.returncode, p.stdout.replace(binary, "hw3"), p.stderr, body))
         assert outs[0] == outs[1], (args, outs)
+
+
+def test_seq2_pack_unpack_round_trip(monkeypatch):
+    """b2a_seq2 (the 2-bit wire format of b2a_align_batch_multi_seq2) is lossless: codes + exception list give back every byte, whatever the
+    thread count of the packer, the buffer length modulo 4 and the share of bytes outside the alphabet."""
+    rng = np.random.default_rng(12)
+    sym = np.frombuffer(b"ACGTNacgt-\x00\xff", np.uint8)
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("B2A_HOST_THREADS", threads)
+        for n in (0, 1, 2, 3, 4, 5, 63, 64, 1001, 262144 * 3 + 1):
+            for p_exc in (0.0, 0.01, 1.0):
+                w = np.array([1 - p_exc] * 4 + [p_exc] * 8) / (4 * (1 - p_exc) + 8 * p_exc)
+                d = sym[rng.choice(12, n, p=w)]
+                ps = pkg.PackedSeq(d)
+                assert np.array_equal(ps.unpack(), d)
+                inside = np.isin(d, sym[:4])
+                assert ps.n_exc == int((~inside).sum())
+                pos = ps.exc_pos[:ps.n_exc].astype(np.int64)
+                assert np.array_equal(pos, np.flatnonzero(~inside)) and np.array_equal(ps.exc_byte[:ps.n_exc], d[pos])
+                if n > 40:
+                    assert np.array_equal(ps.unpack(n // 3, 37), d[n // 3: n // 3 + 37])
+    # another alphabet order, and a repeated alphabet byte (takes its lowest code)
+    d = np.frombuffer(b"TTGACCAGTNAC", np.uint8)
+    assert np.array_equal(pkg.PackedSeq(d, alphabet=b"TGCA").unpack(), d)
+    assert np.array_equal(pkg.PackedSeq(d, alphabet=b"AACG").unpack(), d)
+    lib = pkg.load_library()
+    ps = pkg.PackedSeq(d)
+    assert lib.b2a_seq2_unpack(C.byref(ps.c), 5, 100, np.zeros(200, np.uint8).ctypes.data) == -1          # beyond the buffer
+    assert lib.b2a_seq2_pack(d.ctypes.data, d.size, None, None, None, None, 0) == -1

@@ -461,6 +461,62 @@ def test_multi_run_one_upload_equals_single_runs(eng):
             assert (int(single[mode][0]["score"][k]), single[mode][1][k]) == (a.score, a.ops)
 
 
+def test_seq2_inputs_equal_byte_inputs(eng):
+    """b2a_align_batch_multi_seq2 (2-bit codes + exception list, a quarter of the upload) returns the records and op lists of the byte
+    call bit for bit: ragged shapes (segment boundaries at every byte alignment), 'N' / lower case / NUL exceptions, short16 and wide32
+    pairs, many small segments, an alphabet that matches nothing; a few pairs also against the oracle."""
+    rng = random.Random(404)
+    pat, po, txt, to = workload.config2(9000, seed=17, n_rate=0.002)
+    ps, ts = workload.split(pat, po), workload.split(txt, to)
+    for _ in range(1500):
+        ps.append(bytes(rng.choice(b"ACGT") for _ in range(rng.randint(0, 170))))
+        ts.append(bytes(rng.choice(b"ACGTACGTACGTACGTNa\x00") for _ in range(rng.randint(0, 600))))
+    ps += [bytes(rng.choice(b"ACGT") for _ in range(800)), b"acgtnACGTRYKM" * 9]
+    ts += [bytes(rng.choice(b"ACGT") for _ in range(1100)), b"ACGNT" * 40]
+    order = list(range(len(ps))); rng.shuffle(order)
+    ps, ts = [ps[k] for k in order], [ts[k] for k in order]
+    pat, po = pkg.pack(ps); txt, to = pkg.pack(ts)
+    n = len(ps)
+    modes = [pkg.GLOBAL, pkg.LOCAL]
+    for alphabet, seg in ((b"ACGT", 0), (b"ACGT", 2048), (b"TGCA", 4096), (b"WXYZ", 0)):
+        p2, t2 = pkg.PackedSeq(pat, alphabet), pkg.PackedSeq(txt, alphabet, pinned=True)
+        assert (p2.n_exc > 0) and (t2.n_exc > 0)
+        if seg:
+            eng.set_option(pkg.OPT_SEG_PAIRS, seg); eng.set_option(pkg.OPT_SEG_FIRST, seg)
+        # the byte call under the same segmentation (which pairs share a pair-pair, hence `path`, depends on it)
+        want = [r.copy() for r in eng.align_packed_multi(modes, pat, po, txt, to, 1, -1, -1, want_ops=True)]
+        want_ops = []
+        for r in range(2):
+            eng.select_run(r)
+            want_ops.append(eng.copy_ops(n))
+        got = eng.align_seq2_multi(modes, p2, po, t2, to, 1, -1, -1, want_ops=True)
+        if seg:
+            eng.set_option(pkg.OPT_SEG_FIRST, 1 << 14); eng.set_option(pkg.OPT_SEG_PAIRS, 1 << 17)
+        st = eng.stats()
+        assert st["h2d_bytes"] < (pat.size + txt.size) // 2 or alphabet == b"WXYZ"
+        for r in range(2):
+            assert np.array_equal(got[r], want[r]), (alphabet, seg, r)
+            eng.select_run(r)
+            words, off = eng.copy_ops(n)
+            assert np.array_equal(off, want_ops[r][1]) and np.array_equal(words[:int(off[n])], want_ops[r][0][:int(off[n])]), (alphabet, seg, r)
+    for r, mode in enumerate(modes):
+        for k in list(range(0, n, 397)) + [n - 1]:
+            a = ob.align(mode, ps[k], ts[k], 1, -1, -1)
+            assert (int(want[r]["score"][k]), int(want[r]["overlap"][k]), pkg.unpack_ops(want_ops[r][0], want_ops[r][1], k, want[r]["n_ops"][k])) == \
+                   (a.score, a.overlap, a.ops), (mode, k)
+    # empty batch, and the argument errors: exception positions that do not ascend, a buffer shorter than the offsets say
+    e0 = pkg.PackedSeq(np.zeros(0, np.uint8))
+    assert len(eng.align_seq2_multi(modes, e0, np.zeros(1, np.uint64), e0, np.zeros(1, np.uint64), 1, -1, -1)[0]) == 0
+    p2, t2 = pkg.PackedSeq(pat), pkg.PackedSeq(txt)
+    t2.exc_pos[[0, 1]] = t2.exc_pos[[1, 0]]
+    with pytest.raises(pkg.B2AError):
+        eng.align_seq2_multi(modes, p2, po, t2, to, 1, -1, -1)
+    t2 = pkg.PackedSeq(txt[:-5])
+    with pytest.raises(pkg.B2AError):
+        eng.align_seq2_multi(modes, p2, po, t2, to, 1, -1, -1)
+    assert np.array_equal(eng.align_packed(pkg.GLOBAL, pat, po, txt, to, 1, -1, -1), want[0])           # the context survives the errors
+
+
 def test_fifth_pattern_symbol_stays_on_the_s16x2_path(eng):
     """0.1 % 'N' in the patterns (14 % of the 150-mers hold one): the pair-pairs with an 'N' are served by the 8-symbol s16x2 kernel (per-pair
     codes, XOR-selected score), nothing falls back to the int32 family, and every sampled pair equals the oracle in both modes.  Pairs whose
