@@ -12,6 +12,9 @@ one pass of the hot path over the batch in both modes.
                own P-pair batch (seed 481+rank): WEAK scaling, no data-path collective.
   e2e        = the same metric through b2a_align_batch_multi with HOST (pinned) buffers: ONE H2D of the
                sequences serving both modes, all kernels, D2H of both modes' result records, every step.
+  e2e_seq2   = e2e over compact host buffers (b2a_align_batch_multi_seq2: 2-bit codes + exception list, packed
+               once outside the timed region): a quarter of the H2D bytes, identical records.  The headline
+               e2e stays the byte-string call, since bytes are what the reference program holds.
   strong     = BASELINE.json configs[2]: the ONE seed-481 P-pair batch pair-sharded over the N ranks
                (rank r takes pairs [r P/N, (r+1) P/N)), device-resident and end to end.  The end-to-end
                figure includes the HOST GATHER and the winner selection (hw2.cpp:340-357): every rank's
@@ -351,13 +354,38 @@ def bench_c2(args):
     h2d, d2h, e2e_launches = st["h2d_bytes"], st["d2h_bytes"], st["launches"]
     for k, mode in enumerate(modes):
         assert np.array_equal(res_host[k], d["check"][mode]), "e2e and device-resident arms disagree"
-    eng.close()
     winners = [pkg.select_best(mode, res_host[k]) for k, mode in enumerate(modes)]
+
+    # ---- the same end to end over COMPACT host buffers (b2a_seq2: 2-bit codes + exception list, packed once outside the timed region) ----
+    t0 = time.perf_counter()
+    pat2, txt2 = pkg.PackedSeq(pat, pinned=True), pkg.PackedSeq(txt, pinned=True)
+    pack_s = time.perf_counter() - t0
+    for r in res_host:
+        r["score"] = -7
+    for _ in range(max(1, min(args.warmup, 2))):
+        eng.align_seq2_multi(modes, pat2, po, txt2, to, *SCORING, want_ops=True, results=res_host)
+    dev.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.align_seq2_multi(modes, pat2, po, txt2, to, *SCORING, want_ops=True, results=res_host)
+    dev.barrier()
+    seq2_s = max_over_ranks(time.perf_counter() - t0)
+    st2 = eng.stats()
+    for k, mode in enumerate(modes):
+        assert np.array_equal(res_host[k], d["check"][mode]), "the compact-input arm and the device-resident arm disagree"
+    e2e_seq2 = {"value": total_cells / seq2_s / 1e9, "unit": "GCUPS", "ms_per_step": seq2_s * 1e3 / args.steps,
+                "h2d_bytes_per_step": st2["h2d_bytes"], "d2h_bytes_per_step": st2["d2h_bytes"], "gpu_launches_per_step": st2["launches"],
+                "exceptions": pat2.n_exc + txt2.n_exc, "pack_ms_once": pack_s * 1e3,
+                "what": "b2a_align_batch_multi_seq2: the same pairs as 2-bit codes + exception list in pinned host memory (packed once by "
+                        "b2a_seq2_pack on the host, outside the timed region), expanded to bytes on the device per segment; records identical"}
+    del pat2, txt2
+    eng.close()
 
     # ---- strong (BASELINE configs[2]): the ONE seed-481 batch pair-sharded over the ranks, host gather + selection timed ----
     strong = None
     if world == 1:
         strong = {"value": value, "e2e": e2e_value, "ms_per_step": dev_s * 1e3 / args.steps, "e2e_ms_per_step": e2e_s * 1e3 / args.steps,
+                  "e2e_seq2": e2e_seq2["value"], "e2e_seq2_ms_per_step": e2e_seq2["ms_per_step"],
                   "pairs_total": n_pairs, "winners": winners, "note": "n_gpus = 1: the strong and the weak arm are the same run"}
     else:
         first, count = pair_range(n_pairs, rank, world)
@@ -387,10 +415,14 @@ def bench_c2(args):
         s_dev_s = max_over_ranks(sum(sd["tot_ms"].values()) * 1e-3)
         eng = pkg.Engine(local_rank)
         s_winners = None
+        spat2, stxt2 = pkg.PackedSeq(spat, pinned=True), pkg.PackedSeq(stxt, pinned=True)
 
-        def strong_step():
+        def strong_step(compact=False):
             nonlocal s_winners
-            eng.align_packed_multi(modes, spat, spo, stxt, sto, *SCORING, want_ops=True, results=mine)
+            if compact:
+                eng.align_seq2_multi(modes, spat2, spo, stxt2, sto, *SCORING, want_ops=True, results=mine)
+            else:
+                eng.align_packed_multi(modes, spat, spo, stxt, sto, *SCORING, want_ops=True, results=mine)
             if not dma_into_shared:
                 for k in range(2):
                     shared[k, first:first + count] = mine[k]
@@ -413,6 +445,17 @@ def bench_c2(args):
         dev.barrier()
         s_e2e_s = max_over_ranks(time.perf_counter() - t0)
         sst = eng.stats()
+        byte_winners = s_winners
+        for _ in range(max(1, min(args.warmup, 2))):
+            strong_step(True)
+        dev.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            strong_step(True)
+        dev.barrier()
+        s_seq2_s = max_over_ranks(time.perf_counter() - t0)
+        sst2 = eng.stats()
+        assert rank != 0 or s_winners == byte_winners, "compact and byte inputs pick different winners"
         # cross-check the gathered winner against the collective-free merge of per-rank winners (sharding.merge_best)
         merged = [merge_best(mode, mine[k], first)[0] for k, mode in enumerate(modes)]
         if rank == 0:
@@ -434,6 +477,8 @@ def bench_c2(args):
         strong = {"value": scells / s_dev_s / 1e9, "e2e": scells / s_e2e_s / 1e9, "ms_per_step": s_dev_s * 1e3 / args.steps,
                   "e2e_ms_per_step": s_e2e_s * 1e3 / args.steps, "pairs_total": n_pairs, "pairs_per_gpu": count, "winners": s_winners,
                   "h2d_bytes_per_step_per_gpu": sst["h2d_bytes"], "d2h_bytes_per_step_per_gpu": sst["d2h_bytes"],
+                  "e2e_seq2": scells / s_seq2_s / 1e9, "e2e_seq2_ms_per_step": s_seq2_s * 1e3 / args.steps,
+                  "e2e_seq2_h2d_bytes_per_step_per_gpu": sst2["h2d_bytes"],
                   "gather": ("every rank's D2H lands in its slice of one POSIX-shm host array pinned with b2a_host_register; every rank runs "
                              "b2a_select_best over its slice and posts (key, index); barrier; rank 0 takes the first strict maximum of the N "
                              "candidates in rank order -- all inside the timed region (checked afterwards against one serial scan of all records)")
@@ -489,7 +534,7 @@ def bench_c2(args):
                         "ms_per_step": e2e_s * 1e3 / args.steps, "gpu_launches_per_step": e2e_launches,
                         "returns": "32-byte result records of both modes (score, end/start cell, overlap, n_ops); the 2-bit op lists stay "
                                    "on the device for b2a_fetch_ops / b2a_copy_ops (about 0.3 GB per mode if all are fetched)"},
-                "strong": strong,
+                "e2e_seq2": e2e_seq2, "strong": strong,
                 "nw_fill_ms": fill_ms[0] / args.steps, "nw_tb_ms": tb_ms[0] / args.steps, "sw_fill_ms": fill_ms[1] / args.steps,
                 "sw_tb_ms": tb_ms[1] / args.steps, "nw_gcups": gc(tot_ms[0]), "sw_gcups": gc(tot_ms[1]),
                 "frac_fill": roofline["frac_fill"], "frac_step": roofline["frac_step"],
