@@ -136,6 +136,7 @@ struct RunBuf {
 
 constexpr int MAX_LANES = 8;
 constexpr int MAX_RUNS = B2A_MAX_RUNS;
+constexpr size_t DIRTY_CLASSES = 16;              // >= classes (distinct rows-per-lane values) of one segment
 constexpr uint64_t SEG_MIN_PAIRS = 2048;          // a segment is never closed below this many pairs
 
 } // namespace
@@ -190,6 +191,7 @@ struct b2a_ctx {
     DevBuf<uint32_t> d_hist;                      // 256 pattern-byte counts per segment
     DevBuf<uint8_t> d_dirty;                      // per pair-pair: a pattern byte outside the segment's 4 table symbols -> wide32 serves its pairs
     HostBuf<uint8_t> h_dirty;
+    DevBuf<uint32_t> d_dirty_list, d_dirty_cnt;   // per class of a segment: its flagged pair-pairs, compacted (dirty_compact_kernel); DIRTY_CLASSES counters per segment
     // compact input (b2a_seq2): the codes and exception lists as they arrive, [0] patterns, [1] texts; expanded into d_pat / d_txt
     struct Seq2Dev { DevBuf<uint8_t> codes, ebyte; DevBuf<uint64_t> epos; void release() { codes.release(); ebyte.release(); epos.release(); } } seq2[2];
     HostBuf<PPDesc> h_pps;
@@ -295,6 +297,21 @@ __global__ void dirty_kernel(const uint8_t* __restrict__ pat, const uint64_t* __
         }
     }
     dirty[pp] = bad ? 1 : 0;
+}
+// The flagged pair-pairs of one class, compacted: the 8-symbol kernel then runs FULL CTAs over list[0 .. *count) instead of one busy warp
+// per CTA scattered over the class (0.1 % 'N' in 150-mers flags 26 % of the pair-pairs).  The order of the list is whatever the atomics
+// give; every pair-pair keeps its own record, so results do not depend on it.
+__global__ void dirty_compact_kernel(const uint8_t* __restrict__ dirty, uint32_t n_pp, const AlphaInfo* __restrict__ info,
+                                     uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
+    if (!info->too_many) return;
+    const uint32_t pp = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool flagged = pp < n_pp && dirty[pp] == 1;
+    const uint32_t peers = __ballot_sync(0xFFFFFFFFu, flagged);
+    if (!peers) return;
+    uint32_t base = 0;
+    if ((threadIdx.x & 31u) == 0u) base = atomicAdd(count, (uint32_t)__popc(peers));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (flagged) list[base + (uint32_t)__popc(peers & ((1u << (threadIdx.x & 31u)) - 1u))] = pp;
 }
 void alpha_from_mask(AlphaInfo& a) {
     a.nsym = 0; a.too_many = 0;
@@ -680,7 +697,8 @@ int launch_segment(b2a_ctx* ctx, size_t si, int r, uint64_t* launches)
     CU(cudaStreamWaitEvent(st, ln.tb_done, 0));              // the previous user of this lane's record has been walked
     CU(cudaEventRecord(ev[1], st));
     const AlphaInfo* alpha = ctx->d_alpha.p + si;
-    for (const ClassRange& c : sg.classes) {
+    for (size_t ci = 0; ci < sg.classes.size(); ++ci) {
+        const ClassRange& c = sg.classes[ci];
         Short16Plan pl{0, 0, 0};
         short16_plan(mode, (uint32_t)c.R * 32u, c.max_n, prm.match, prm.mismatch, prm.gap, pl);   // bias for the class' largest shape
         FillArgs a{};
@@ -693,6 +711,8 @@ int launch_segment(b2a_ctx* ctx, size_t si, int r, uint64_t* launches)
         a.radix = 1u << ctx->K;
         a.alpha = alpha;
         a.dirty = ctx->d_dirty.p + sg.pp_first + c.first;
+        a.dirty_list = ctx->d_dirty_list.p + sg.pp_first + c.first;
+        a.dirty_cnt = ctx->d_dirty_cnt.p + si * DIRTY_CLASSES + ci;
         CU(launch_fill(ctx->K, c.R, local, a, st));
         *launches += 2;
     }
@@ -987,6 +1007,8 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
     }
     CU(ctx->d_alpha.reserve(ctx->alpha_slots)); CU(ctx->h_alpha.reserve(ctx->alpha_slots));
     CU(ctx->d_hist.reserve(ctx->alpha_slots * 256)); CU(ctx->d_dirty.reserve(n_pairs)); CU(ctx->h_dirty.reserve(n_pairs));
+    CU(ctx->d_dirty_list.reserve(n_pairs)); CU(ctx->d_dirty_cnt.reserve(ctx->alpha_slots * DIRTY_CLASSES));
+    CU(cudaMemsetAsync(ctx->d_dirty_cnt.p, 0, ctx->alpha_slots * DIRTY_CLASSES * sizeof(uint32_t), ctx->s_copy));
     if (want_ops) CU(ctx->d_ops_off.reserve(n_pairs + 1));
     CU(cudaMemsetAsync(ctx->d_alpha.p, 0, ctx->alpha_slots * sizeof(AlphaInfo), ctx->s_copy));
     CU(cudaMemsetAsync(ctx->d_hist.p, 0, ctx->alpha_slots * 256 * sizeof(uint32_t), ctx->s_copy));
@@ -1196,6 +1218,14 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
                                                                                   ctx->d_alpha.p + si, ctx->d_dirty.p + sg.pp_first);
             CU(cudaGetLastError());
             ++launches;
+            if (sg.classes.size() > DIRTY_CLASSES) return fail(ctx, B2A_ERR_STATE, "internal: more short16 classes than counters");
+            for (size_t ci = 0; ci < sg.classes.size(); ++ci) {          // exits at once as well
+                const ClassRange& c = sg.classes[ci];
+                dirty_compact_kernel<<<(c.count + 255) / 256, 256, 0, ctx->s_fill>>>(ctx->d_dirty.p + sg.pp_first + c.first, c.count, ctx->d_alpha.p + si,
+                                                                                       ctx->d_dirty_list.p + sg.pp_first + c.first, ctx->d_dirty_cnt.p + si * DIRTY_CLASSES + ci);
+                CU(cudaGetLastError());
+                ++launches;
+            }
         }
         if (ctx->trace) tr_host.push_back(ms_since(t_begin));
 
@@ -1359,7 +1389,7 @@ void b2a_destroy(b2a_ctx* ctx) {
     ctx->d_pat.release(); ctx->d_txt.release(); ctx->d_pat_off.release(); ctx->d_txt_off.release();
     ctx->d_code_off.release(); ctx->d_ops_off.release(); ctx->d_pps.release();
     ctx->seq2[0].release(); ctx->seq2[1].release();
-    ctx->d_alpha.release(); ctx->d_nops.release(); ctx->d_hist.release(); ctx->d_dirty.release(); ctx->h_dirty.release();
+    ctx->d_alpha.release(); ctx->d_nops.release(); ctx->d_hist.release(); ctx->d_dirty.release(); ctx->d_dirty_list.release(); ctx->d_dirty_cnt.release(); ctx->h_dirty.release();
     for (auto& rb : ctx->run) rb.release();
     ctx->h_pps.release(); ctx->h_code_off.release(); ctx->h_ops_off.release(); ctx->h_alpha.release();
     ctx->wide.release();

@@ -52,6 +52,8 @@ struct FillArgs {
     const AlphaInfo* alpha;     // device-resident: the (<= 4) table symbols of this segment
     uint8_t*        dirty;      // per pair-pair of this launch: 0 = the four table symbols cover its patterns (4-symbol kernel), 1 = they do
                                 // not: the 8-symbol kernel (A8) serves it, or raises it to 2 = more than 7 distinct pattern symbols: wide32
+    const uint32_t* dirty_list; // the pair-pairs with dirty == 1, compacted (dirty_compact_kernel): the 8-symbol kernel's warps take list[0 .. *dirty_cnt)
+    const uint32_t* dirty_cnt;
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -87,11 +89,12 @@ short16_fill_kernel(const FillArgs A)
     __shared__ uint8_t s_code[A8 ? FILL_WARPS : 1][2][A8 ? 256 : 1];   // A8: byte -> code of pair a / pair b
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t pp = blockIdx.x * FILL_WARPS + warp;
+    uint32_t pp = blockIdx.x * FILL_WARPS + warp;
     uint8_t sym[4] = {0, 0, 0, 0};
     if (A8) {
         if (!A.alpha->too_many) return;                  // uniform: the segment has no pair-pair outside its four symbols
-        if (pp >= A.n_pp || A.dirty[pp] != 1) return;    // warp-uniform
+        if (pp >= *A.dirty_cnt) return;                  // warp-uniform: the flagged pair-pairs are served in list order, full CTAs
+        pp = A.dirty_list[pp];
     } else {
         const int nsym = A.alpha->nsym;
 #pragma unroll
