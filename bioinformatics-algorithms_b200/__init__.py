@@ -31,7 +31,7 @@ RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<u4"), ("end_j", "<u4"), (
 
 EXPORTS = ["b2a_device_count", "b2a_create", "b2a_destroy", "b2a_last_error", "b2a_host_alloc", "b2a_host_free",
            "b2a_host_register", "b2a_host_unregister", "b2a_align_batch", "b2a_align_batch_multi", "b2a_select_run",
-           "b2a_seq2_pack", "b2a_seq2_unpack", "b2a_align_batch_multi_seq2", "b2a_affine_score_batch", "b2a_affine_align_batch", "b2a_affine_fetch_ops", "b2a_affine_star_scores", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
+           "b2a_seq2_pack", "b2a_seq2_unpack", "b2a_align_batch_multi_seq2", "b2a_find_anchors", "b2a_align_anchored", "b2a_affine_score_batch", "b2a_affine_align_batch", "b2a_affine_fetch_ops", "b2a_affine_star_scores", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
            "b2a_batch_download", "b2a_batch_times", "b2a_set_option", "b2a_batch_stats", "b2a_render_cigar", "b2a_render_mdz", "b2a_select_best",
            "b2a_upgma_newick", "b2a_center_star_phylip",
            "b2a_microbench_int16x2", "b2a_debug_copy_record"]
@@ -77,6 +77,10 @@ def load_library():
         lib.b2a_seq2_pack.restype = C.c_int64
         lib.b2a_seq2_pack.argtypes = [P, C.c_uint64, P, P, P, P, C.c_uint64]
         lib.b2a_seq2_unpack.argtypes = [C.POINTER(Seq2), C.c_uint64, C.c_uint64, P]
+        lib.b2a_find_anchors.restype = C.c_int64
+        lib.b2a_find_anchors.argtypes = [P, C.c_uint64, P, C.c_uint64, C.c_uint32, C.c_uint32, P, C.c_uint64]
+        lib.b2a_align_anchored.restype = C.c_int64
+        lib.b2a_align_anchored.argtypes = [P, C.POINTER(Params), P, C.c_uint64, P, C.c_uint64, P, C.c_uint64, P, P, C.c_uint64]
         lib.b2a_align_batch_multi_seq2.argtypes = [P, C.POINTER(Params), C.c_uint32, C.POINTER(Seq2), P, C.POINTER(Seq2), P, C.c_uint64, P]
         lib.b2a_host_register.argtypes = [P, C.c_size_t]
         lib.b2a_host_unregister.argtypes = [P]
@@ -154,6 +158,22 @@ class PackedSeq:
         if load_library().b2a_seq2_unpack(C.byref(self.c), first, count, out.ctypes.data) != 0:
             raise B2AError("b2a_seq2_unpack failed")
         return out[:count]
+
+
+ANCHOR_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("len", "<u4")])
+
+
+def find_anchors(pattern, text, k=16, spacing=256):
+    """b2a_find_anchors: chain of unique exact k-mer matches, ascending in both sequences (numpy record array i, j, len)."""
+    lib = load_library()
+    p = np.frombuffer(pattern, dtype=np.uint8) if isinstance(pattern, (bytes, bytearray)) else np.ascontiguousarray(pattern, dtype=np.uint8)
+    t = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, dtype=np.uint8)
+    cap = max(1, p.size // max(spacing, k, 1) + 2)
+    out = np.zeros(cap, dtype=ANCHOR_DTYPE)
+    got = lib.b2a_find_anchors(p.ctypes.data, p.size, t.ctypes.data, t.size, k, spacing, out.ctypes.data, cap)
+    if got < 0 or got > cap:
+        raise B2AError(f"b2a_find_anchors failed ({got})")
+    return out[:got]
 
 
 def pinned_empty(n, dtype):
@@ -290,6 +310,19 @@ class Engine:
         self._check(self.lib.b2a_align_batch_multi_seq2(self.ctx, prms, len(modes), C.byref(pat2.c), pat_off.ctypes.data,
                                                         C.byref(txt2.c), txt_off.ctypes.data, n, ptrs), "b2a_align_batch_multi_seq2")
         return results
+
+    def align_anchored(self, pattern, text, anchors, match, mismatch, gap, tie_hw4=False):
+        """b2a_align_anchored: global alignment through the given exact-match anchors -> (result record, ops bytes in traceback order)."""
+        p = np.frombuffer(pattern, dtype=np.uint8) if isinstance(pattern, (bytes, bytearray)) else np.ascontiguousarray(pattern, dtype=np.uint8)
+        t = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, dtype=np.uint8)
+        a = np.ascontiguousarray(anchors, dtype=ANCHOR_DTYPE)
+        prm = Params(GLOBAL, match, mismatch, gap, TIE_HW4 if tie_hw4 else 0)
+        res = np.zeros(1, dtype=RESULT_DTYPE)
+        cap = p.size + t.size + 1
+        buf = C.create_string_buffer(cap)
+        n = self._check(self.lib.b2a_align_anchored(self.ctx, C.byref(prm), p.ctypes.data, p.size, t.ctypes.data, t.size,
+                                                    a.ctypes.data, len(a), res.ctypes.data, buf, cap), "b2a_align_anchored")
+        return res[0], buf.raw[:n]
 
     def select_run(self, run):
         self._check(self.lib.b2a_select_run(self.ctx, int(run)), "b2a_select_run")

@@ -262,3 +262,142 @@ extern "C" int b2a_seq2_unpack(const b2a_seq2* s, uint64_t first, uint64_t count
     for (; lo != s->exc_pos + s->n_exc && *lo < first + count; ++lo) out[*lo - first] = s->exc_byte[lo - s->exc_pos];
     return B2A_OK;
 }
+
+// ---- seed-anchored global alignment (not in the reference's code, see include/b2align.h) ---------------------------
+// Built on the public batch call only: the stretches between anchors are ordinary pairs of b2a_align_batch.
+
+extern "C" int64_t b2a_find_anchors(const uint8_t* pattern, uint64_t m, const uint8_t* text, uint64_t n, uint32_t k, uint32_t spacing,
+                                    b2a_anchor* out, uint64_t cap)
+{
+    if ((!pattern && m) || (!text && n) || k == 0 || (cap && !out) || m > 0xFFFFFFF0ull || n > 0xFFFFFFF0ull) return B2A_ERR_ARG;
+    if (m < k || n < k) return 0;
+    // One open-addressing table per side: k-mer hash -> (first position, occurrences).  A k-mer is a candidate iff it occurs once on
+    // each side and the bytes agree.  Walking the pattern in order yields the candidates sorted by i (no sort of 1e5 records on the path).
+    // The table accesses are cache misses (4 MB per 100 kb side), so only a hash-selected 1/2 .. 1/16 of the k-mers is considered when
+    // the spacing leaves room for it (>= 32 candidates per kept anchor either way); a k-mer is selected on both sides or on neither.
+    struct Slot { uint64_t h; uint32_t pos, cnt; };
+    uint64_t smask = 0;
+    while (smask < 15 && (smask + 1) * 2 * 32 <= (uint64_t)spacing) smask = smask * 2 + 1;
+    const uint64_t B = 0x9E3779B97F4A7C15ull;
+    uint64_t top = 1;
+    for (uint32_t t = 1; t < k; ++t) top *= B;
+    auto roll = [&](const uint8_t* s, uint64_t len, auto&& visit) {           // visit(hash, position) for every k-mer, in order
+        uint64_t h = 0;
+        for (uint32_t t = 0; t < k; ++t) h = h * B + (s[t] + 1u);
+        visit(h, (uint32_t)0);
+        for (uint64_t p = 1; p + k <= len; ++p) {
+            h = (h - (s[p - 1] + 1u) * top) * B + (s[p + k - 1] + 1u);
+            visit(h, (uint32_t)p);
+        }
+    };
+    struct Table {
+        std::vector<Slot> slots; int shift = 0;
+        void init(uint64_t n_keys) { int bits = 4; while ((1ull << bits) < 2 * n_keys) ++bits; shift = 64 - bits; slots.assign(1ull << bits, Slot{0, 0, 0}); }
+        Slot& find(uint64_t h) {
+            const uint64_t mask = slots.size() - 1;
+            for (uint64_t x = (h * 0xD6E8FEB86659FD93ull) >> shift;; x = (x + 1) & mask) { Slot& sl = slots[x]; if (sl.cnt == 0 || sl.h == h) return sl; }
+        }
+    };
+    Table tp_, tt_;
+    auto build = [&](Table& tb, const uint8_t* s, uint64_t len) {
+        uint64_t selected = 0;                                               // exact, so the table can never fill up
+        roll(s, len, [&](uint64_t h, uint32_t) { selected += ((h >> 24) & smask) == 0; });
+        tb.init(selected + 1);
+        roll(s, len, [&](uint64_t h, uint32_t pos) { if ((h >> 24) & smask) return; Slot& sl = tb.find(h); if (sl.cnt++ == 0) { sl.h = h; sl.pos = pos; } });
+    };
+    {
+        std::thread th([&]() { build(tp_, pattern, m); });
+        build(tt_, text, n);
+        th.join();
+    }
+    std::vector<b2a_anchor> cand;
+    roll(pattern, m, [&](uint64_t h, uint32_t pos) {
+        if (((h >> 24) & smask) || tp_.find(h).cnt != 1) return;
+        const Slot& st = tt_.find(h);
+        if (st.cnt == 1 && std::memcmp(pattern + pos, text + st.pos, k) == 0) cand.push_back(b2a_anchor{pos, st.pos, k});
+    });
+    // longest chain with strictly increasing j (patience sorting with predecessor links); i ascends strictly already
+    std::vector<uint32_t> tail, prev(cand.size(), 0xFFFFFFFFu);
+    for (uint32_t c = 0; c < cand.size(); ++c) {
+        auto it = std::lower_bound(tail.begin(), tail.end(), cand[c].j, [&](uint32_t t, uint32_t j) { return cand[t].j < j; });
+        if (it != tail.begin()) prev[c] = *(it - 1);
+        if (it == tail.end()) tail.push_back(c); else *it = c;
+    }
+    std::vector<b2a_anchor> chain;
+    for (uint32_t c = tail.empty() ? 0xFFFFFFFFu : tail.back(); c != 0xFFFFFFFFu; c = prev[c]) chain.push_back(cand[c]);
+    std::reverse(chain.begin(), chain.end());
+    // thin: consecutive anchors start >= max(spacing, k) pattern bases apart and do not overlap in the text either
+    uint64_t kept = 0;
+    b2a_anchor last{0, 0, 0};
+    for (const b2a_anchor& a : chain) {
+        if (kept && (a.i < last.i + std::max(spacing, k) || a.j < last.j + last.len)) continue;
+        if (kept < cap) out[kept] = a;
+        last = a; ++kept;
+    }
+    return (int64_t)kept;
+}
+
+extern "C" int64_t b2a_align_anchored(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pattern, uint64_t m, const uint8_t* text, uint64_t n,
+                                      const b2a_anchor* anchors, uint64_t n_anchors, b2a_result* result, char* ops, uint64_t ops_cap)
+{
+    if (!ctx || !prm || !result || (!pattern && m) || (!text && n) || (n_anchors && !anchors)) return B2A_ERR_ARG;
+    if (prm->mode != B2A_MODE_GLOBAL || m + n >= 0x7FFFFFF0ull) return B2A_ERR_ARG;
+    // stretch s = what lies between anchor s-1 and anchor s (n_anchors + 1 stretches, some possibly empty)
+    const uint64_t ns = n_anchors + 1;
+    uint64_t pi = 0, tj = 0, anchored = 0;
+    for (uint64_t s = 0; s < n_anchors; ++s) {
+        const b2a_anchor& a = anchors[s];
+        if (a.i < pi || a.j < tj || (uint64_t)a.i + a.len > m || (uint64_t)a.j + a.len > n || a.len == 0 ||
+            std::memcmp(pattern + a.i, text + a.j, a.len) != 0) return B2A_ERR_ARG;
+        pi = (uint64_t)a.i + a.len; tj = (uint64_t)a.j + a.len; anchored += a.len;
+    }
+    // pair s of the batch = stretch s: the stretches copied back to back (the anchors' bytes are left out: an exact match needs no DP)
+    std::vector<uint8_t> pb, tb;
+    pb.reserve(m - anchored); tb.reserve(n - anchored);
+    std::vector<uint64_t> spo(ns + 1, 0), sto(ns + 1, 0);
+    pi = 0; tj = 0;
+    for (uint64_t s = 0; s < ns; ++s) {
+        const uint64_t pe = s < n_anchors ? anchors[s].i : m, te = s < n_anchors ? anchors[s].j : n;
+        pb.insert(pb.end(), pattern + pi, pattern + pe); tb.insert(tb.end(), text + tj, text + te);
+        spo[s + 1] = pb.size(); sto[s + 1] = tb.size();
+        if (s < n_anchors) { pi = pe + anchors[s].len; tj = te + anchors[s].len; }
+    }
+    b2a_params q = *prm;
+    q.flags = (q.flags & B2A_TIE_HW4) | B2A_WANT_OPS;
+    std::vector<b2a_result> res(ns);
+    int rc = b2a_align_batch(ctx, &q, pb.data(), spo.data(), tb.data(), sto.data(), ns, res.data());
+    if (rc != B2A_OK) return rc;
+    const int64_t nw = b2a_copy_ops(ctx, nullptr, 0, nullptr);
+    if (nw < 0) return nw;
+    std::vector<uint32_t> words((size_t)nw + 1);
+    std::vector<uint64_t> woff(ns + 1);
+    const int64_t got = b2a_copy_ops(ctx, words.data(), (uint64_t)nw, woff.data());
+    if (got < 0) return got;
+    // assemble in TRACEBACK order (alignment end -> start): last stretch first, each stretch's own list as it is, anchors as runs of 'M'
+    b2a_result r{};
+    int64_t score = (int64_t)prm->match * (int64_t)anchored;
+    uint64_t nops = 0;
+    static const char L[4] = {'M', 'D', 'I', '?'};
+    auto put = [&](char c) { if (ops && nops < ops_cap) ops[nops] = c; ++nops; };
+    for (uint64_t s = ns; s-- > 0;) {
+        const uint32_t* w = words.data() + woff[s];
+        for (uint32_t t = 0; t < res[s].n_ops; ++t) put(L[(w[t >> 4] >> (2 * (t & 15))) & 3u]);
+        score += res[s].score;
+        if (s > 0) for (uint32_t t = 0; t < anchors[s - 1].len; ++t) put('M');
+    }
+    // overlapLongestExactMatch over the whole alignment (hw2.cpp:267-278), from the op list in alignment order; hw4's distance with B2A_TIE_HW4
+    int best = 0, cur = 0; uint64_t i = 0, j = 0, mism = 0, gaps = 0;
+    if (ops && nops <= ops_cap) {
+        for (uint64_t t = nops; t-- > 0;) {
+            const char c = ops[t];
+            if (c == 'M') { const bool eq = pattern[i] == text[j]; cur = (eq && pattern[i] != '-') ? cur + 1 : 0; mism += !eq; ++i; ++j; }
+            else { cur = 0; ++gaps; if (c == 'D') ++i; else ++j; }
+            best = std::max(best, cur);
+        }
+        r.overlap = (prm->flags & B2A_TIE_HW4) ? (int32_t)(mism + gaps) : best;
+    } else r.overlap = -1;                                   // not computed without the op list
+    r.score = (int32_t)score; r.end_i = (uint32_t)m; r.end_j = (uint32_t)n; r.start_i = 0; r.start_j = 0;
+    r.n_ops = (uint32_t)nops; r.path = 3;
+    *result = r;
+    return (int64_t)nops;
+}

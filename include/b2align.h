@@ -231,6 +231,27 @@ int64_t b2a_center_star_phylip(uint32_t n_seqs, uint32_t centre, const char* con
                                const uint8_t* const* seqs, const uint64_t* seq_len,
                                const char* const* ops, const uint64_t* n_ops, char* out, uint64_t cap);
 
+/* ---- seed-anchored global alignment of one long pair ------------------------------------- */
+/* Not in the reference's code: its report ("Performance Bottlenecks") names banded / seed-anchored alignment as the way out of the
+ * O(mn) matrices of hw2.cpp:119-120.  An anchor is an exact match pattern[i .. i+len) == text[j .. j+len) (0-based).  The anchored
+ * alignment is the global alignment CONSTRAINED to contain every anchor as a run of 'M' columns: the stretches between consecutive
+ * anchors (and before the first / after the last) are independent Needleman-Wunsch problems with hw2's recurrences and tie order
+ * (hw2.cpp:118-190), which the engine runs as ONE batch; score = sum of the stretch scores + match * sum(len).  m*n cells shrink to
+ * sum(m_s * n_s).  The result is optimal among alignments through the anchors; it equals hw2's unconstrained score whenever some
+ * optimal alignment passes through them (tests compare both). */
+typedef struct b2a_anchor { uint32_t i, j, len; } b2a_anchor;
+/* Host only.  Candidate anchors = k-mers that occur exactly once in the pattern and exactly once in the text (verified byte-wise);
+ * the longest chain increasing in both coordinates is kept, thinned so that consecutive anchors start at least `spacing` pattern
+ * bases apart and never overlap.  Returns the number of anchors of the chain (>= 0) and writes the first min(that, cap), or <0. */
+int64_t b2a_find_anchors(const uint8_t* pattern, uint64_t m, const uint8_t* text, uint64_t n, uint32_t k, uint32_t spacing,
+                         b2a_anchor* out, uint64_t cap);
+/* prm->mode must be B2A_MODE_GLOBAL.  anchors must ascend strictly in i and j without overlapping (as b2a_find_anchors returns them)
+ * and be exact matches (checked: B2A_ERR_ARG otherwise).  result receives one record (overlap = longest exact-match run of the whole
+ * alignment, hw2.cpp:267-278; path = 3); ops (may be NULL) receives the op list, ASCII 'M'/'D'/'I' in traceback order like
+ * b2a_fetch_ops, at most ops_cap characters.  Returns the op count or <0.  The context's last batch is replaced. */
+int64_t b2a_align_anchored(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pattern, uint64_t m, const uint8_t* text, uint64_t n,
+                           const b2a_anchor* anchors, uint64_t n_anchors, b2a_result* result, char* ops, uint64_t ops_cap);
+
 /* ---- measurement helper: sustained issue rate of the packed int16x2 DPX instructions ------- */
 /* Runs the microbenchmark kernel on ctx's device; *gops = 1e9 lane-instructions/s sustained by
  * kind 0: VIADDMNMX.S16x2 only, 1: the fill kernel's ALU mix, 2: ALU mix + IMAD (both pipes). */

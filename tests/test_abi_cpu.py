@@ -219,3 +219,38 @@ def test_seq2_pack_unpack_round_trip(monkeypatch):
     ps = pkg.PackedSeq(d)
     assert lib.b2a_seq2_unpack(C.byref(ps.c), 5, 100, np.zeros(200, np.uint8).ctypes.data) == -1          # beyond the buffer
     assert lib.b2a_seq2_pack(d.ctypes.data, d.size, None, None, None, None, 0) == -1
+
+
+def test_find_anchors_chain_properties():
+    """b2a_find_anchors (host only): every anchor is an exact match, the chain ascends strictly in both sequences without
+    overlaps, respects the spacing, and degenerate inputs give an empty chain instead of an error."""
+    rng = random.Random(9)
+    base = bytes(rng.choice(b"ACGT") for _ in range(30000))
+    mut = bytearray()
+    for ch in base:
+        r = rng.random()
+        if r < 0.01:
+            continue
+        if r < 0.02:
+            mut.append(rng.choice(b"ACGT"))
+        mut.append(rng.choice(b"ACGT") if rng.random() < 0.06 else ch)
+    mut = bytes(mut)
+    for k, spacing in ((12, 64), (16, 256), (20, 1000), (16, 1)):
+        a = pkg.find_anchors(mut, base, k, spacing)
+        assert len(a) > 30000 // max(spacing, 3 * k) // 4
+        for x in a:
+            assert mut[x["i"]:x["i"] + x["len"]] == base[x["j"]:x["j"] + x["len"]] and x["len"] == k
+        i, j = a["i"].astype(np.int64), a["j"].astype(np.int64)
+        assert np.all(np.diff(i) >= max(spacing, k)) and np.all(np.diff(j) >= k)
+    assert len(pkg.find_anchors(b"ACGT", base, 16, 64)) == 0                       # shorter than k
+    assert len(pkg.find_anchors(b"", b"", 16, 64)) == 0
+    assert len(pkg.find_anchors(b"ACGT" * 500, b"ACGT" * 400, 16, 64)) == 0        # no unique k-mer
+    assert len(pkg.find_anchors(base[:5000], bytes(rng.choice(b"ACGT") for _ in range(5000)), 16, 64)) == 0    # unrelated sequences
+    # a reversed block cannot be chained with its surroundings: the chain stays monotone
+    t2 = base[:10000] + base[20000:30000] + base[10000:20000]
+    a = pkg.find_anchors(base, t2, 16, 128)
+    assert np.all(np.diff(a["j"].astype(np.int64)) > 0) and len(a) > 50
+    lib = pkg.load_library()
+    assert lib.b2a_find_anchors(None, 10, None, 10, 16, 1, None, 0) == -1
+    assert lib.b2a_find_anchors(base, 100, base, 100, 0, 1, None, 0) == -1
+    assert lib.b2a_align_anchored(None, None, None, 0, None, 0, None, 0, None, None, 0) == -1

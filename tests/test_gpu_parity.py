@@ -517,6 +517,76 @@ def test_seq2_inputs_equal_byte_inputs(eng):
     assert np.array_equal(eng.align_packed(pkg.GLOBAL, pat, po, txt, to, 1, -1, -1), want[0])           # the context survives the errors
 
 
+def oracle_anchored(p, t, anchors, s):
+    """The constrained alignment restated with the (pinned) per-pair oracle: every stretch between anchors is hw2's NW, anchors are runs
+    of 'M'.  Returns (score, ops in traceback order, overlapLongestExactMatch of the whole alignment)."""
+    parts, score, pi, tj = [], 0, 0, 0
+    for x in list(anchors) + [None]:
+        pe, te = (int(x["i"]), int(x["j"])) if x is not None else (len(p), len(t))
+        a = ob.align(ob.GLOBAL, p[pi:pe], t[tj:te], *s)
+        score += a.score
+        parts.append(a.ops)
+        if x is not None:
+            parts.append(b"M" * int(x["len"]))
+            score += s[0] * int(x["len"])
+            pi, tj = pe + int(x["len"]), te + int(x["len"])
+    ops = b"".join(reversed(parts))
+    best = cur = i = j = 0
+    for op in reversed(ops):
+        if op == 0x4D:
+            cur = cur + 1 if (p[i] == t[j] and p[i] != 0x2D) else 0
+            i += 1; j += 1
+        else:
+            cur = 0
+            if op == 0x44:
+                i += 1
+            else:
+                j += 1
+        best = max(best, cur)
+    return score, ops, best
+
+
+def test_anchored_alignment_equals_oracle_composition(eng):
+    """SURVEY 8 f4 (not in the reference's code): b2a_align_anchored = hw2's NW on every stretch between exact-match anchors, run as one
+    batch.  Equal to the composition of per-stretch oracle alignments (score, op list byte for byte, longest exact-match run); never above
+    hw2's unconstrained score and equal to it on lightly diverged pairs; argument errors are reported, not executed."""
+    rng = random.Random(31)
+    for n, psub, k, spacing, s in ((3000, 0.05, 12, 100, (1, -1, -1)), (6000, 0.08, 16, 300, (2, -3, -4)), (2500, 0.02, 16, 64, (1, -1, -1)),
+                                   (4000, 0.30, 10, 50, (1, -1, -1)), (1500, 0.0, 16, 200, (5, -4, -16))):
+        t = rnd(rng, n)
+        p = mutate(rng, t, psub=psub, pindel=0.01)
+        anchors = pkg.find_anchors(p, t, k, spacing)
+        res, ops = eng.align_anchored(p, t, anchors, *s)
+        score, wops, best = oracle_anchored(p, t, anchors, s)
+        assert (int(res["score"]), ops, int(res["overlap"]), int(res["n_ops"]), int(res["path"])) == (score, wops, best, len(wops), 3), (n, psub, len(anchors))
+        assert (int(res["end_i"]), int(res["end_j"]), int(res["start_i"]), int(res["start_j"])) == (len(p), len(t), 0, 0)
+        full = ob.align(ob.GLOBAL, p, t, *s)
+        assert score <= full.score
+        if psub <= 0.05:
+            assert score == full.score, (n, psub, score, full.score)
+    # no anchors at all = the plain global alignment; hw4's tie order is passed through to the stretches
+    t = rnd(rng, 700); p = mutate(rng, t)
+    res, ops = eng.align_anchored(p, t, np.zeros(0, pkg.ANCHOR_DTYPE), 1, -1, -1)
+    full = ob.align(ob.GLOBAL, p, t, 1, -1, -1)
+    assert (int(res["score"]), ops, int(res["overlap"])) == (full.score, full.ops, full.overlap)
+    res, ops = eng.align_anchored(p, t, np.zeros(0, pkg.ANCHOR_DTYPE), 1, -1, -1, tie_hw4=True)
+    sc4, dist4, ops4 = ob.hw4_nw(p, t, 1, -1, -1)
+    assert (int(res["score"]), int(res["overlap"]), ops) == (sc4, dist4, ops4)
+    # errors: an anchor that is not an exact match, anchors out of order, local mode
+    anchors = pkg.find_anchors(p, t, 12, 50).copy()
+    assert len(anchors) >= 2
+    bad = anchors.copy(); bad["j"][0] += 1
+    with pytest.raises(pkg.B2AError):
+        eng.align_anchored(p, t, bad, 1, -1, -1)
+    with pytest.raises(pkg.B2AError):
+        eng.align_anchored(p, t, anchors[::-1], 1, -1, -1)
+    lib = pkg.load_library()
+    prm = pkg.Params(pkg.LOCAL, 1, -1, -1, 0)
+    out = np.zeros(1, pkg.RESULT_DTYPE)
+    pa, ta = np.frombuffer(p, np.uint8), np.frombuffer(t, np.uint8)
+    assert lib.b2a_align_anchored(eng.ctx, C.byref(prm), pa.ctypes.data, pa.size, ta.ctypes.data, ta.size, None, 0, out.ctypes.data, None, 0) == -1
+
+
 def test_fifth_pattern_symbol_stays_on_the_s16x2_path(eng):
     """0.1 % 'N' in the patterns (14 % of the 150-mers hold one): the pair-pairs with an 'N' are served by the 8-symbol s16x2 kernel (per-pair
     codes, XOR-selected score), nothing falls back to the int32 family, and every sampled pair equals the oracle in both modes.  Pairs whose
