@@ -93,6 +93,8 @@ int main(int argc, char** argv)
         if (ndev <= 0) { std::cerr << "Error: no usable CUDA device (this build has no CPU alignment path)" << std::endl; return 1; }
         if ((uint64_t)ndev > n_pairs) ndev = (int)n_pairs;
         if (!all_gpus) ndev = (int)std::max(1.0, std::min((double)ndev, cells / 1e12));
+        const char* pin_env = std::getenv("HW2_PIN");
+        const bool pin = pin_env != nullptr && std::atoi(pin_env) != 0;
         std::vector<Shard> shards(ndev);
         std::vector<b2a_ctx*> ctxs(ndev, nullptr);
         std::vector<std::thread> th;
@@ -109,9 +111,17 @@ int main(int argc, char** argv)
                 std::vector<uint64_t> po(s.count + 1), to(s.count + 1);
                 for (uint64_t k = 0; k <= s.count; ++k) { po[k] = pats.off[s.first + k] - pats.off[s.first]; to[k] = txts.off[s.first + k] - txts.off[s.first]; }
                 b2a_params prm{mode, match, mismatch, gap, B2A_WANT_OPS};
+                // HW2_PIN=1: page-lock the shard's slices of the loader's buffers, so that the segment copies run at PCIe speed instead of
+                // being staged.  Opt-in: locking 1.2 GB costs 0.24 s, and the copies hide under the kernels either way (profiles/r02_cli_pinning.log)
+                void* pin_p[3] = {pats.data + pats.off[s.first], txts.data + txts.off[s.first], results.data() + s.first};
+                const size_t pin_n[3] = {(size_t)po[s.count], (size_t)to[s.count], (size_t)s.count * sizeof(b2a_result)};
+                bool pinned[3] = {false, false, false};
+                for (int q = 0; q < 3 && pin; ++q) pinned[q] = pin_n[q] >= (1u << 20) && b2a_host_register(pin_p[q], pin_n[q]) == B2A_OK;
+                if (d == 0) stamp("buffers pinned");
                 s.rc = b2a_align_batch(ctx, &prm, pats.data + pats.off[s.first], po.data(),
                                        txts.data + txts.off[s.first], to.data(), s.count, results.data() + s.first);
                 if (s.rc != B2A_OK) s.err = b2a_last_error(ctx);
+                for (int q = 0; q < 3; ++q) if (pinned[q]) b2a_host_unregister(pin_p[q]);
             });
         }
         for (auto& t : th) t.join();

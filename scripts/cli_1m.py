@@ -15,7 +15,9 @@ workload.write_fasta(pf, pat, po, b"p"); workload.write_fasta(tf, txt, to, b"t")
 print(f"wrote FASTA ({os.path.getsize(pf) + os.path.getsize(tf)} bytes) in {time.perf_counter() - t0:.1f} s", flush=True)
 os.environ["HW2_TIMING"] = "1"
 os.environ["B2A_TRACE"] = "0"
-for flag in ("-g", "-l"):
+for flag, pin in (("-g", "0"), ("-g", "1"), ("-l", "0"), ("-l", "1")):
+    os.environ["HW2_PIN"] = pin
+    print("---- HW2_PIN =", pin, flush=True)
     for it in range(3):
         t0 = time.perf_counter()
         subprocess.check_call([pkg.HW2_BIN, flag, "-p", pf, "-t", tf, "-o", os.path.join(d, "cli_out.txt"), "-s", "1", "-1", "-1"])
