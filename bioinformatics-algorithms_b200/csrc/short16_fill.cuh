@@ -21,7 +21,8 @@
 // SW stays in H space: its per-row maximum and its floor at 0 do not survive the transform.
 // Every 3 words a lane stores one 16-byte chunk {w0,w1,w2,anchor} per row at chunk index (c*32 + lane)*R + r
 // (b2a_format.h: consecutive DP rows are 16 bytes apart, which is what the traceback wants); the R stores of a warp
-// fill 512R contiguous bytes between them.
+// fill 512R contiguous bytes between them.  (Cache hints on these stores -- st.cs, st.wt, st.cg -- change nothing: 2-bit and 4-bit
+// deltas, NW and SW, all within 0.2 %, profiles/r02_store_hints.log.  The 4-bit record's cost is its word bookkeeping, twice per 24 steps.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
