@@ -973,6 +973,11 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
         if (sq[w]->n_bytes < sq_bytes[w] || (sq_bytes[w] && !sq[w]->codes) || (sq[w]->n_exc && (!sq[w]->exc_pos || !sq[w]->exc_byte)))
             return fail(ctx, B2A_ERR_ARG, "b2a_align_batch_multi_seq2: the b2a_seq2 is shorter than its offsets say, or lacks an array");
         std::memcpy(&sq_alpha[w], sq[w]->alphabet, 4);
+        // The offsets need not start at 0: a caller that shards ONE packed buffer over several contexts hands each of them the same
+        // b2a_seq2 and its own slice of the offsets; only the slice's codes and exceptions are copied and expanded.
+        const uint64_t base = n_pairs ? (w ? txt_off[0] : pat_off[0]) : 0;
+        sq_copied[w] = base / 4;
+        sq_exc[w] = (uint64_t)(std::lower_bound(sq[w]->exc_pos, sq[w]->exc_pos + sq[w]->n_exc, base) - sq[w]->exc_pos);
     }
     // Appendix A.8: (m+n)*max|score| must stay inside int32 (beyond that the reference itself is undefined)
     const int64_t smag = std::max<int64_t>({std::llabs((long long)prm->match), std::llabs((long long)prm->mismatch),

@@ -136,7 +136,9 @@ int64_t b2a_seq2_pack(const uint8_t* seq, uint64_t n_bytes, const uint8_t alphab
 /* Host only: bytes [first, first + count) of the buffer a b2a_seq2 stands for (e.g. the winner's pattern and text for
  * b2a_render_mdz).  Returns B2A_OK or B2A_ERR_ARG. */
 int b2a_seq2_unpack(const b2a_seq2* s, uint64_t first, uint64_t count, uint8_t* out);
-/* b2a_align_batch_multi over compact inputs: same pairs, same results, a quarter of the upload. */
+/* b2a_align_batch_multi over compact inputs: same pairs, same results, a quarter of the upload.  As in every batch call the offsets
+ * need not start at 0: several contexts (one per GPU) can share ONE b2a_seq2 pair and take consecutive slices off + first of the
+ * offsets arrays; each context copies and expands only the bytes its slice covers. */
 int b2a_align_batch_multi_seq2(b2a_ctx* ctx, const b2a_params* prm, uint32_t n_runs,
                                const b2a_seq2* pat, const uint64_t* pat_off,
                                const b2a_seq2* txt, const uint64_t* txt_off,

@@ -504,6 +504,15 @@ def test_seq2_inputs_equal_byte_inputs(eng):
             a = ob.align(mode, ps[k], ts[k], 1, -1, -1)
             assert (int(want[r]["score"][k]), int(want[r]["overlap"][k]), pkg.unpack_ops(want_ops[r][0], want_ops[r][1], k, want[r]["n_ops"][k])) == \
                    (a.score, a.overlap, a.ops), (mode, k)
+    # sharding without repacking: a slice of the offsets (absolute, not rebased) over the SAME packed buffers gives that slice of the records
+    p2, t2 = pkg.PackedSeq(pat), pkg.PackedSeq(txt)
+    for a, b in ((0, n // 3), (n // 3, n // 3 + 1), (n // 3 + 1, n - 7), (n - 7, n)):
+        sub = eng.align_seq2_multi(modes, p2, po[a:b + 1].copy(), t2, to[a:b + 1].copy(), 1, -1, -1, want_ops=True)
+        byt = eng.align_packed_multi(modes, pat, po[a:b + 1].copy(), txt, to[a:b + 1].copy(), 1, -1, -1)
+        assert eng.stats()["h2d_bytes"] < 2 * (int(po[b] - po[a]) + int(to[b] - to[a])) + 64 * (b - a) + 4096
+        for r in range(2):
+            for f in ("score", "end_i", "end_j", "start_i", "start_j", "overlap", "n_ops"):      # `path` depends on which pairs share a pair-pair
+                assert np.array_equal(sub[r][f], want[r][f][a:b]) and np.array_equal(byt[r][f], want[r][f][a:b]), (a, b, r, f)
     # empty batch, and the argument errors: exception positions that do not ascend, a buffer shorter than the offsets say
     e0 = pkg.PackedSeq(np.zeros(0, np.uint8))
     assert len(eng.align_seq2_multi(modes, e0, np.zeros(1, np.uint64), e0, np.zeros(1, np.uint64), 1, -1, -1)[0]) == 0
