@@ -15,6 +15,8 @@ one pass of the hot path over the batch in both modes.
   e2e_seq2   = e2e over compact host buffers (b2a_align_batch_multi_seq2: 2-bit codes + exception list, packed
                once outside the timed region): a quarter of the H2D bytes, identical records.  The headline
                e2e stays the byte-string call, since bytes are what the reference program holds.
+  e2e_all_ops = e2e with every pair's traceback op list of both modes delivered to pinned host memory as well
+               (b2a_set_ops_sink), i.e. all of struct AlignmentResult for all pairs, not only the records.
   strong     = BASELINE.json configs[2]: the ONE seed-481 P-pair batch pair-sharded over the N ranks
                (rank r takes pairs [r P/N, (r+1) P/N)), device-resident and end to end.  The end-to-end
                figure includes the HOST GATHER and the winner selection (hw2.cpp:340-357): every rank's
@@ -356,6 +358,31 @@ def bench_c2(args):
         assert np.array_equal(res_host[k], d["check"][mode]), "e2e and device-resident arms disagree"
     winners = [pkg.select_best(mode, res_host[k]) for k, mode in enumerate(modes)]
 
+    # ---- end to end with EVERY pair's op list delivered to pinned host memory too (b2a_set_ops_sink: copied per segment under the kernels) ----
+    off_all, ops_total = eng.ops_offsets(n_pairs)
+    sinks = [pkg.pinned_empty(ops_total, np.uint32) for _ in range(2)]
+    eng.set_ops_sink(sinks)
+    for _ in range(max(1, min(args.warmup, 2))):
+        eng.align_packed_multi(modes, pat, po, txt, to, *SCORING, want_ops=True, results=res_host)
+    dev.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.align_packed_multi(modes, pat, po, txt, to, *SCORING, want_ops=True, results=res_host)
+    dev.barrier()
+    ops_s = max_over_ranks(time.perf_counter() - t0)
+    st_ops = eng.stats()
+    eng.set_ops_sink(None)
+    for k, mode in enumerate(modes):                             # a sampled op list re-scores to the reported score
+        for q in range(0, n_pairs, max(1, n_pairs // 50)):
+            o = np.frombuffer(pkg.unpack_ops(sinks[k], off_all, q, res_host[k]["n_ops"][q]), np.uint8)
+            nm = int((o == 0x4D).sum())
+            assert len(o) == int(res_host[k]["n_ops"][q]) and int(res_host[k]["end_i"][q]) - int(res_host[k]["start_i"][q]) == nm + int((o == 0x44).sum())
+    e2e_all_ops = {"value": total_cells / ops_s / 1e9, "unit": "GCUPS", "ms_per_step": ops_s * 1e3 / args.steps,
+                   "h2d_bytes_per_step": st_ops["h2d_bytes"], "d2h_bytes_per_step": st_ops["d2h_bytes"],
+                   "what": "the byte-input e2e with the 2-bit op lists of ALL pairs of both modes copied to pinned host memory as well "
+                           "(b2a_set_ops_sink: per segment, under the kernels of the next segments): everything struct AlignmentResult carries, for every pair"}
+    del sinks
+
     # ---- the same end to end over COMPACT host buffers (b2a_seq2: 2-bit codes + exception list, packed once outside the timed region) ----
     t0 = time.perf_counter()
     pat2, txt2 = pkg.PackedSeq(pat, pinned=True), pkg.PackedSeq(txt, pinned=True)
@@ -534,7 +561,7 @@ def bench_c2(args):
                         "ms_per_step": e2e_s * 1e3 / args.steps, "gpu_launches_per_step": e2e_launches,
                         "returns": "32-byte result records of both modes (score, end/start cell, overlap, n_ops); the 2-bit op lists stay "
                                    "on the device for b2a_fetch_ops / b2a_copy_ops (about 0.3 GB per mode if all are fetched)"},
-                "e2e_seq2": e2e_seq2, "strong": strong,
+                "e2e_seq2": e2e_seq2, "e2e_all_ops": e2e_all_ops, "strong": strong,
                 "nw_fill_ms": fill_ms[0] / args.steps, "nw_tb_ms": tb_ms[0] / args.steps, "sw_fill_ms": fill_ms[1] / args.steps,
                 "sw_tb_ms": tb_ms[1] / args.steps, "nw_gcups": gc(tot_ms[0]), "sw_gcups": gc(tot_ms[1]),
                 "frac_fill": roofline["frac_fill"], "frac_step": roofline["frac_step"],

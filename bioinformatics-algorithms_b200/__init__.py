@@ -31,7 +31,7 @@ RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<u4"), ("end_j", "<u4"), (
 
 EXPORTS = ["b2a_device_count", "b2a_create", "b2a_destroy", "b2a_last_error", "b2a_host_alloc", "b2a_host_free",
            "b2a_host_register", "b2a_host_unregister", "b2a_align_batch", "b2a_align_batch_multi", "b2a_select_run",
-           "b2a_seq2_pack", "b2a_seq2_unpack", "b2a_align_batch_multi_seq2", "b2a_find_anchors", "b2a_align_anchored", "b2a_affine_score_batch", "b2a_affine_align_batch", "b2a_affine_fetch_ops", "b2a_affine_star_scores", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
+           "b2a_seq2_pack", "b2a_seq2_unpack", "b2a_align_batch_multi_seq2", "b2a_find_anchors", "b2a_align_anchored", "b2a_set_ops_sink", "b2a_affine_score_batch", "b2a_affine_align_batch", "b2a_affine_fetch_ops", "b2a_affine_star_scores", "b2a_fetch_ops", "b2a_copy_ops", "b2a_batch_upload", "b2a_batch_run",
            "b2a_batch_download", "b2a_batch_times", "b2a_set_option", "b2a_batch_stats", "b2a_render_cigar", "b2a_render_mdz", "b2a_select_best",
            "b2a_upgma_newick", "b2a_center_star_phylip",
            "b2a_microbench_int16x2", "b2a_debug_copy_record"]
@@ -77,6 +77,7 @@ def load_library():
         lib.b2a_seq2_pack.restype = C.c_int64
         lib.b2a_seq2_pack.argtypes = [P, C.c_uint64, P, P, P, P, C.c_uint64]
         lib.b2a_seq2_unpack.argtypes = [C.POINTER(Seq2), C.c_uint64, C.c_uint64, P]
+        lib.b2a_set_ops_sink.argtypes = [P, P, C.c_uint32, C.c_uint64]
         lib.b2a_find_anchors.restype = C.c_int64
         lib.b2a_find_anchors.argtypes = [P, C.c_uint64, P, C.c_uint64, C.c_uint32, C.c_uint32, P, C.c_uint64]
         lib.b2a_align_anchored.restype = C.c_int64
@@ -323,6 +324,22 @@ class Engine:
         n = self._check(self.lib.b2a_align_anchored(self.ctx, C.byref(prm), p.ctypes.data, p.size, t.ctypes.data, t.size,
                                                     a.ctypes.data, len(a), res.ctypes.data, buf, cap), "b2a_align_anchored")
         return res[0], buf.raw[:n]
+
+    def set_ops_sink(self, buffers):
+        """b2a_set_ops_sink: uint32 arrays (one per run, pinned for asynchronous copies) that receive the op words of the next batch calls
+        segment by segment; None switches it off.  The arrays must stay alive while the sink is set."""
+        if not buffers:
+            self._sink = None
+            return self._check(self.lib.b2a_set_ops_sink(self.ctx, None, 0, 0), "b2a_set_ops_sink")
+        self._sink = list(buffers)
+        ptrs = (C.c_void_p * len(buffers))(*[b.ctypes.data for b in buffers])
+        self._check(self.lib.b2a_set_ops_sink(self.ctx, ptrs, len(buffers), min(b.size for b in buffers)), "b2a_set_ops_sink")
+
+    def ops_offsets(self, n_pairs):
+        """per-pair word offsets of the last batch's op lists (n_pairs + 1 entries) and the total word count"""
+        off = np.empty(n_pairs + 1, dtype=np.uint64)
+        total = self._check(self.lib.b2a_copy_ops(self.ctx, None, 0, off.ctypes.data), "b2a_copy_ops")
+        return off, total
 
     def select_run(self, run):
         self._check(self.lib.b2a_select_run(self.ctx, int(run)), "b2a_select_run")

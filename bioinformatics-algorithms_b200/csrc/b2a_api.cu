@@ -171,6 +171,9 @@ struct b2a_ctx {
     b2a_params prm{};                             // scoring + flags of the batch; prm.mode = mode of run 0
     RunBuf run[MAX_RUNS];
     uint32_t n_runs = 1, sel_run = 0;             // sel_run: the run b2a_fetch_ops / b2a_copy_ops / b2a_batch_download read
+    uint32_t* ops_sink[MAX_RUNS] = {};            // b2a_set_ops_sink: host buffers the op words of run r are copied to segment by segment
+    uint32_t ops_sink_runs = 0;
+    uint64_t ops_sink_cap = 0;
     uint64_t n_launched = 0;                      // (segment, run) launches so far: they alternate over the lanes
     uint64_t n_pairs = 0;
     int K = 0;
@@ -1020,6 +1023,7 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
     if (n_pairs) CU(cudaMemsetAsync(ctx->d_dirty.p, 0, n_pairs, ctx->s_copy));
     bool async_down = pipelined && results;
     for (uint32_t r = 0; r < n_runs && async_down; ++r) async_down = is_pinned(results[r]);
+    const bool sink = pipelined && want_ops && ctx->ops_sink_runs >= n_runs;      // op lists go to the host per segment, under the kernels
     uint64_t launches = 0;
     using clk = std::chrono::steady_clock;
     const clk::time_point t_begin = clk::now();
@@ -1238,11 +1242,19 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
             for (uint32_t r = 0; r < n_runs; ++r) {              // every run's kernels follow the ONE upload of the segment
                 int rc = launch_segment(ctx, si, (int)r, &launches);
                 if (rc != B2A_OK) return rc;
-                if (async_down && !sg.classes.empty()) {
+                if ((async_down || sink) && !sg.classes.empty()) {
                     cudaEvent_t* evr = seg_events(ctx, si, (int)r);
                     CU(cudaStreamWaitEvent(ctx->s_down, evr[3], 0));
+                }
+                if (async_down && !sg.classes.empty()) {
                     CU(cudaMemcpyAsync(results[r] + first, ctx->run[r].d_results.p + first, sg.count * sizeof(b2a_result), cudaMemcpyDeviceToHost, ctx->s_down));
                     ctx->d2h += sg.count * sizeof(b2a_result);
+                }
+                if (sink && !sg.classes.empty()) {
+                    const uint64_t w0 = ctx->h_ops_off.p[first];                  // the segment's words: [w0, opsw)
+                    if (opsw > ctx->ops_sink_cap) return fail(ctx, B2A_ERR_ARG, "b2a_set_ops_sink: the op lists of this batch do not fit the sink");
+                    CU(cudaMemcpyAsync(ctx->ops_sink[r] + w0, ctx->run[r].d_ops.p + w0, (opsw - w0) * 4, cudaMemcpyDeviceToHost, ctx->s_down));
+                    ctx->d2h += (opsw - w0) * 4;
                 }
             }
         }
@@ -1316,6 +1328,12 @@ int batch_prepare(b2a_ctx* ctx, const b2a_params* prms, uint32_t n_runs, const u
         for (uint32_t r = 0; r < n_runs; ++r)
             CU(cudaMemcpyAsync(results[r], ctx->run[r].d_results.p, n_pairs * sizeof(b2a_result), cudaMemcpyDeviceToHost, ctx->s_down));
         ctx->d2h = n_runs * n_pairs * sizeof(b2a_result);
+    }
+    if (sink && !ctx->wide_pairs.empty()) {                      // wide32 wrote its pairs' op lists after the segments were copied
+        if (opsw > ctx->ops_sink_cap) return fail(ctx, B2A_ERR_ARG, "b2a_set_ops_sink: the op lists of this batch do not fit the sink");
+        for (uint32_t r = 0; r < n_runs; ++r)
+            CU(cudaMemcpyAsync(ctx->ops_sink[r], ctx->run[r].d_ops.p, opsw * 4, cudaMemcpyDeviceToHost, ctx->s_down));
+        ctx->d2h += n_runs * opsw * 4;
     }
     CU(cudaStreamSynchronize(ctx->s_down));
     if (ctx->trace) {
@@ -1504,6 +1522,16 @@ int b2a_align_batch_multi_seq2(b2a_ctx* ctx, const b2a_params* prm, uint32_t n_r
     if (!ctx) return B2A_ERR_ARG;
     if (!pat || !txt) return fail(ctx, B2A_ERR_ARG, "b2a_align_batch_multi_seq2: null b2a_seq2");
     return batch_prepare(ctx, prm, n_runs, nullptr, pat_off, nullptr, txt_off, n_pairs, true, results, pat, txt);
+}
+
+int b2a_set_ops_sink(b2a_ctx* ctx, uint32_t* const* ops_words, uint32_t n_runs, uint64_t cap_words)
+{
+    if (!ctx || n_runs > (uint32_t)MAX_RUNS) return B2A_ERR_ARG;
+    ctx->ops_sink_runs = 0; ctx->ops_sink_cap = 0;
+    if (!ops_words || n_runs == 0) return B2A_OK;
+    for (uint32_t r = 0; r < n_runs; ++r) { if (!ops_words[r]) return fail(ctx, B2A_ERR_ARG, "b2a_set_ops_sink: null buffer"); ctx->ops_sink[r] = ops_words[r]; }
+    ctx->ops_sink_runs = n_runs; ctx->ops_sink_cap = cap_words;
+    return B2A_OK;
 }
 
 int b2a_select_run(b2a_ctx* ctx, uint32_t run)

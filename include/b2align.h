@@ -155,6 +155,13 @@ int64_t b2a_fetch_ops(b2a_ctx* ctx, uint64_t pair, char* ops, uint64_t ops_cap);
  * ops_words == NULL to query it. */
 int64_t b2a_copy_ops(b2a_ctx* ctx, uint32_t* ops_words, uint64_t cap_words, uint64_t* ops_off);
 
+/* Optional: have the NEXT b2a_align_batch / _multi / _multi_seq2 calls (with B2A_WANT_OPS) also deliver every pair's op list to host
+ * memory, copied segment by segment under the kernels of the following segments instead of in one b2a_copy_ops afterwards.
+ * ops_words[r] (cap_words 32-bit words each; pinned memory makes the copies asynchronous) receives run r's words in exactly the
+ * b2a_copy_ops layout; the per-pair offsets come from b2a_copy_ops(ctx, NULL, 0, ops_off) after the call.  A batch whose op words
+ * (sum over pairs of (m + n + 15) / 16 + 1) exceed cap_words fails with B2A_ERR_ARG.  NULL / n_runs = 0 switches the sink off. */
+int b2a_set_ops_sink(b2a_ctx* ctx, uint32_t* const* ops_words, uint32_t n_runs, uint64_t cap_words);
+
 /* ---- device-resident variant (kernel-only timing; inputs already in HBM) ------------------- */
 int b2a_batch_upload(b2a_ctx* ctx, const b2a_params* prm,
                      const uint8_t* pat, const uint64_t* pat_off,
@@ -249,8 +256,8 @@ int64_t b2a_find_anchors(const uint8_t* pattern, uint64_t m, const uint8_t* text
                          b2a_anchor* out, uint64_t cap);
 /* prm->mode must be B2A_MODE_GLOBAL.  anchors must ascend strictly in i and j without overlapping (as b2a_find_anchors returns them)
  * and be exact matches (checked: B2A_ERR_ARG otherwise).  result receives one record (overlap = longest exact-match run of the whole
- * alignment, hw2.cpp:267-278; path = 3); ops (may be NULL) receives the op list, ASCII 'M'/'D'/'I' in traceback order like
- * b2a_fetch_ops, at most ops_cap characters.  Returns the op count or <0.  The context's last batch is replaced. */
+ * alignment, hw2.cpp:267-278; path = 3); ops (may be NULL: overlap is then -1, as it is when ops_cap is too small) receives the op list, ASCII
+ * 'M'/'D'/'I' in traceback order like b2a_fetch_ops, at most ops_cap characters.  Returns the op count or <0.  The context's last batch is replaced. */
 int64_t b2a_align_anchored(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pattern, uint64_t m, const uint8_t* text, uint64_t n,
                            const b2a_anchor* anchors, uint64_t n_anchors, b2a_result* result, char* ops, uint64_t ops_cap);
 

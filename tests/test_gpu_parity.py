@@ -526,6 +526,52 @@ def test_seq2_inputs_equal_byte_inputs(eng):
     assert np.array_equal(eng.align_packed(pkg.GLOBAL, pat, po, txt, to, 1, -1, -1), want[0])           # the context survives the errors
 
 
+def test_ops_sink_delivers_the_op_lists_of_every_run(eng):
+    """b2a_set_ops_sink: the op words of every run arrive in host memory segment by segment during the batch call and equal what
+    b2a_copy_ops returns afterwards -- short16 segments, a batch that also holds wide32 pairs (their lists are written after the
+    segments), byte and compact inputs; a sink that is too small is an error; switching the sink off restores the old behaviour."""
+    rng = random.Random(5)
+    pat, po, txt, to = workload.config2(20000, seed=5)
+    ps, ts = workload.split(pat, po), workload.split(txt, to)
+    modes = [pkg.GLOBAL, pkg.LOCAL]
+    for with_wide in (False, True):
+        if with_wide:
+            ps = ps + [rnd(rng, 700), rnd(rng, 90, b"ACGTNRYKMSWB")]; ts = ts + [rnd(rng, 900), rnd(rng, 400)]
+        pat, po = pkg.pack(ps); txt, to = pkg.pack(ts)
+        n = len(ps)
+        eng.set_option(pkg.OPT_SEG_PAIRS, 4096); eng.set_option(pkg.OPT_SEG_FIRST, 2048)
+        eng.set_ops_sink(None)
+        ref = eng.align_packed_multi(modes, pat, po, txt, to, 1, -1, -1, want_ops=True)
+        off, total = eng.ops_offsets(n)
+        want = []
+        for r in range(2):
+            eng.select_run(r)
+            want.append(eng.copy_ops(n)[0][:total].copy())
+        sink = [pkg.pinned_empty(total + 5, np.uint32) for _ in range(2)]
+        for compact in (False, True):
+            for b in sink:
+                b[:] = 0xFFFFFFFF
+            eng.set_ops_sink(sink)
+            if compact:
+                got = eng.align_seq2_multi(modes, pkg.PackedSeq(pat), po, pkg.PackedSeq(txt), to, 1, -1, -1, want_ops=True)
+            else:
+                got = eng.align_packed_multi(modes, pat, po, txt, to, 1, -1, -1, want_ops=True)
+            for r in range(2):
+                assert np.array_equal(got[r], ref[r])
+                for k in list(range(0, n, 97)) + [n - 2, n - 1]:             # the words a pair's list occupies (the rest of its slot is never written)
+                    w = (int(ref[r]["n_ops"][k]) + 15) // 16
+                    assert np.array_equal(sink[r][int(off[k]):int(off[k]) + w], want[r][int(off[k]):int(off[k]) + w]), (with_wide, compact, r, k)
+                    assert pkg.unpack_ops(sink[r], off, k, ref[r]["n_ops"][k]) == pkg.unpack_ops(want[r], off, k, ref[r]["n_ops"][k])
+                assert np.all(sink[r][total:] == 0xFFFFFFFF)
+        eng.set_ops_sink([s_[:total - 1] for s_ in sink])
+        with pytest.raises(pkg.B2AError):
+            eng.align_packed_multi(modes, pat, po, txt, to, 1, -1, -1, want_ops=True)
+        eng.set_ops_sink(None)
+        eng.set_option(pkg.OPT_SEG_FIRST, 1 << 14); eng.set_option(pkg.OPT_SEG_PAIRS, 1 << 17)
+    a = ob.align(ob.LOCAL, ps[-1], ts[-1], 1, -1, -1)
+    assert pkg.unpack_ops(sink[1], off, n - 1, ref[1]["n_ops"][n - 1]) == a.ops
+
+
 def oracle_anchored(p, t, anchors, s):
     """The constrained alignment restated with the (pinned) per-pair oracle: every stretch between anchors is hw2's NW, anchors are runs
     of 'M'.  Returns (score, ops in traceback order, overlapLongestExactMatch of the whole alignment)."""
