@@ -364,6 +364,7 @@ extern "C" int64_t b2a_align_anchored(b2a_ctx* ctx, const b2a_params* prm, const
     }
     b2a_params q = *prm;
     q.flags = (q.flags & B2A_TIE_HW4) | B2A_WANT_OPS;
+    b2a_set_ops_sink(ctx, nullptr, 0, 0);                     // the stretches' op lists are this call's own business, not the caller's sink's
     std::vector<b2a_result> res(ns);
     int rc = b2a_align_batch(ctx, &q, pb.data(), spo.data(), tb.data(), sto.data(), ns, res.data());
     if (rc != B2A_OK) return rc;

@@ -257,7 +257,8 @@ int64_t b2a_find_anchors(const uint8_t* pattern, uint64_t m, const uint8_t* text
 /* prm->mode must be B2A_MODE_GLOBAL.  anchors must ascend strictly in i and j without overlapping (as b2a_find_anchors returns them)
  * and be exact matches (checked: B2A_ERR_ARG otherwise).  result receives one record (overlap = longest exact-match run of the whole
  * alignment, hw2.cpp:267-278; path = 3); ops (may be NULL: overlap is then -1, as it is when ops_cap is too small) receives the op list, ASCII
- * 'M'/'D'/'I' in traceback order like b2a_fetch_ops, at most ops_cap characters.  Returns the op count or <0.  The context's last batch is replaced. */
+ * 'M'/'D'/'I' in traceback order like b2a_fetch_ops, at most ops_cap characters.  Returns the op count or <0.  The context's last batch is replaced and a sink set with
+ * b2a_set_ops_sink is switched off. */
 int64_t b2a_align_anchored(b2a_ctx* ctx, const b2a_params* prm, const uint8_t* pattern, uint64_t m, const uint8_t* text, uint64_t n,
                            const b2a_anchor* anchors, uint64_t n_anchors, b2a_result* result, char* ops, uint64_t ops_cap);
 
