@@ -254,3 +254,36 @@ def test_find_anchors_chain_properties():
     assert lib.b2a_find_anchors(None, 10, None, 10, 16, 1, None, 0) == -1
     assert lib.b2a_find_anchors(base, 100, base, 100, 0, 1, None, 0) == -1
     assert lib.b2a_align_anchored(None, None, None, 0, None, 0, None, 0, None, None, 0) == -1
+
+
+def test_seq2_and_anchor_properties_hypothesis():
+    """Property tests of the two host-only additions: pack -> unpack is the identity for arbitrary bytes and alphabets; every anchor chain
+    consists of exact matches ascending in both coordinates; forcing a chain through identical sequences covers them on the diagonal."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.binary(min_size=0, max_size=600), st.binary(min_size=4, max_size=4))
+    def roundtrip(data, alphabet):
+        d = np.frombuffer(data, np.uint8)
+        ps = pkg.PackedSeq(d, alphabet=alphabet)
+        assert ps.unpack().tobytes() == data
+        assert ps.n_exc == sum(1 for b in data if b not in alphabet)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.text(alphabet="ACGT", min_size=0, max_size=400), st.text(alphabet="ACGT", min_size=0, max_size=400),
+           st.integers(min_value=4, max_value=12), st.integers(min_value=1, max_value=64))
+    def chain(p, t, k, spacing):
+        p, t = p.encode(), t.encode()
+        a = pkg.find_anchors(p, t, k, spacing)
+        pi = tj = 0
+        for x in a:
+            i, j, ln = int(x["i"]), int(x["j"]), int(x["len"])
+            assert ln == k and p[i:i + ln] == t[j:j + ln] and i >= pi and j >= tj
+            pi, tj = i + ln, j + ln
+
+    roundtrip()
+    chain()
+    rng = random.Random(2)
+    s_ = bytes(rng.choice(b"ACGT") for _ in range(5000))
+    a = pkg.find_anchors(s_, s_, 16, 100)
+    assert len(a) >= 40 and np.array_equal(a["i"], a["j"])
