@@ -136,15 +136,17 @@ class PackedSeq:
         n = data.size
         alloc = pinned_empty if pinned else (lambda k, dt: np.empty(max(k, 1), dtype=dt))
         self.codes = alloc((n + 3) // 4, np.uint8)
-        n_exc = lib.b2a_seq2_pack(data.ctypes.data, n, alpha, None, None, None, 0)
-        if n_exc < 0:
-            raise B2AError("b2a_seq2_pack failed")
-        self.exc_pos = alloc(n_exc, np.uint64)
-        self.exc_byte = alloc(n_exc, np.uint8)
-        got = lib.b2a_seq2_pack(data.ctypes.data, n, alpha, self.codes.ctypes.data, self.exc_pos.ctypes.data,
-                                self.exc_byte.ctypes.data, n_exc)
-        if got != n_exc:
-            raise B2AError("b2a_seq2_pack failed")
+        cap = n // 128 + 4096                                  # usually enough: one pass.  Otherwise the call says how many there are
+        while True:
+            self.exc_pos = alloc(cap, np.uint64)
+            self.exc_byte = alloc(cap, np.uint8)
+            n_exc = lib.b2a_seq2_pack(data.ctypes.data, n, alpha, self.codes.ctypes.data, self.exc_pos.ctypes.data,
+                                      self.exc_byte.ctypes.data, cap)
+            if n_exc < 0:
+                raise B2AError("b2a_seq2_pack failed")
+            if n_exc <= cap:
+                break
+            cap = int(n_exc)
         self.n_bytes, self.n_exc = n, int(n_exc)
         self.c = Seq2(self.codes.ctypes.data, n, alpha, 0, self.exc_pos.ctypes.data, self.exc_byte.ctypes.data, n_exc)
 

@@ -210,43 +210,50 @@ extern "C" int64_t b2a_seq2_pack(const uint8_t* seq, uint64_t n_bytes, const uin
     if ((!seq && n_bytes) || !alphabet) return B2A_ERR_ARG;
     if (exc_cap && (!exc_pos || !exc_byte)) return B2A_ERR_ARG;
     uint8_t lut[256];
-    std::memset(lut, 0xFF, sizeof lut);
+    std::memset(lut, 0x80, sizeof lut);                                  // 0x80 = not in the alphabet
     for (int c = 3; c >= 0; --c) lut[alphabet[c]] = (uint8_t)c;          // a repeated alphabet byte takes its lowest code
-    // slices of whole code bytes, one per thread; pass 1 counts the exceptions, pass 2 writes codes and exceptions at their offsets
+    // ONE pass: slices of whole code bytes, one per thread; a thread writes its codes in place and collects its exceptions in a list of
+    // its own (four bytes at a time, the exception test once per four), the lists are concatenated afterwards.
     const uint64_t quads = (n_bytes + 3) / 4;
     unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
     if (const char* e = std::getenv("B2A_HOST_THREADS")) nt = (unsigned)std::max(1, std::atoi(e));
     nt = (unsigned)std::min<uint64_t>(nt, std::max<uint64_t>(1, quads / 65536));
-    std::vector<uint64_t> cnt(nt + 1, 0);
-    auto slice = [&](unsigned t, uint64_t& b0, uint64_t& b1) {
-        b0 = std::min(n_bytes, quads * t / nt * 4); b1 = std::min(n_bytes, quads * (t + 1) / nt * 4);
-    };
-    auto run = [&](auto&& fn) {
-        std::vector<std::thread> th;
-        for (unsigned t = 1; t < nt; ++t) th.emplace_back(fn, t);
-        fn(0u);
-        for (auto& x : th) x.join();
-    };
-    run([&](unsigned t) {
-        uint64_t b0, b1, c = 0; slice(t, b0, b1);
-        for (uint64_t p = b0; p < b1; ++p) c += lut[seq[p]] == 0xFF;
-        cnt[t + 1] = c;
-    });
-    for (unsigned t = 0; t < nt; ++t) cnt[t + 1] += cnt[t];
-    run([&](unsigned t) {
-        uint64_t b0, b1, e = cnt[t]; slice(t, b0, b1);
-        for (uint64_t p = b0; p < b1; p += 4) {
+    struct Exc { uint64_t pos; uint8_t byte; };
+    std::vector<std::vector<Exc>> found(nt);
+    auto work = [&](unsigned t) {
+        const uint64_t b0 = std::min(n_bytes, quads * t / nt * 4), b1 = std::min(n_bytes, quads * (t + 1) / nt * 4);
+        std::vector<Exc>& ex = found[t];
+        uint64_t p = b0;
+        for (; p + 4 <= b1; p += 4) {
+            uint32_t l0 = lut[seq[p]], l1 = lut[seq[p + 1]], l2 = lut[seq[p + 2]], l3 = lut[seq[p + 3]];
+            if ((l0 | l1 | l2 | l3) & 0x80u) {
+                if (l0 & 0x80u) { ex.push_back(Exc{p, seq[p]}); l0 = 0; }
+                if (l1 & 0x80u) { ex.push_back(Exc{p + 1, seq[p + 1]}); l1 = 0; }
+                if (l2 & 0x80u) { ex.push_back(Exc{p + 2, seq[p + 2]}); l2 = 0; }
+                if (l3 & 0x80u) { ex.push_back(Exc{p + 3, seq[p + 3]}); l3 = 0; }
+            }
+            if (codes) codes[p / 4] = (uint8_t)(l0 | (l1 << 2) | (l2 << 4) | (l3 << 6));
+        }
+        if (p < b1) {                                                    // the buffer's last, partial code byte
             uint32_t byte = 0;
-            const uint64_t lim = std::min<uint64_t>(4, b1 - p);
-            for (uint64_t k = 0; k < lim; ++k) {
+            for (uint64_t k = 0; p + k < b1; ++k) {
                 uint32_t c = lut[seq[p + k]];
-                if (c == 0xFF) { if (e < exc_cap) { exc_pos[e] = p + k; exc_byte[e] = seq[p + k]; } ++e; c = 0; }
+                if (c & 0x80u) { ex.push_back(Exc{p + k, seq[p + k]}); c = 0; }
                 byte |= c << (2 * k);
             }
             if (codes) codes[p / 4] = (uint8_t)byte;
         }
-    });
-    return (int64_t)cnt[nt];
+    };
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0u);
+        for (auto& x : th) x.join();
+    }
+    uint64_t total = 0;
+    for (unsigned t = 0; t < nt; ++t)
+        for (const Exc& e : found[t]) { if (total < exc_cap) { exc_pos[total] = e.pos; exc_byte[total] = e.byte; } ++total; }
+    return (int64_t)total;
 }
 
 extern "C" int b2a_seq2_unpack(const b2a_seq2* s, uint64_t first, uint64_t count, uint8_t* out)
