@@ -1,8 +1,8 @@
-"""Every kernel family once on tiny inputs (for compute-sanitizer --tool memcheck): short16 4-symbol and 8-symbol fills, both tracebacks, wide32
+"""Test helper (lives under tests/ because it checks against the oracle; not collected by pytest): every kernel family once on tiny inputs (for compute-sanitizer --tool memcheck): short16 4-symbol and 8-symbol fills, both tracebacks, wide32
 with stored record and with checkpoint tiles, score-only tile kernel, affine score + traceback, hw4 tie order, multi-run batches."""
 import os, sys, random
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 import oracle_binding as ob
 from __graft_entry__ import load_package
