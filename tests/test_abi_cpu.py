@@ -287,3 +287,41 @@ def test_seq2_and_anchor_properties_hypothesis():
     s_ = bytes(rng.choice(b"ACGT") for _ in range(5000))
     a = pkg.find_anchors(s_, s_, 16, 100)
     assert len(a) >= 40 and np.array_equal(a["i"], a["j"])
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/b2align.h compiles as strict C99 (the boundary is a C ABI: no C++ types, no default arguments) and a C program linked against
+    libb2align.so can call the host-only entry points; the computing ones report the missing GPU instead of falling back."""
+    src = tmp_path / "abi.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <string.h>
+#include "b2align.h"
+int main(void) {
+    const uint8_t acgt[4] = {'A', 'C', 'G', 'T'};
+    const uint8_t seq[] = "ACGTNACGTACGTTTGA";
+    uint8_t codes[8], exc_byte[4], back[17];
+    uint64_t exc_pos[4];
+    int64_t ne = b2a_seq2_pack(seq, 17, acgt, codes, exc_pos, exc_byte, 4);
+    b2a_seq2 s;
+    char cigar[64];
+    b2a_anchor a[4];
+    b2a_result r;
+    memset(&s, 0, sizeof s);
+    s.codes = codes; s.n_bytes = 17; memcpy(s.alphabet, acgt, 4); s.exc_pos = exc_pos; s.exc_byte = exc_byte; s.n_exc = (uint64_t)ne;
+    if (ne != 1 || exc_pos[0] != 4 || exc_byte[0] != 'N') return 1;
+    if (b2a_seq2_unpack(&s, 0, 17, back) != B2A_OK || memcmp(back, seq, 17) != 0) return 2;
+    if (b2a_render_cigar("MMIDM", 5, cigar, sizeof cigar) != 8 || strcmp(cigar, "1M1D1I2M") != 0) return 3;
+    if (b2a_find_anchors(seq, 17, seq, 17, 4, 1, a, 4) < 0) return 4;
+    if (sizeof(b2a_result) != 32 || sizeof(b2a_anchor) != 12 || sizeof r != 32) return 5;
+    if (b2a_device_count() == 0 && b2a_create(0) != NULL) return 6;          /* no GPU: no context, no fallback */
+    printf("ok %d\n", B2A_VERSION);
+    return 0;
+}
+""")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lb2align", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), (out.returncode, out.stdout, out.stderr)
