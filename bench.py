@@ -379,8 +379,7 @@ def bench_c2(args):
             assert len(o) == int(res_host[k]["n_ops"][q]) and int(res_host[k]["end_i"][q]) - int(res_host[k]["start_i"][q]) == nm + int((o == 0x44).sum())
     e2e_all_ops = {"value": total_cells / ops_s / 1e9, "unit": "GCUPS", "ms_per_step": ops_s * 1e3 / args.steps,
                    "h2d_bytes_per_step": st_ops["h2d_bytes"], "d2h_bytes_per_step": st_ops["d2h_bytes"],
-                   "what": "the byte-input e2e with the 2-bit op lists of ALL pairs of both modes copied to pinned host memory as well "
-                           "(b2a_set_ops_sink: per segment, under the kernels of the next segments): everything struct AlignmentResult carries, for every pair"}
+                   "what": "e2e + the op lists of ALL pairs of both modes copied to pinned host memory per segment (b2a_set_ops_sink)"}
     del sinks
 
     # ---- the same end to end over COMPACT host buffers (b2a_seq2: 2-bit codes + exception list, packed once outside the timed region) ----
@@ -403,8 +402,8 @@ def bench_c2(args):
     e2e_seq2 = {"value": total_cells / seq2_s / 1e9, "unit": "GCUPS", "ms_per_step": seq2_s * 1e3 / args.steps,
                 "h2d_bytes_per_step": st2["h2d_bytes"], "d2h_bytes_per_step": st2["d2h_bytes"], "gpu_launches_per_step": st2["launches"],
                 "exceptions": pat2.n_exc + txt2.n_exc, "pack_ms_once": pack_s * 1e3,
-                "what": "b2a_align_batch_multi_seq2: the same pairs as 2-bit codes + exception list in pinned host memory (packed once by "
-                        "b2a_seq2_pack on the host, outside the timed region), expanded to bytes on the device per segment; records identical"}
+                "what": "b2a_align_batch_multi_seq2: 2-bit codes + exception list in pinned host memory (packed once, outside the timed "
+                        "region), expanded on the device per segment; records identical"}
     del pat2, txt2
     eng.close()
 
